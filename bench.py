@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- chunks/sec generated+meshed (BASELINE.json metric) on N B200s of one node.
+
+A step = one pass of the fused generate+mesh hot path over one region of chunk columns per GPU:
+BASELINE config 4, "fused gen+mesh for a 256x256-chunk region" (256x256 columns x cy in [-3,3) =
+393 216 chunks).  With N GPUs every rank takes its own 256x256 slab of a (256*N)x256 region
+(x-slab partition, no collective on the data path) -> weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--columns C]
+
+  value    : kernel-only throughput, outputs resident in HBM (CUDA events on the launching stream,
+             max over ranks).
+  e2e      : same metric through the C ABI's host entry point hb_generate_mesh_region, finished
+             Instance3d buffers landed in pinned host memory (device->host copies in the timed region).
+  roofline : the dominant kernel (k_mesh_region<EMIT>: 100 B per emitted quad) vs measured HBM peak.
+  cpu_baseline / --impl reference : the CPU restatement of the reference path (oracle/, "port" --
+             the Rust reference cannot be built here) on a bounded sample of the same region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+SEED = 0
+CY0, NCY = -3, 6
+METRIC = "chunks/sec generated+meshed"
+UNIT = "chunks/s"
+
+
+def region_for_rank(columns: int, rank: int, world: int):
+    # global region: x in [-columns*world/2, +columns*world/2), z in [-columns/2, columns/2)
+    cx0 = -(columns * world) // 2 + rank * columns
+    return (cx0, -(columns // 2), columns, columns, CY0, NCY)
+
+
+def cpu_sample_region(columns: int):
+    s = min(32, columns)
+    return (-(columns // 2), -(columns // 2), s, s, CY0, NCY)
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu(sample, threads: int, reps: int):
+    """The reference's CPU path as restated in oracle/ (literal set() + cull_shared_faces + generate_mesh)."""
+    import oracle as O
+    w = O.world(SEED)
+    n = sample[2] * sample[3] * sample[5]
+    times = []
+    quads = 0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = O.region_pipeline(w, sample, literal=True, threads=threads, want_instances=False)
+        times.append(time.perf_counter() - t0)
+        quads = r["total"]
+    return n, quads, times
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.t = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--columns", type=int, default=256, help="region is columns x columns chunk columns per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (rank 0, N=1 only anyway)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cols = args.columns
+    workload = (f"BASELINE config 4: fused gen+mesh, {cols}x{cols} chunk columns x cy[{CY0},{CY0 + NCY}) = "
+                f"{cols * cols * NCY} chunks per GPU, seed {SEED}; region border = absent chunks")
+    config = {"workload": workload, "columns_per_gpu": cols * cols, "chunks_per_gpu": cols * cols * NCY,
+              "parallelism": f"x-slab partition over {world} GPU(s), no data-path collective",
+              "l2": "no explicit flush: each step writes ~17 GB of instances and re-reads 268 MB of height tiles "
+                    "(both >> 126 MB L2)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = host_threads()
+        sample = cpu_sample_region(cols)
+        for _ in range(min(warmup, 1)):
+            run_cpu(sample, threads, 1)
+        n, quads, times = run_cpu(sample, threads, steps)
+        total_t = sum(times)
+        val = n * steps / total_t
+        sample_txt = (f"{sample[2]}x{sample[3]} columns x {NCY} = {n} chunks per step (sub-region of the workload), "
+                      f"literal CubeMesh::set + cull_shared_faces + generate_mesh, {quads} quads")
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": warmup, "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "CPU restatement of the reference path (oracle/hb_oracle.c); the Rust reference cannot be "
+                        "built in this image (no cargo/rustc, nightly-only, un-vendored deps)"}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import numpy as np
+    import torch
+
+    import herbolution_b200 as hb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libherbgpu has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = hb.Context(device=local_rank, seed=SEED)
+    reg = hb.Region(*region_for_rank(cols, rank, world))
+    plan = ctx.region_plan(reg)  # sizes the instance buffer with one synchronous count pass
+    # a dedicated non-default stream: kernels are launched on it and the CUDA events are recorded on it
+    tstream = torch.cuda.Stream(device=local_rank)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    ALL = hb.STAGE_ALL_MESH
+    launches_per_step = plan.launches(ALL)
+
+    for _ in range(max(warmup, 3)):
+        plan.enqueue(ALL, stream)
+    res = plan.result(stream)
+    n_chunks, quads, span = res["n_chunks"], res["quads"], res["span"]
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(tstream)
+    for _ in range(steps):
+        plan.enqueue(ALL, stream)
+    ev1.record(tstream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    total_chunks = sum_over_ranks(float(n_chunks))
+    value = total_chunks * steps / (ms_total * 1e-3)
+
+    # per-kernel durations (same stream, CUDA events), for the roofline of the dominant kernel
+    stage_names = [("heights", hb.STAGE_HEIGHTS), ("count", hb.STAGE_COUNT), ("scan", hb.STAGE_SCAN), ("emit", hb.STAGE_EMIT)]
+    reps = 5
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)] for _ in range(reps)]
+    for r in range(reps):
+        evs[r][0].record(tstream)
+        for i, (_, st) in enumerate(stage_names):
+            plan.enqueue(st, stream)
+            evs[r][i + 1].record(tstream)
+    torch.cuda.synchronize()
+    stage_ms = {nm: statistics.mean(evs[r][i].elapsed_time(evs[r][i + 1]) for r in range(reps))
+                for i, (nm, _) in enumerate(stage_names)}
+    peak, peak_src = measured_peaks()
+    emit_bytes = 100.0 * quads  # fused path writes 100 B per emitted quad, no reads beyond coords
+    emit_gbs = emit_bytes / (stage_ms["emit"] * 1e-3) / 1e9
+    flops_per_column = 333824.0  # 1024 samples x 326 flops
+    ncols_noise = reg.ncx * reg.ncz
+    noise_tflops = flops_per_column * ncols_noise / (stage_ms["heights"] * 1e-3) / 1e12
+    roofline = {"kernel": "k_mesh_region<EMIT=true>", "bound": "hbm", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
+                "frac": emit_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": emit_bytes, "avg_launch_ms": stage_ms["emit"],
+                "share_of_step": stage_ms["emit"] / sum(stage_ms.values())}
+    kernels = {"stage_ms": stage_ms,
+               "noise": {"kernel": "k_heights", "bound": "fp32", "achieved_tflops": noise_tflops, "peak_tflops": 74.4,
+                         "frac": noise_tflops / 74.4, "flops_per_column": flops_per_column}}
+
+    # ---- end to end through the host entry point: instances land in pinned host memory
+    e2e = None
+    stats = {"span": 0, "chunks": 0}
+
+    def sink(first, off, cnt, inst, ids):
+        stats["span"] += len(inst)
+        stats["chunks"] += len(cnt)
+
+    ctx.generate_mesh_region(reg, sink=sink)  # warm-up: pinned staging is allocated here
+    e2e_steps = max(1, min(args.e2e_steps, steps))
+    stats["span"] = stats["chunks"] = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.generate_mesh_region(reg, sink=sink)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    d2h = (stats["span"] * 100 + stats["chunks"] * 12) / e2e_steps
+    e2e = {"value": total_chunks * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 24,
+           "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
+           "api": "hb_generate_mesh_region (C ABI, host sink, pinned double-buffered D2H)",
+           "note": "input is the 24-byte region descriptor; output is every Instance3d (100 B/quad) + offsets/counts"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = host_threads()
+        sample = cpu_sample_region(cols)
+        n, q, times = run_cpu(sample, threads, 2)
+        best = min(times)
+        cpu = {"value": n / best, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sample[2]}x{sample[3]} columns x {NCY} = {n} chunks (sub-region of the workload), oracle "
+                         f"literal path, best of 2 passes, {best:.2f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+                "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches_per_step * steps, "roofline": roofline, "cpu_baseline": cpu,
+                "kernels": kernels, "quads_per_step_per_gpu": quads, "instance_bytes_per_step_per_gpu": span * 100}
+        print(json.dumps(line))
+    plan.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,202 @@
+"""Context: one hb_ctx (one GPU) with numpy-typed wrappers over the C ABI.
+
+These are 1:1 wrappers (same argument meaning, same error behaviour as include/herbgpu.h); the
+reference-shaped interface (ChunkGenerator, GenerationParams, generate_mesh) lives in
+generator.py / mesher.py on top of this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import (CHUNK_AREA, CHUNK_PT_DTYPE, CHUNK_VOLUME, CUBE_DTYPE, INSTANCE_DTYPE, MAX_COLORS, HerbGpuError,
+                   Region, check, ptr)
+
+
+def as_chunk_pts(positions) -> np.ndarray:
+    """Accepts a CHUNK_PT_DTYPE array or an (n, 3) integer array / list of (x, y, z)."""
+    a = np.asarray(positions)
+    if a.dtype == CHUNK_PT_DTYPE:
+        return np.ascontiguousarray(a)
+    a = np.asarray(positions, dtype=np.int64).reshape(-1, 3)
+    if a.size and (np.abs(a) > 2**31 - 1).any():
+        raise HerbGpuError(_lib.HB_ERR_RANGE, "chunk coordinate does not fit i32")
+    out = np.empty(a.shape[0], dtype=CHUNK_PT_DTYPE)
+    out["x"], out["y"], out["z"] = a[:, 0], a[:, 1], a[:, 2]
+    return out
+
+
+class RegionPlan:
+    """Device-resident fused gen+mesh pipeline for a slab of a region (hb_region_plan)."""
+
+    def __init__(self, ctx: "Context", region: Region, ix_begin: int = 0, ix_end: Optional[int] = None,
+                 quad_capacity: int = 0, want_ids: bool = False):
+        self._lib = _lib.load()
+        self.ctx = ctx
+        self.region = region
+        self._h = C.c_void_p()
+        ix_end = region.ncx if ix_end is None else ix_end
+        check(self._lib.hb_region_plan_create(ctx._h, C.byref(region), ix_begin, ix_end, quad_capacity, int(want_ids),
+                                              C.byref(self._h)))
+
+    def enqueue(self, stages: int = _lib.STAGE_ALL_MESH, stream: int = 0) -> None:
+        check(self._lib.hb_region_plan_enqueue(self._h, stages, C.c_void_p(stream or None)))
+
+    def launches(self, stages: int = _lib.STAGE_ALL_MESH) -> int:
+        return self._lib.hb_region_plan_launches(self._h, stages)
+
+    def result(self, stream: int = 0) -> dict:
+        """Synchronises the stream; returns totals and raw device pointers."""
+        n, q, span = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        p = [C.c_void_p() for _ in range(5)]
+        check(self._lib.hb_region_plan_result(self._h, C.c_void_p(stream or None), C.byref(n), C.byref(q), C.byref(span),
+                                              *[C.byref(x) for x in p]))
+        return {"n_chunks": n.value, "quads": q.value, "span": span.value, "d_instances": p[0].value,
+                "d_offsets": p[1].value, "d_counts": p[2].value, "d_ids": p[3].value, "d_heights": p[4].value}
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.hb_region_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device: int = 0, seed: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        check(self._lib.hb_create(device, C.byref(self._h)))
+        self.device = device
+        self.set_world(seed)
+
+    # -- parameters ------------------------------------------------------------------------
+    def set_world(self, seed: int, freq: float = 0.001, octaves: int = 6, lacunarity: float = 2.0,
+                  gain: float = 0.6) -> None:
+        """Defaults = server/src/generator/mod.rs:103-108."""
+        check(self._lib.hb_set_world(self._h, seed, freq, octaves, lacunarity, gain))
+        self.seed = seed
+
+    def set_materials(self, colors: list) -> None:
+        """colors[m] = list of rgba tuples of material id m+1 (server/src/chunk/material.rs:27-61)."""
+        n = len(colors)
+        ncol = np.array([len(c) for c in colors], dtype=np.int32)
+        rgba = np.zeros((n, MAX_COLORS, 4), dtype=np.float32)
+        for i, cs in enumerate(colors):
+            if len(cs) > MAX_COLORS:
+                raise HerbGpuError(_lib.HB_ERR_INVALID, f"material {i + 1}: more than {MAX_COLORS} colours")
+            for j, c in enumerate(cs):
+                rgba[i, j] = c
+        check(self._lib.hb_set_materials(self._h, n, ptr(ncol), ptr(rgba)))
+
+    # -- generation ------------------------------------------------------------------------
+    def noise_tiles(self, cols_xz, want_heights: bool = False):
+        cols = np.ascontiguousarray(np.asarray(cols_xz, dtype=np.int32).reshape(-1, 2))
+        n = cols.shape[0]
+        noise = np.empty((n, CHUNK_AREA), dtype=np.float32)
+        heights = np.empty((n, CHUNK_AREA), dtype=np.int32) if want_heights else None
+        check(self._lib.hb_noise_tiles(self._h, ptr(cols), n, ptr(noise), ptr(heights)))
+        return (noise, heights) if want_heights else noise
+
+    def noise_fbm3d(self, start, extent, freq) -> np.ndarray:
+        nx, ny, nz = (int(v) for v in extent)
+        f = np.asarray(freq, dtype=np.float32).reshape(3)
+        out = np.empty(max(nx, 0) * max(ny, 0) * max(nz, 0), dtype=np.float32)
+        check(self._lib.hb_noise_fbm3d(self._h, float(start[0]), float(start[1]), float(start[2]), nx, ny, nz, ptr(f),
+                                       ptr(out)))
+        return out.reshape(nz, ny, nx)
+
+    def generate(self, positions, want_cubes: bool = False, want_noise: bool = False) -> dict:
+        pts = as_chunk_pts(positions)
+        n = pts.shape[0]
+        ids = np.empty((n, CHUNK_VOLUME), dtype=np.uint16)
+        cubes = np.empty((n, CHUNK_VOLUME), dtype=CUBE_DTYPE) if want_cubes else None
+        noise = np.empty((n, CHUNK_AREA), dtype=np.float32) if want_noise else None
+        check(self._lib.hb_generate(self._h, ptr(pts), n, ptr(ids), ptr(cubes), ptr(noise)))
+        return {"ids": ids, "cubes": cubes, "noise": noise}
+
+    # -- meshing ---------------------------------------------------------------------------
+    def build_neighbor_index(self, positions) -> np.ndarray:
+        pts = as_chunk_pts(positions)
+        out = np.empty((pts.shape[0], 27), dtype=np.int32)
+        check(self._lib.hb_build_neighbor_index(ptr(pts), pts.shape[0], ptr(out)))
+        return out
+
+    def mesh(self, positions, ids: np.ndarray, neighbor_index: Optional[np.ndarray] = None) -> dict:
+        """Returns {"instances": INSTANCE_DTYPE[span], "offsets": u64[n], "counts": u32[n]}."""
+        pts = as_chunk_pts(positions)
+        n = pts.shape[0]
+        ids = np.ascontiguousarray(ids, dtype=np.uint16).reshape(n, CHUNK_VOLUME)
+        nbr = self.build_neighbor_index(pts) if neighbor_index is None else \
+            np.ascontiguousarray(neighbor_index, dtype=np.int32).reshape(n, 27)
+        offsets = np.zeros(n, dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.uint32)
+        total = C.c_uint64(0)
+        rc = self._lib.hb_mesh(self._h, ptr(pts), n, ptr(ids), ptr(nbr), None, 0, ptr(offsets), ptr(counts),
+                               C.byref(total))
+        if rc not in (_lib.HB_OK, _lib.HB_ERR_CAPACITY):
+            check(rc)
+        inst = np.zeros(total.value, dtype=INSTANCE_DTYPE)
+        if total.value:
+            check(self._lib.hb_mesh(self._h, ptr(pts), n, ptr(ids), ptr(nbr), ptr(inst), total.value, ptr(offsets),
+                                    ptr(counts), C.byref(total)))
+        return {"instances": inst, "offsets": offsets, "counts": counts}
+
+    # -- fused region ----------------------------------------------------------------------
+    def generate_mesh_region(self, region: Region, want_ids: bool = False,
+                             sink: Optional[Callable[..., None]] = None) -> dict:
+        """sink(first_chunk, offsets u64[n], counts u32[n], instances INSTANCE_DTYPE[span], ids or None);
+        the arrays are views of pinned library buffers, valid only during the call."""
+
+        def _cb(_user, first, n, p_off, p_cnt, p_inst, span, p_ids):
+            if sink is None:
+                return
+            off = np.frombuffer((C.c_uint64 * n).from_address(p_off), dtype=np.uint64) if n else np.zeros(0, np.uint64)
+            cnt = np.frombuffer((C.c_uint32 * n).from_address(p_cnt), dtype=np.uint32) if n else np.zeros(0, np.uint32)
+            inst = np.frombuffer((C.c_char * (span * 100)).from_address(p_inst), dtype=INSTANCE_DTYPE) if span else \
+                np.zeros(0, INSTANCE_DTYPE)
+            ids = None
+            if p_ids:
+                ids = np.frombuffer((C.c_uint16 * (n * CHUNK_VOLUME)).from_address(p_ids), dtype=np.uint16)
+                ids = ids.reshape(n, CHUNK_VOLUME)
+            sink(first, off, cnt, inst, ids)
+
+        cb = _lib.REGION_SINK(_cb)
+        tc, tq = C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.hb_generate_mesh_region(self._h, C.byref(region), int(want_ids), cb, None, C.byref(tc),
+                                                C.byref(tq)))
+        return {"chunks": tc.value, "quads": tq.value}
+
+    def download(self, dev_ptr: int, dtype, count: int) -> np.ndarray:
+        """Blocking device->host copy of `count` items at a raw device pointer (plan results)."""
+        out = np.empty(count, dtype=dtype)
+        if count:
+            check(self._lib.hb_dev_download(self._h, ptr(out), C.c_void_p(dev_ptr), out.nbytes))
+        return out
+
+    def region_plan(self, region: Region, **kw) -> RegionPlan:
+        return RegionPlan(self, region, **kw)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.hb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,771 @@
+// api.cu -- the C ABI of libherbgpu.so (include/herbgpu.h): context, host-pointer entry points,
+// device-resident region plans.  Everything here is plumbing around the kernels in gen.cu/mesh.cu;
+// there is deliberately no CPU implementation of any stage.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace hb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define HB_CUDA(expr)                                                                                 \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(HB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// Growable device / pinned-host scratch buffer.
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+        p = nullptr; cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Instance3d model_0..2 per face: CubeFace::rotation (lib/src/spatial/face.rs:60-69) ->
+// Quat::from_euler (lib/src/rotation.rs:77-88) -> to_axes (:109-116) -> * Mat3::from(Vec3::ONE)
+// (lib/src/matrix/mat3.rs:63-90), columns extended with 0.0 (client/src/video/world/vertex.rs:53-62).
+// Evaluated on the host with libm sinf/cosf, which is what f32::sin_cos resolves to on linux.
+// volatile keeps the compiler from contracting or pre-folding the f32 expression tree.
+void face_matrix(int face, float out12[12]) {
+    const float FRAC_PI_2 = 1.57079632679489661923132169163975144f;
+    const float PI = 3.14159265358979323846264338327950288f;
+    float yaw = 0.0f, pitch = 0.0f, roll = 0.0f;
+    switch (face) {
+        case 0: pitch = FRAC_PI_2; break;   // East
+        case 1: pitch = -FRAC_PI_2; break;  // West
+        case 2: yaw = -FRAC_PI_2; break;    // Up
+        case 3: yaw = FRAC_PI_2; break;     // Down
+        case 4: break;                      // North
+        default: pitch = PI; break;         // South
+    }
+    volatile float sx = sinf(yaw / 2.0f), cx = cosf(yaw / 2.0f);
+    volatile float sy = sinf(pitch / 2.0f), cy = cosf(pitch / 2.0f);
+    volatile float sz = sinf(roll / 2.0f), cz = cosf(roll / 2.0f);
+    auto mul = [](float a, float b) { volatile float r = a * b; return (float)r; };
+    auto add = [](float a, float b) { volatile float r = a + b; return (float)r; };
+    auto sub = [](float a, float b) { volatile float r = a - b; return (float)r; };
+    const float x = sub(mul(mul(sx, cy), cz), mul(mul(cx, sy), sz));
+    const float y = add(mul(mul(cx, sy), cz), mul(mul(sx, cy), sz));
+    const float z = sub(mul(mul(cx, cy), sz), mul(mul(sx, sy), cz));
+    const float w = add(mul(mul(cx, cy), cz), mul(mul(sx, sy), sz));
+    const float ax[3][3] = {
+        {sub(1.f, mul(2.f, add(mul(y, y), mul(z, z)))), mul(2.f, add(mul(x, y), mul(z, w))), mul(2.f, sub(mul(x, z), mul(y, w)))},
+        {mul(2.f, sub(mul(x, y), mul(z, w))), sub(1.f, mul(2.f, add(mul(x, x), mul(z, z)))), mul(2.f, add(mul(y, z), mul(x, w)))},
+        {mul(2.f, add(mul(x, z), mul(y, w))), mul(2.f, sub(mul(y, z), mul(x, w))), sub(1.f, mul(2.f, add(mul(x, x), mul(y, y))))},
+    };
+    static const float S[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r)
+            out12[c * 4 + r] = add(add(mul(ax[0][r], S[c][0]), mul(ax[1][r], S[c][1])), mul(ax[2][r], S[c][2]));
+    out12[3] = out12[7] = out12[11] = 0.0f;
+}
+
+// client/src/world/chunk.rs:271-275: `Vec4<u8>.cast() / 3.0` resolves to f64, then cast::<f32>(),
+// `-a + 1.0`, max_each(0.15)
+float ao_value(int k) {
+    volatile double amount = (double)k / 3.0;
+    volatile float a = (float)amount;
+    volatile float factor = -a + 1.0f;
+    return factor > 0.15f ? (float)factor : 0.15f;
+}
+
+void default_materials(MaterialsDev* m) {
+    // Material::stone/dirt/grass, server/src/chunk/material.rs:27-61
+    static const float c[3][3][4] = {
+        {{0.5f, 0.5f, 0.5f, 1.0f}, {0.6f, 0.6f, 0.6f, 1.0f}, {0.7f, 0.7f, 0.7f, 1.0f}},
+        {{0.4f, 0.3f, 0.2f, 1.0f}, {0.5f, 0.4f, 0.3f, 1.0f}, {0.6f, 0.5f, 0.4f, 1.0f}},
+        {{0.1f, 0.8f, 0.1f, 1.0f}, {0.2f, 0.9f, 0.2f, 1.0f}, {0.3f, 1.0f, 0.3f, 1.0f}},
+    };
+    memset(m, 0, sizeof(*m));
+    m->n_materials = 3;
+    for (int i = 0; i < 3; ++i) {
+        m->n_colors[i] = 3;
+        memcpy(m->rgba[i], c[i], sizeof(c[i]));
+    }
+}
+
+struct KeyXZ {
+    int32_t x, z;
+    bool operator==(const KeyXZ& o) const { return x == o.x && z == o.z; }
+};
+struct KeyXZHash {
+    size_t operator()(const KeyXZ& k) const {
+        return (size_t)(((uint64_t)(uint32_t)k.x << 32) | (uint32_t)k.z) * 0x9E3779B97F4A7C15ULL >> 7;
+    }
+};
+struct KeyXYZ {
+    int32_t x, y, z;
+    bool operator==(const KeyXYZ& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct KeyXYZHash {
+    size_t operator()(const KeyXYZ& k) const {
+        uint64_t h = (uint64_t)(uint32_t)k.x * 0x9E3779B97F4A7C15ULL;
+        h ^= ((uint64_t)(uint32_t)k.y + 0x7F4A7C15ULL) * 0xC2B2AE3D27D4EB4FULL;
+        h = (h << 31) | (h >> 33);
+        h ^= (uint64_t)(uint32_t)k.z * 0x165667B19E3779F9ULL;
+        return (size_t)(h ^ (h >> 29));
+    }
+};
+
+bool coord_ok(int32_t c) { return c >= -HB_MAX_CHUNK_COORD && c <= HB_MAX_CHUNK_COORD; }
+
+}  // namespace
+
+struct hb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;  // compute
+    cudaStream_t copy = nullptr;    // D2H of finished slabs
+    std::mutex mu;
+    WorldDev world{};
+    int64_t seed = 0;
+    MeshTables tables{};
+    MaterialsDev mats{};
+    MaterialsDev* d_mats = nullptr;
+    // scratch for the host-pointer entry points
+    Buf d_pts, d_cols, d_colidx, d_heights, d_noise, d_ids, d_cubes, d_nbr, d_bitmaps, d_summary, d_counts,
+        d_offsets, d_scan, d_total, d_out;
+    Buf h_total;
+    // region streaming
+    Buf h_inst[2], h_off[2], h_cnt[2], h_ids[2];
+    hb_ctx() {
+        h_total.pinned = true;
+        for (int i = 0; i < 2; ++i) h_inst[i].pinned = h_off[i].pinned = h_cnt[i].pinned = h_ids[i].pinned = true;
+    }
+};
+
+struct hb_region_plan {
+    hb_ctx* ctx = nullptr;
+    hb_region region{};
+    RegionDev dev{};
+    int want_ids = 0;
+    size_t max_chunks = 0, max_hcols = 0;
+    uint64_t capacity = 0;
+    Buf d_heights, d_counts, d_offsets, d_scan, d_total, d_out, d_ids;
+    Buf h_total;
+    hb_region_plan() { h_total.pinned = true; }
+    size_t n_chunks() const { return (size_t)(dev.ix_end - dev.ix_begin) * dev.ncz * dev.ncy; }
+};
+
+namespace {
+
+void plan_target(hb_region_plan* p, int32_t ix_begin, int32_t ix_end) {
+    const hb_region& r = p->region;
+    RegionDev d;
+    d.cx0 = r.cx0; d.cz0 = r.cz0; d.ncx = r.ncx; d.ncz = r.ncz; d.cy0 = r.cy0; d.ncy = r.ncy;
+    d.ix_begin = ix_begin; d.ix_end = ix_end;
+    d.hx_begin = std::max(0, ix_begin - 1);
+    d.hx_end = std::min(r.ncx, ix_end + 1);
+    p->dev = d;
+}
+
+int region_check(const hb_region* r) {
+    if (!r) return fail(HB_ERR_INVALID, "region is null");
+    if (r->ncx <= 0 || r->ncz <= 0 || r->ncy <= 0) return fail(HB_ERR_INVALID, "region extents must be positive");
+    const int64_t x1 = (int64_t)r->cx0 + r->ncx - 1, z1 = (int64_t)r->cz0 + r->ncz - 1, y1 = (int64_t)r->cy0 + r->ncy - 1;
+    if (!coord_ok(r->cx0) || !coord_ok(r->cz0) || !coord_ok(r->cy0) || x1 > HB_MAX_CHUNK_COORD ||
+        z1 > HB_MAX_CHUNK_COORD || y1 > HB_MAX_CHUNK_COORD)
+        return fail(HB_ERR_RANGE, "region exceeds +-%d chunks", HB_MAX_CHUNK_COORD);
+    return HB_OK;
+}
+
+int plan_alloc(hb_region_plan* p, int32_t max_width) {
+    const hb_region& r = p->region;
+    p->max_chunks = (size_t)max_width * r.ncz * r.ncy;
+    p->max_hcols = (size_t)std::min(r.ncx, max_width + 2) * r.ncz;
+    HB_CUDA(p->d_heights.reserve(p->max_hcols * HB_CHUNK_AREA * sizeof(int32_t)));
+    HB_CUDA(p->d_counts.reserve(p->max_chunks * sizeof(uint32_t)));
+    HB_CUDA(p->d_offsets.reserve(p->max_chunks * sizeof(uint64_t)));
+    HB_CUDA(p->d_scan.reserve(scan_workspace_bytes(p->max_chunks)));
+    HB_CUDA(p->d_total.reserve(4 * sizeof(uint64_t)));
+    HB_CUDA(p->h_total.reserve(4 * sizeof(uint64_t)));
+    if (p->want_ids) HB_CUDA(p->d_ids.reserve(p->max_chunks * HB_CHUNK_VOLUME * sizeof(uint16_t)));
+    return HB_OK;
+}
+
+int plan_enqueue(hb_region_plan* p, int stages, cudaStream_t s) {
+    hb_ctx* c = p->ctx;
+    if (stages & HB_STAGE_HEIGHTS) HB_CUDA(launch_heights_region(s, c->world, p->dev, p->d_heights.as<int32_t>()));
+    if (stages & HB_STAGE_COUNT) {
+        HB_CUDA(cudaMemsetAsync(p->d_total.p, 0, 4 * sizeof(uint64_t), s));
+        HB_CUDA(launch_mesh_region(s, false, c->tables, c->d_mats, p->dev, p->d_heights.as<int32_t>(),
+                                   p->d_counts.as<uint32_t>(), nullptr, nullptr, 0, p->d_total.as<uint64_t>()));
+    }
+    if (stages & HB_STAGE_SCAN)
+        HB_CUDA(launch_scan(s, p->d_counts.as<uint32_t>(), p->n_chunks(), p->d_offsets.as<uint64_t>(), p->d_scan.p,
+                            p->d_total.as<uint64_t>()));
+    if (stages & HB_STAGE_EMIT) {
+        if (!p->d_out.p && p->capacity) return fail(HB_ERR_INVALID, "plan has no instance buffer");
+        HB_CUDA(launch_mesh_region(s, true, c->tables, c->d_mats, p->dev, p->d_heights.as<int32_t>(),
+                                   p->d_counts.as<uint32_t>(), p->d_offsets.as<uint64_t>(),
+                                   p->d_out.as<hb_instance3d>(), p->capacity, p->d_total.as<uint64_t>()));
+    }
+    if (stages & HB_STAGE_FILL) {
+        if (!p->want_ids) return fail(HB_ERR_INVALID, "plan was created without want_ids");
+        HB_CUDA(launch_fill_region(s, p->dev, p->d_heights.as<int32_t>(), p->d_ids.as<uint16_t>()));
+    }
+    return HB_OK;
+}
+
+int plan_totals(hb_region_plan* p, cudaStream_t s, uint64_t tot[4]) {
+    HB_CUDA(cudaMemcpyAsync(p->h_total.p, p->d_total.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    memcpy(tot, p->h_total.p, 4 * sizeof(uint64_t));
+    return HB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hb_last_error(void) { return g_err; }
+const char* hb_version(void) { return "herbgpu 0.1 (sm_100a)"; }
+
+int hb_create(int device, hb_ctx** out) {
+    if (!out) return fail(HB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(HB_ERR_CUDA, "no CUDA device available (%s); libherbgpu has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(HB_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    HB_CUDA(cudaSetDevice(device));
+    hb_ctx* c = new (std::nothrow) hb_ctx();
+    if (!c) return fail(HB_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    HB_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    c->seed = 0;
+    c->world = WorldDev{0, 0.001f, 6, 2.0f, 0.6f};
+    for (int f = 0; f < 6; ++f) face_matrix(f, c->tables.face_mat[f]);
+    for (int k = 0; k < 4; ++k) c->tables.ao_lut[k] = ao_value(k);
+    default_materials(&c->mats);
+    HB_CUDA(cudaMalloc(&c->d_mats, sizeof(MaterialsDev)));
+    HB_CUDA(cudaMemcpy(c->d_mats, &c->mats, sizeof(MaterialsDev), cudaMemcpyHostToDevice));
+    *out = c;
+    return HB_OK;
+}
+
+void hb_destroy(hb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    Buf* bufs[] = {&c->d_pts, &c->d_cols, &c->d_colidx, &c->d_heights, &c->d_noise, &c->d_ids, &c->d_cubes, &c->d_nbr,
+                   &c->d_bitmaps, &c->d_summary, &c->d_counts, &c->d_offsets, &c->d_scan, &c->d_total, &c->d_out,
+                   &c->h_total, &c->h_inst[0], &c->h_inst[1], &c->h_off[0], &c->h_off[1], &c->h_cnt[0], &c->h_cnt[1],
+                   &c->h_ids[0], &c->h_ids[1]};
+    for (Buf* b : bufs) b->release();
+    if (c->d_mats) cudaFree(c->d_mats);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy) cudaStreamDestroy(c->copy);
+    delete c;
+}
+
+int hb_set_world(hb_ctx* c, int64_t seed, float freq, int32_t octaves, float lacunarity, float gain) {
+    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    if (octaves < 1 || octaves > 255) return fail(HB_ERR_INVALID, "octaves must be in 1..255 (u8 in the reference)");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->seed = seed;
+    c->world = WorldDev{(int32_t)seed, freq, octaves, lacunarity, gain};
+    return HB_OK;
+}
+
+int hb_set_materials(hb_ctx* c, int32_t n_materials, const int32_t* n_colors, const float* rgba) {
+    if (!c || !n_colors || !rgba) return fail(HB_ERR_INVALID, "null argument");
+    if (n_materials < 1 || n_materials > HB_MAX_MATERIALS)
+        return fail(HB_ERR_INVALID, "n_materials must be in 1..%d", HB_MAX_MATERIALS);
+    std::lock_guard<std::mutex> lk(c->mu);
+    HB_CUDA(cudaSetDevice(c->device));
+    MaterialsDev m;
+    memset(&m, 0, sizeof(m));
+    m.n_materials = n_materials;
+    for (int i = 0; i < n_materials; ++i) {
+        if (n_colors[i] < 1 || n_colors[i] > HB_MAX_COLORS)
+            return fail(HB_ERR_INVALID, "material %d: n_colors must be in 1..%d", i + 1, HB_MAX_COLORS);
+        m.n_colors[i] = n_colors[i];
+        memcpy(m.rgba[i], rgba + (size_t)i * HB_MAX_COLORS * 4, sizeof(float) * HB_MAX_COLORS * 4);
+    }
+    c->mats = m;
+    HB_CUDA(cudaMemcpyAsync(c->d_mats, &c->mats, sizeof(MaterialsDev), cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
+}
+
+int hb_host_alloc(hb_ctx* c, size_t bytes, void** out) {
+    if (!c || !out) return fail(HB_ERR_INVALID, "null argument");
+    HB_CUDA(cudaSetDevice(c->device));
+    HB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return HB_OK;
+}
+
+int hb_host_free(hb_ctx* c, void* p) {
+    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    if (p) HB_CUDA(cudaFreeHost(p));
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generation
+// ------------------------------------------------------------------------------------------------
+
+int hb_noise_tiles(hb_ctx* c, const int32_t* cols_xz, size_t n, float* out_noise, int32_t* out_heights) {
+    if (!c || (n && !cols_xz)) return fail(HB_ERR_INVALID, "null argument");
+    if (n == 0) return HB_OK;
+    for (size_t i = 0; i < 2 * n; ++i)
+        if (!coord_ok(cols_xz[i])) return fail(HB_ERR_RANGE, "column %zu outside +-%d", i / 2, HB_MAX_CHUNK_COORD);
+    std::lock_guard<std::mutex> lk(c->mu);
+    HB_CUDA(cudaSetDevice(c->device));
+    const size_t batch = 16384;
+    for (size_t b0 = 0; b0 < n; b0 += batch) {
+        const size_t nb = std::min(batch, n - b0);
+        HB_CUDA(c->d_cols.reserve(nb * 2 * sizeof(int32_t)));
+        HB_CUDA(c->d_heights.reserve(nb * HB_CHUNK_AREA * sizeof(int32_t)));
+        HB_CUDA(c->d_noise.reserve(nb * HB_CHUNK_AREA * sizeof(float)));
+        HB_CUDA(cudaMemcpyAsync(c->d_cols.p, cols_xz + 2 * b0, nb * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        HB_CUDA(launch_heights(c->stream, c->world, c->d_cols.as<int32_t>(), nb, c->d_heights.as<int32_t>(),
+                               out_noise ? c->d_noise.as<float>() : nullptr));
+        if (out_noise)
+            HB_CUDA(cudaMemcpyAsync(out_noise + b0 * HB_CHUNK_AREA, c->d_noise.p, nb * HB_CHUNK_AREA * sizeof(float),
+                                    cudaMemcpyDeviceToHost, c->stream));
+        if (out_heights)
+            HB_CUDA(cudaMemcpyAsync(out_heights + b0 * HB_CHUNK_AREA, c->d_heights.p, nb * HB_CHUNK_AREA * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, c->stream));
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return HB_OK;
+}
+
+int hb_noise_fbm3d(hb_ctx* c, float sx, float sy, float sz, int32_t nx, int32_t ny, int32_t nz, const float* freq3,
+                   float* out) {
+    if (!c || !freq3 || !out) return fail(HB_ERR_INVALID, "null argument");
+    if (nx <= 0 || ny <= 0 || nz <= 0) return fail(HB_ERR_INVALID, "extents must be positive");
+    // the reference advances coordinates by repeated f32 additions (noise/f32.rs:152-190); they are exact,
+    // and equal to start + index, only for integer-valued starts below 2^24
+    const float lim = 16777216.0f;
+    const float s[3] = {sx, sy, sz};
+    const int ext[3] = {nx, ny, nz};
+    for (int a = 0; a < 3; ++a)
+        if (!(s[a] == floorf(s[a])) || fabsf(s[a]) + (float)ext[a] > lim)
+            return fail(HB_ERR_RANGE, "3-D tile start must be integer-valued with |start|+extent <= 2^24");
+    std::lock_guard<std::mutex> lk(c->mu);
+    HB_CUDA(cudaSetDevice(c->device));
+    const size_t total = (size_t)nx * ny * nz;
+    HB_CUDA(c->d_noise.reserve(total * sizeof(float)));
+    HB_CUDA(launch_noise3d(c->stream, c->world, sx, sy, sz, nx, ny, nz, freq3[0], freq3[1], freq3[2], c->d_noise.as<float>()));
+    HB_CUDA(cudaMemcpyAsync(out, c->d_noise.p, total * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
+}
+
+int hb_generate(hb_ctx* c, const hb_chunk_pt* pts, size_t n, uint16_t* out_ids, hb_palette_cube* out_cubes,
+                float* out_noise) {
+    if (!c || (n && !pts)) return fail(HB_ERR_INVALID, "null argument");
+    if (n == 0) return HB_OK;
+    for (size_t i = 0; i < n; ++i)
+        if (!coord_ok(pts[i].x) || !coord_ok(pts[i].y) || !coord_ok(pts[i].z))
+            return fail(HB_ERR_RANGE, "chunk %zu outside +-%d", i, HB_MAX_CHUNK_COORD);
+    std::lock_guard<std::mutex> lk(c->mu);
+    HB_CUDA(cudaSetDevice(c->device));
+    const size_t batch = out_cubes ? 2048 : 8192;
+    std::vector<int32_t> cols, colidx;
+    std::unordered_map<KeyXZ, int32_t, KeyXZHash> map;
+    for (size_t b0 = 0; b0 < n; b0 += batch) {
+        const size_t nb = std::min(batch, n - b0);
+        // every chunk of a column shares one noise tile: evaluate each (cx, cz) once per batch
+        cols.clear(); colidx.resize(nb); map.clear();
+        for (size_t i = 0; i < nb; ++i) {
+            const KeyXZ k{pts[b0 + i].x, pts[b0 + i].z};
+            auto it = map.find(k);
+            if (it == map.end()) {
+                it = map.emplace(k, (int32_t)(cols.size() / 2)).first;
+                cols.push_back(k.x); cols.push_back(k.z);
+            }
+            colidx[i] = it->second;
+        }
+        const size_t ncol = cols.size() / 2;
+        HB_CUDA(c->d_cols.reserve(ncol * 2 * sizeof(int32_t)));
+        HB_CUDA(c->d_colidx.reserve(nb * sizeof(int32_t)));
+        HB_CUDA(c->d_pts.reserve(nb * sizeof(hb_chunk_pt)));
+        HB_CUDA(c->d_heights.reserve(ncol * HB_CHUNK_AREA * sizeof(int32_t)));
+        if (out_noise) HB_CUDA(c->d_noise.reserve(ncol * HB_CHUNK_AREA * sizeof(float)));
+        if (out_ids) HB_CUDA(c->d_ids.reserve(nb * HB_CHUNK_VOLUME * sizeof(uint16_t)));
+        if (out_cubes) HB_CUDA(c->d_cubes.reserve(nb * HB_CHUNK_VOLUME * sizeof(hb_palette_cube)));
+        HB_CUDA(cudaMemcpyAsync(c->d_cols.p, cols.data(), ncol * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        HB_CUDA(cudaMemcpyAsync(c->d_colidx.p, colidx.data(), nb * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        HB_CUDA(cudaMemcpyAsync(c->d_pts.p, pts + b0, nb * sizeof(hb_chunk_pt), cudaMemcpyHostToDevice, c->stream));
+        int rc = hb_dev_generate(c, c->stream, c->d_cols.as<int32_t>(), ncol, c->d_pts.as<hb_chunk_pt>(),
+                                 c->d_colidx.as<int32_t>(), nb, c->d_heights.as<int32_t>(),
+                                 out_noise ? c->d_noise.as<float>() : nullptr, out_ids ? c->d_ids.as<uint16_t>() : nullptr,
+                                 out_cubes ? c->d_cubes.as<hb_palette_cube>() : nullptr);
+        if (rc != HB_OK) return rc;
+        if (out_ids)
+            HB_CUDA(cudaMemcpyAsync(out_ids + b0 * HB_CHUNK_VOLUME, c->d_ids.p, nb * HB_CHUNK_VOLUME * sizeof(uint16_t),
+                                    cudaMemcpyDeviceToHost, c->stream));
+        if (out_cubes)
+            HB_CUDA(cudaMemcpyAsync(out_cubes + b0 * HB_CHUNK_VOLUME, c->d_cubes.p,
+                                    nb * HB_CHUNK_VOLUME * sizeof(hb_palette_cube), cudaMemcpyDeviceToHost, c->stream));
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        if (out_noise) {
+            // per-chunk tiles in the caller's order (a column's tile is repeated for each of its chunks)
+            std::vector<float> tiles(ncol * HB_CHUNK_AREA);
+            HB_CUDA(cudaMemcpy(tiles.data(), c->d_noise.p, tiles.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nb; ++i)
+                memcpy(out_noise + (b0 + i) * HB_CHUNK_AREA, tiles.data() + (size_t)colidx[i] * HB_CHUNK_AREA,
+                       HB_CHUNK_AREA * sizeof(float));
+        }
+    }
+    return HB_OK;
+}
+
+int hb_dev_generate(hb_ctx* c, void* stream, const int32_t* d_cols_xz, size_t ncol, const hb_chunk_pt* d_pts,
+                    const int32_t* d_col_of_chunk, size_t n, int32_t* d_heights, float* d_noise, uint16_t* d_ids,
+                    hb_palette_cube* d_cubes) {
+    if (!c || !d_cols_xz || !d_heights) return fail(HB_ERR_INVALID, "null argument");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    HB_CUDA(launch_heights(s, c->world, d_cols_xz, ncol, d_heights, d_noise));
+    if (n && (d_ids || d_cubes)) {
+        if (!d_pts || !d_col_of_chunk) return fail(HB_ERR_INVALID, "null argument");
+        HB_CUDA(launch_fill(s, d_pts, d_col_of_chunk, n, d_heights, d_ids, d_cubes));
+    }
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// meshing
+// ------------------------------------------------------------------------------------------------
+
+int hb_build_neighbor_index(const hb_chunk_pt* pts, size_t n, int32_t* out) {
+    if ((n && !pts) || (n && !out)) return fail(HB_ERR_INVALID, "null argument");
+    if (n > (size_t)INT32_MAX) return fail(HB_ERR_INVALID, "too many chunks");
+    std::unordered_map<KeyXYZ, int32_t, KeyXYZHash> map;
+    map.reserve(n * 2);
+    for (size_t i = 0; i < n; ++i) map[KeyXYZ{pts[i].x, pts[i].y, pts[i].z}] = (int32_t)i;
+    for (size_t i = 0; i < n; ++i) {
+        int k = 0;
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dz = -1; dz <= 1; ++dz, ++k) {
+                    auto it = map.find(KeyXYZ{pts[i].x + dx, pts[i].y + dy, pts[i].z + dz});
+                    out[i * 27 + k] = it == map.end() ? -1 : it->second;
+                }
+    }
+    return HB_OK;
+}
+
+size_t hb_dev_mesh_workspace_bytes(size_t n) {
+    const size_t a = n * HB_CHUNK_AREA * sizeof(uint32_t);  // bitmaps
+    const size_t b = (n * sizeof(uint32_t) + 255) & ~(size_t)255;  // summary
+    return a + b + scan_workspace_bytes(n) + 256;
+}
+
+int hb_dev_mesh(hb_ctx* c, void* stream, const hb_chunk_pt* d_pts, size_t n, const uint16_t* d_ids,
+                const int32_t* d_neighbor_index, void* d_workspace, hb_instance3d* d_out, uint64_t out_capacity,
+                uint64_t* d_offsets, uint32_t* d_counts, uint64_t* d_total) {
+    if (!c || !d_total) return fail(HB_ERR_INVALID, "null argument");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    HB_CUDA(cudaMemsetAsync(d_total, 0, 4 * sizeof(uint64_t), s));
+    if (n == 0) return HB_OK;
+    if (!d_pts || !d_ids || !d_neighbor_index || !d_workspace || !d_offsets || !d_counts)
+        return fail(HB_ERR_INVALID, "null argument");
+    uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+    uint32_t* bitmaps = reinterpret_cast<uint32_t*>(ws);
+    ws += n * HB_CHUNK_AREA * sizeof(uint32_t);
+    uint32_t* summary = reinterpret_cast<uint32_t*>(ws);
+    ws += (n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    void* scan_ws = ws;
+    HB_CUDA(launch_pack(s, d_ids, n, c->mats.n_materials, bitmaps, summary, d_total));
+    HB_CUDA(launch_mesh_ids(s, false, c->tables, c->d_mats, d_pts, n, d_ids, d_neighbor_index, bitmaps, summary, d_counts,
+                            nullptr, nullptr, 0, d_total));
+    HB_CUDA(launch_scan(s, d_counts, n, d_offsets, scan_ws, d_total));
+    if (d_out)
+        HB_CUDA(launch_mesh_ids(s, true, c->tables, c->d_mats, d_pts, n, d_ids, d_neighbor_index, bitmaps, summary, d_counts,
+                                d_offsets, d_out, out_capacity, d_total));
+    return HB_OK;
+}
+
+int hb_mesh(hb_ctx* c, const hb_chunk_pt* pts, size_t n, const uint16_t* ids, const int32_t* neighbor_index,
+            hb_instance3d* out, uint64_t out_capacity, uint64_t* out_offsets, uint32_t* out_counts, uint64_t* out_total) {
+    if (!c || !out_total) return fail(HB_ERR_INVALID, "null argument");
+    *out_total = 0;
+    if (n == 0) return HB_OK;
+    if (!pts || !ids || !neighbor_index || !out_offsets || !out_counts) return fail(HB_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < n; ++i)
+        if (!coord_ok(pts[i].x) || !coord_ok(pts[i].y) || !coord_ok(pts[i].z))
+            return fail(HB_ERR_RANGE, "chunk %zu outside +-%d", i, HB_MAX_CHUNK_COORD);
+    for (size_t i = 0; i < n * 27; ++i)
+        if (neighbor_index[i] < -1 || neighbor_index[i] >= (int64_t)n)
+            return fail(HB_ERR_INVALID, "neighbor_index[%zu] = %d out of range", i, neighbor_index[i]);
+    std::lock_guard<std::mutex> lk(c->mu);
+    HB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    HB_CUDA(c->d_pts.reserve(n * sizeof(hb_chunk_pt)));
+    HB_CUDA(c->d_ids.reserve(n * HB_CHUNK_VOLUME * sizeof(uint16_t)));
+    HB_CUDA(c->d_nbr.reserve(n * 27 * sizeof(int32_t)));
+    HB_CUDA(c->d_bitmaps.reserve(hb_dev_mesh_workspace_bytes(n)));
+    HB_CUDA(c->d_counts.reserve(n * sizeof(uint32_t)));
+    HB_CUDA(c->d_offsets.reserve(n * sizeof(uint64_t)));
+    HB_CUDA(c->d_total.reserve(4 * sizeof(uint64_t)));
+    HB_CUDA(c->h_total.reserve(4 * sizeof(uint64_t)));
+    HB_CUDA(cudaMemcpyAsync(c->d_pts.p, pts, n * sizeof(hb_chunk_pt), cudaMemcpyHostToDevice, s));
+    HB_CUDA(cudaMemcpyAsync(c->d_ids.p, ids, n * HB_CHUNK_VOLUME * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    HB_CUDA(cudaMemcpyAsync(c->d_nbr.p, neighbor_index, n * 27 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    // pass 1: pack + count + scan (no instance buffer yet)
+    int rc = hb_dev_mesh(c, s, c->d_pts.as<hb_chunk_pt>(), n, c->d_ids.as<uint16_t>(), c->d_nbr.as<int32_t>(),
+                         c->d_bitmaps.p, nullptr, 0, c->d_offsets.as<uint64_t>(), c->d_counts.as<uint32_t>(),
+                         c->d_total.as<uint64_t>());
+    if (rc != HB_OK) return rc;
+    HB_CUDA(cudaMemcpyAsync(c->h_total.p, c->d_total.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaStreamSynchronize(s));
+    uint64_t tot[4];
+    memcpy(tot, c->h_total.p, sizeof(tot));
+    if (tot[2] & 2) return fail(HB_ERR_INVALID, "block array contains a material id above the palette size %d", c->mats.n_materials);
+    *out_total = tot[0];
+    HB_CUDA(cudaMemcpyAsync(out_offsets, c->d_offsets.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    HB_CUDA(cudaMemcpyAsync(out_counts, c->d_counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (tot[0] > out_capacity || (tot[0] && !out)) {
+        HB_CUDA(cudaStreamSynchronize(s));
+        return fail(HB_ERR_CAPACITY, "instance buffer holds %llu, %llu required", (unsigned long long)out_capacity,
+                    (unsigned long long)tot[0]);
+    }
+    if (tot[0]) {
+        HB_CUDA(c->d_out.reserve(tot[0] * sizeof(hb_instance3d)));
+        const uint8_t* ws = c->d_bitmaps.as<uint8_t>();
+        const uint32_t* bitmaps = reinterpret_cast<const uint32_t*>(ws);
+        const uint32_t* summary = reinterpret_cast<const uint32_t*>(ws + n * HB_CHUNK_AREA * sizeof(uint32_t));
+        HB_CUDA(launch_mesh_ids(s, true, c->tables, c->d_mats, c->d_pts.as<hb_chunk_pt>(), n, c->d_ids.as<uint16_t>(),
+                                c->d_nbr.as<int32_t>(), bitmaps, summary, c->d_counts.as<uint32_t>(),
+                                c->d_offsets.as<uint64_t>(), c->d_out.as<hb_instance3d>(), tot[0], c->d_total.as<uint64_t>()));
+        HB_CUDA(cudaMemcpyAsync(out, c->d_out.p, tot[0] * sizeof(hb_instance3d), cudaMemcpyDeviceToHost, s));
+    }
+    HB_CUDA(cudaStreamSynchronize(s));
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused region
+// ------------------------------------------------------------------------------------------------
+
+int hb_region_plan_create(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t ix_end, uint64_t quad_capacity,
+                          int want_ids, hb_region_plan** out) {
+    if (!c || !out) return fail(HB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = region_check(region);
+    if (rc != HB_OK) return rc;
+    if (ix_begin < 0 || ix_end > region->ncx || ix_begin >= ix_end) return fail(HB_ERR_INVALID, "bad slab [%d,%d)", ix_begin, ix_end);
+    if ((uint64_t)(ix_end - ix_begin) * region->ncz * region->ncy > (uint64_t)INT32_MAX)
+        return fail(HB_ERR_INVALID, "slab has too many chunks for one plan");
+    HB_CUDA(cudaSetDevice(c->device));
+    hb_region_plan* p = new (std::nothrow) hb_region_plan();
+    if (!p) return fail(HB_ERR_NOMEM, "out of host memory");
+    p->ctx = c;
+    p->region = *region;
+    p->want_ids = want_ids;
+    plan_target(p, ix_begin, ix_end);
+    rc = plan_alloc(p, ix_end - ix_begin);
+    if (rc == HB_OK && quad_capacity == 0) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        rc = plan_enqueue(p, HB_STAGE_HEIGHTS | HB_STAGE_COUNT | HB_STAGE_SCAN, c->stream);
+        uint64_t tot[4] = {0, 0, 0, 0};
+        if (rc == HB_OK) rc = plan_totals(p, c->stream, tot);
+        quad_capacity = tot[0] ? tot[0] : 4;
+    }
+    if (rc == HB_OK) {
+        p->capacity = quad_capacity;
+        cudaError_t e = p->d_out.reserve(quad_capacity * sizeof(hb_instance3d));
+        if (e != cudaSuccess) rc = fail(HB_ERR_CUDA, "instance buffer allocation failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != HB_OK) { hb_region_plan_destroy(p); return rc; }
+    *out = p;
+    return HB_OK;
+}
+
+void hb_region_plan_destroy(hb_region_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaDeviceSynchronize();
+    Buf* bufs[] = {&p->d_heights, &p->d_counts, &p->d_offsets, &p->d_scan, &p->d_total, &p->d_out, &p->d_ids, &p->h_total};
+    for (Buf* b : bufs) b->release();
+    delete p;
+}
+
+int hb_region_plan_enqueue(hb_region_plan* p, int stages, void* stream) {
+    if (!p) return fail(HB_ERR_INVALID, "plan is null");
+    HB_CUDA(cudaSetDevice(p->ctx->device));
+    return plan_enqueue(p, stages, stream ? (cudaStream_t)stream : p->ctx->stream);
+}
+
+int hb_region_plan_launches(const hb_region_plan* p, int stages) {
+    if (!p) return 0;
+    int n = 0;
+    if (stages & HB_STAGE_HEIGHTS) n += 1;
+    if (stages & HB_STAGE_COUNT) n += 1;
+    if (stages & HB_STAGE_SCAN) n += 3;
+    if (stages & HB_STAGE_EMIT) n += 1;
+    if (stages & HB_STAGE_FILL) n += 1;
+    return n;
+}
+
+int hb_region_plan_result(hb_region_plan* p, void* stream, uint64_t* n_chunks, uint64_t* total_quads, uint64_t* total_span,
+                          const hb_instance3d** d_instances, const uint64_t** d_offsets, const uint32_t** d_counts,
+                          const uint16_t** d_ids, const int32_t** d_heights) {
+    if (!p) return fail(HB_ERR_INVALID, "plan is null");
+    HB_CUDA(cudaSetDevice(p->ctx->device));
+    uint64_t tot[4];
+    int rc = plan_totals(p, stream ? (cudaStream_t)stream : p->ctx->stream, tot);
+    if (rc != HB_OK) return rc;
+    if (n_chunks) *n_chunks = p->n_chunks();
+    if (total_span) *total_span = tot[0];
+    if (total_quads) *total_quads = tot[1];
+    if (d_instances) *d_instances = p->d_out.as<hb_instance3d>();
+    if (d_offsets) *d_offsets = p->d_offsets.as<uint64_t>();
+    if (d_counts) *d_counts = p->d_counts.as<uint32_t>();
+    if (d_ids) *d_ids = p->d_ids.as<uint16_t>();
+    if (d_heights) *d_heights = p->d_heights.as<int32_t>();
+    if (tot[2] & 1) return fail(HB_ERR_CAPACITY, "instance buffer holds %llu, %llu required", (unsigned long long)p->capacity,
+                                (unsigned long long)tot[0]);
+    return HB_OK;
+}
+
+int hb_dev_download(hb_ctx* c, void* host_dst, const void* dev_src, size_t bytes) {
+    if (!c || (bytes && (!host_dst || !dev_src))) return fail(HB_ERR_INVALID, "null argument");
+    HB_CUDA(cudaSetDevice(c->device));
+    HB_CUDA(cudaDeviceSynchronize());
+    if (bytes) HB_CUDA(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+int hb_generate_mesh_region(hb_ctx* c, const hb_region* region, int want_ids, hb_region_sink sink, void* user,
+                            uint64_t* total_chunks, uint64_t* total_quads) {
+    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    int rc = region_check(region);
+    if (rc != HB_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    HB_CUDA(cudaSetDevice(c->device));
+    // slab width: aim at ~384 MiB of instances per slab (about 300 KB per column on this terrain),
+    // bounded so that the optional id image (64 KiB/chunk) stays below ~1 GiB per slab
+    const size_t per_col = 300 * 1024;
+    int32_t width = (int32_t)std::max<size_t>(1, ((size_t)384 << 20) / (per_col * (size_t)region->ncz));
+    if (want_ids) {
+        const size_t ids_per_ix = (size_t)region->ncz * region->ncy * HB_CHUNK_VOLUME * sizeof(uint16_t);
+        width = (int32_t)std::max<size_t>(1, std::min<size_t>(width, ((size_t)1 << 30) / ids_per_ix));
+    }
+    width = std::min(width, region->ncx);
+
+    hb_region_plan plan[2];
+    for (int b = 0; b < 2; ++b) {
+        plan[b].ctx = c; plan[b].region = *region; plan[b].want_ids = want_ids;
+        plan_target(&plan[b], 0, width);
+        rc = plan_alloc(&plan[b], width);
+        if (rc != HB_OK) goto done;
+    }
+    {
+        cudaEvent_t ev_kernels[2], ev_copied[2];
+        for (int b = 0; b < 2; ++b) {
+            cudaEventCreateWithFlags(&ev_kernels[b], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming);
+        }
+        struct Pending { bool live; uint64_t first, n, span; } pend[2] = {{false, 0, 0, 0}, {false, 0, 0, 0}};
+        uint64_t sum_chunks = 0, sum_quads = 0;
+        auto drain = [&](int b) -> int {
+            if (!pend[b].live) return HB_OK;
+            HB_CUDA(cudaEventSynchronize(ev_copied[b]));
+            if (sink)
+                sink(user, pend[b].first, pend[b].n, c->h_off[b].as<uint64_t>(), c->h_cnt[b].as<uint32_t>(),
+                     c->h_inst[b].as<hb_instance3d>(), pend[b].span, want_ids ? c->h_ids[b].as<uint16_t>() : nullptr);
+            pend[b].live = false;
+            return HB_OK;
+        };
+        int slab = 0;
+        for (int32_t ix0 = 0; ix0 < region->ncx && rc == HB_OK; ix0 += width, ++slab) {
+            const int b = slab & 1;
+            hb_region_plan* p = &plan[b];
+            rc = drain(b);  // buffers of parity b are free again (device out + pinned)
+            if (rc != HB_OK) break;
+            plan_target(p, ix0, std::min(region->ncx, ix0 + width));
+            const size_t nch = p->n_chunks();
+            rc = plan_enqueue(p, HB_STAGE_HEIGHTS | HB_STAGE_COUNT | HB_STAGE_SCAN, c->stream);
+            if (rc != HB_OK) break;
+            uint64_t tot[4];
+            rc = plan_totals(p, c->stream, tot);
+            if (rc != HB_OK) break;
+            p->capacity = tot[0];
+            cudaError_t e = p->d_out.reserve(std::max<uint64_t>(tot[0], 4) * sizeof(hb_instance3d));
+            if (e == cudaSuccess) e = c->h_inst[b].reserve(std::max<uint64_t>(tot[0], 4) * sizeof(hb_instance3d));
+            if (e == cudaSuccess) e = c->h_off[b].reserve(nch * sizeof(uint64_t));
+            if (e == cudaSuccess) e = c->h_cnt[b].reserve(nch * sizeof(uint32_t));
+            if (e == cudaSuccess && want_ids) e = c->h_ids[b].reserve(nch * HB_CHUNK_VOLUME * sizeof(uint16_t));
+            if (e != cudaSuccess) { rc = fail(HB_ERR_CUDA, "slab buffer allocation failed: %s", cudaGetErrorString(e)); break; }
+            rc = plan_enqueue(p, HB_STAGE_EMIT | (want_ids ? HB_STAGE_FILL : 0), c->stream);
+            if (rc != HB_OK) break;
+            cudaEventRecord(ev_kernels[b], c->stream);
+            cudaStreamWaitEvent(c->copy, ev_kernels[b], 0);
+            cudaMemcpyAsync(c->h_off[b].p, p->d_offsets.p, nch * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->copy);
+            cudaMemcpyAsync(c->h_cnt[b].p, p->d_counts.p, nch * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy);
+            if (tot[0])
+                cudaMemcpyAsync(c->h_inst[b].p, p->d_out.p, tot[0] * sizeof(hb_instance3d), cudaMemcpyDeviceToHost, c->copy);
+            if (want_ids)
+                cudaMemcpyAsync(c->h_ids[b].p, p->d_ids.p, nch * HB_CHUNK_VOLUME * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->copy);
+            cudaError_t ce = cudaEventRecord(ev_copied[b], c->copy);
+            if (ce != cudaSuccess) { rc = fail(HB_ERR_CUDA, "slab copy failed: %s", cudaGetErrorString(ce)); break; }
+            pend[b] = Pending{true, (uint64_t)ix0 * region->ncz * region->ncy, nch, tot[0]};
+            sum_chunks += nch;
+            sum_quads += tot[1];
+            // hand the previous slab to the sink while this one is computed and copied
+            rc = drain(b ^ 1);
+        }
+        if (rc == HB_OK) rc = drain((slab & 1));
+        if (rc == HB_OK) rc = drain((slab & 1) ^ 1);
+        cudaStreamSynchronize(c->copy);
+        cudaStreamSynchronize(c->stream);
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_kernels[b]); cudaEventDestroy(ev_copied[b]); }
+        if (rc == HB_OK) {
+            if (total_chunks) *total_chunks = sum_chunks;
+            if (total_quads) *total_quads = sum_quads;
+        }
+    }
+done:
+    cudaDeviceSynchronize();
+    for (int b = 0; b < 2; ++b) {
+        Buf* bufs[] = {&plan[b].d_heights, &plan[b].d_counts, &plan[b].d_offsets, &plan[b].d_scan, &plan[b].d_total,
+                       &plan[b].d_out, &plan[b].d_ids, &plan[b].h_total};
+        for (Buf* q : bufs) q->release();
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// common.cuh -- shared types for libherbgpu's sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/herbgpu.h"
+
+namespace hb {
+
+// World parameters as the kernels see them (server/src/generator/mod.rs:103-108).
+struct WorldDev {
+    int32_t seed_lo;  // `seed as i32`: the only part of the seed the 2-D/3-D paths use
+                      // (functions/gradient_32.rs:15, hash3d_32.rs:23)
+    float freq;
+    int32_t octaves;
+    float lacunarity;
+    float gain;
+};
+
+// Constant tables built on the host with the reference's formulas (api.cu) and passed by value.
+struct MeshTables {
+    float face_mat[6][12];  // Instance3d model_0..2 per face (vertex.rs:53-62)
+    float ao_lut[4];        // max(1 - k/3, 0.15) (client/src/world/chunk.rs:271-275)
+};
+
+struct MaterialsDev {
+    int32_t n_materials;
+    int32_t n_colors[HB_MAX_MATERIALS];
+    alignas(16) float rgba[HB_MAX_MATERIALS][HB_MAX_COLORS][4];  // read as float4
+};
+
+struct RegionDev {
+    int32_t cx0, cz0, ncx, ncz, cy0, ncy;
+    int32_t ix_begin, ix_end;  // slab of the region this launch handles
+    int32_t hx_begin, hx_end;  // x-range of columns present in the heights buffer (slab + apron)
+};
+
+constexpr int kHeightAbsent = INT32_MIN;  // heights-tile sentinel: column belongs to an absent chunk
+
+static_assert(sizeof(hb_instance3d) == 100, "Instance3d must be 100 bytes");
+static_assert(sizeof(hb_palette_cube) == 8, "PaletteCube must be 8 bytes");
+
+// ---- launch wrappers implemented in gen.cu / mesh.cu (all enqueue-only) ----
+cudaError_t launch_heights(cudaStream_t s, const WorldDev& w, const int32_t* d_cols_xz, size_t ncol,
+                           int32_t* d_heights, float* d_noise);
+cudaError_t launch_heights_region(cudaStream_t s, const WorldDev& w, const RegionDev& r, int32_t* d_heights);
+cudaError_t launch_fill(cudaStream_t s, const hb_chunk_pt* d_pts, const int32_t* d_col_of_chunk, size_t n,
+                        const int32_t* d_heights, uint16_t* d_ids, hb_palette_cube* d_cubes);
+cudaError_t launch_fill_region(cudaStream_t s, const RegionDev& r, const int32_t* d_heights, uint16_t* d_ids);
+cudaError_t launch_noise3d(cudaStream_t s, const WorldDev& w, float sx, float sy, float sz, int nx, int ny, int nz,
+                           float fx, float fy, float fz, float* d_out);
+
+cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_materials, uint32_t* d_bitmaps,
+                        uint32_t* d_summary, uint64_t* d_total);
+cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
+                            const hb_chunk_pt* d_pts, size_t n, const uint16_t* d_ids, const int32_t* d_nbr,
+                            const uint32_t* d_bitmaps, const uint32_t* d_summary, uint32_t* d_counts,
+                            const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity, uint64_t* d_total);
+cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
+                               const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
+                               const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
+                               uint64_t* d_total);
+// counts -> offsets (each chunk's start rounded up to 4 instances); d_total[0]=span, d_total[1]=quads
+size_t scan_workspace_bytes(size_t n);
+cudaError_t launch_scan(cudaStream_t s, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* d_ws,
+                        uint64_t* d_total);
+int num_sms();
+
+}  // namespace hb

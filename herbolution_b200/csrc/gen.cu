@@ -1,0 +1,242 @@
+// gen.cu -- terrain generation kernels (sm_100a).
+//
+//   k_heights : batched 2-D simplex FBM, one CTA per chunk column, permutation table in shared
+//               memory, 4 independent samples per thread.  FP32/ALU-issue bound.
+//               Replaces get_2d_noise_helper_f32 + fbm_2d + simplex_2d (crates/simd-noise) and the
+//               height computation of GenerationParams::generate (server/src/generator/mod.rs:74-79).
+//   k_fill    : heights -> u16 block ids, one 128-bit streaming store per thread per 8 voxels,
+//               warp-contiguous (512 B per store instruction).  HBM-write bound.
+//               Replaces the fill loop of GenerationParams::generate (generator/mod.rs:77-94).
+//   k_fill_cubes : heights -> 8-byte PaletteCube image incl. the in-chunk face flags CubeMesh::set
+//               leaves behind (server/src/chunk/mesh.rs:125-232).
+//   k_noise3d : 3-D simplex FBM tile (crates/simd-noise/src/noise/f32.rs:131-198).
+#include "noise.cuh"
+
+namespace hb {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct ColList {
+    const int32_t* cols_xz;
+    __device__ __forceinline__ void get(int col, int& cx, int& cz) const {
+        cx = cols_xz[2 * col];
+        cz = cols_xz[2 * col + 1];
+    }
+};
+struct ColRegion {
+    RegionDev r;
+    __device__ __forceinline__ void get(int col, int& cx, int& cz) const {
+        const int ix = r.hx_begin + col / r.ncz;
+        const int iz = col % r.ncz;
+        cx = r.cx0 + ix;
+        cz = r.cz0 + iz;
+    }
+};
+
+// One CTA = one chunk column = 32x32 samples.  Sample i: x = i & 31, z = i >> 5 (the crate's tile
+// order x + z*32, noise/f32.rs:95-113).  Heights are written in voxel-column order x*32 + z.
+template <class Cols>
+__global__ void __launch_bounds__(kThreads) k_heights(WorldDev w, Cols cols, int32_t* __restrict__ heights,
+                                                       float* __restrict__ noise) {
+    __shared__ __align__(16) uint8_t s_perm[256];
+    __shared__ int s_h[HB_CHUNK_AREA];
+    load_perm(s_perm);
+    const int col = blockIdx.x;
+    int cx, cz;
+    cols.get(col, cx, cz);
+    // chunk.position.xz().cast() * CHUNK_LENGTH as f32 (generator/mod.rs:74); lane coordinate =
+    // start + i, exact in f32 for |c| <= HB_MAX_CHUNK_COORD
+    const float start_x = __fmul_rn(__int2float_rn(cx), 32.0f);
+    const float start_z = __fmul_rn(__int2float_rn(cz), 32.0f);
+    __syncthreads();
+
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        const float x = __fadd_rn(start_x, __int2float_rn(i & 31));
+        const float z = __fadd_rn(start_z, __int2float_rn(i >> 5));
+        v[k] = fbm2(s_perm, __fmul_rn(x, w.freq), __fmul_rn(z, w.freq), w);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        if (noise) noise[(size_t)col * HB_CHUNK_AREA + i] = v[k];
+        s_h[(i & 31) * 32 + (i >> 5)] = height_from_noise(v[k]);
+    }
+    __syncthreads();
+    if (heights) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = threadIdx.x + k * kThreads;
+            heights[(size_t)col * HB_CHUNK_AREA + i] = s_h[i];
+        }
+    }
+}
+
+struct ChunkList {
+    const hb_chunk_pt* pts;
+    const int32_t* col_of_chunk;
+    __device__ __forceinline__ void get(size_t chunk, int& col, int& cy) const {
+        col = col_of_chunk[chunk];
+        cy = pts[chunk].y;
+    }
+};
+struct ChunkRegion {
+    RegionDev r;
+    // chunk index is relative to the slab: ((ix-ix_begin)*ncz + iz)*ncy + iy
+    __device__ __forceinline__ void get(size_t chunk, int& col, int& cy) const {
+        const int iy = (int)(chunk % r.ncy);
+        const size_t c2 = chunk / r.ncy;
+        const int iz = (int)(c2 % r.ncz);
+        const int ix = r.ix_begin + (int)(c2 / r.ncz);
+        col = (ix - r.hx_begin) * r.ncz + iz;
+        cy = r.cy0 + iy;
+    }
+};
+
+// generator/mod.rs:85-91 with d = h - y: stone if y < h-6, dirt if y < h-1, grass if y < h
+__device__ __forceinline__ uint32_t block_id(int d) { return d > 6 ? 1u : (d > 1 ? 2u : (d > 0 ? 3u : 0u)); }
+
+template <class Chunks>
+__global__ void __launch_bounds__(kThreads) k_fill(Chunks chunks, const int32_t* __restrict__ heights,
+                                                    uint16_t* __restrict__ ids) {
+    __shared__ int s_h[HB_CHUNK_AREA];
+    const size_t chunk = blockIdx.x;
+    int col, cy;
+    chunks.get(chunk, col, cy);
+    const int4* src = reinterpret_cast<const int4*>(heights + (size_t)col * HB_CHUNK_AREA);
+    reinterpret_cast<int4*>(s_h)[threadIdx.x] = __ldg(src + threadIdx.x);
+    __syncthreads();
+    const long long wy0 = (long long)cy * 32;
+    uint4* dst = reinterpret_cast<uint4*>(ids + chunk * HB_CHUNK_VOLUME);
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+        const int u = it * kThreads + threadIdx.x;  // 8-voxel unit: column u>>2, y0 = (u&3)*8
+        const int h = s_h[u >> 2];
+        long long dl = (long long)h - (wy0 + (u & 3) * 8);
+        dl = dl < -8 ? -8 : (dl > 16 ? 16 : dl);
+        const int d = (int)dl;
+        uint4 o;
+        o.x = block_id(d) | (block_id(d - 1) << 16);
+        o.y = block_id(d - 2) | (block_id(d - 3) << 16);
+        o.z = block_id(d - 4) | (block_id(d - 5) << 16);
+        o.w = block_id(d - 6) | (block_id(d - 7) << 16);
+        __stcs(dst + u, o);
+    }
+}
+
+// PaletteCube image after generate(): for a solid voxel, face f is kept iff the in-chunk neighbour
+// in direction f is air or f leaves the chunk; an air voxel has flags = 1 iff some in-chunk neighbour
+// is solid (CubeMesh::set touches it through remove_neighboring_faces, mesh.rs:209-232), else 0.
+template <class Chunks>
+__global__ void __launch_bounds__(kThreads) k_fill_cubes(Chunks chunks, const int32_t* __restrict__ heights,
+                                                          hb_palette_cube* __restrict__ cubes) {
+    __shared__ int s_h[HB_CHUNK_AREA];
+    const size_t chunk = blockIdx.x;
+    int col, cy;
+    chunks.get(chunk, col, cy);
+    const int4* src = reinterpret_cast<const int4*>(heights + (size_t)col * HB_CHUNK_AREA);
+    reinterpret_cast<int4*>(s_h)[threadIdx.x] = __ldg(src + threadIdx.x);
+    __syncthreads();
+    const long long wy0 = (long long)cy * 32;
+    uint4* dst = reinterpret_cast<uint4*>(cubes + chunk * HB_CHUNK_VOLUME);
+    for (int it = 0; it < 64; ++it) {
+        const int p = it * kThreads + threadIdx.x;  // voxel pair
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int L = 2 * p + e;
+            const int y = L & 31, z = (L >> 5) & 31, x = L >> 10;
+            const long long wy = wy0 + y;
+            const int c = x * 32 + z;
+            auto dcl = [&](int hh) -> int {
+                long long dl = (long long)hh - wy;
+                return (int)(dl < -8 ? -8 : (dl > 16 ? 16 : dl));
+            };
+            const int d = dcl(s_h[c]);
+            const uint32_t id = block_id(d);
+            // neighbour solidity: same column y+-1 -> d-1 / d+1; lateral columns at the same y
+            const bool sU = (y < 31) && (d - 1 > 0);
+            const bool sD = (y > 0) && (d + 1 > 0);
+            const bool sE = (x < 31) && (dcl(s_h[c + 32]) > 0);
+            const bool sW = (x > 0) && (dcl(s_h[c - 32]) > 0);
+            const bool sN = (z < 31) && (dcl(s_h[c + 1]) > 0);
+            const bool sS = (z > 0) && (dcl(s_h[c - 1]) > 0);
+            uint32_t flags;
+            if (id) {
+                const uint32_t faces = (sE ? 0u : 1u) | (sW ? 0u : 2u) | (sU ? 0u : 4u) | (sD ? 0u : 8u) |
+                                       (sN ? 0u : 16u) | (sS ? 0u : 32u);
+                flags = (faces << 1) | 1u;
+            } else {
+                flags = (sE | sW | sU | sD | sN | sS) ? 1u : 0u;
+            }
+            w[2 * e] = id;  // material u16 + zero pad
+            w[2 * e + 1] = flags;
+        }
+        __stcs(dst + p, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_noise3d(WorldDev w, float sx, float sy, float sz, int nx, int ny,
+                                                       int nz, float fx, float fy, float fz,
+                                                       float* __restrict__ out) {
+    const size_t total = (size_t)nx * ny * nz;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+        const int ix = (int)(i % nx);
+        const int iy = (int)((i / nx) % ny);
+        const int iz = (int)(i / ((size_t)nx * ny));
+        // coordinates advance by repeated +1.0 / +WIDTH in the reference; integers, exact in f32
+        const float x = __fadd_rn(sx, __int2float_rn(ix));
+        const float y = __fadd_rn(sy, __int2float_rn(iy));
+        const float z = __fadd_rn(sz, __int2float_rn(iz));
+        out[i] = fbm3(__fmul_rn(x, fx), __fmul_rn(y, fy), __fmul_rn(z, fz), w);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_heights(cudaStream_t s, const WorldDev& w, const int32_t* d_cols_xz, size_t ncol,
+                           int32_t* d_heights, float* d_noise) {
+    if (ncol == 0) return cudaSuccess;
+    k_heights<ColList><<<(unsigned)ncol, kThreads, 0, s>>>(w, ColList{d_cols_xz}, d_heights, d_noise);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_heights_region(cudaStream_t s, const WorldDev& w, const RegionDev& r, int32_t* d_heights) {
+    const size_t ncol = (size_t)(r.hx_end - r.hx_begin) * r.ncz;
+    if (ncol == 0) return cudaSuccess;
+    k_heights<ColRegion><<<(unsigned)ncol, kThreads, 0, s>>>(w, ColRegion{r}, d_heights, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill(cudaStream_t s, const hb_chunk_pt* d_pts, const int32_t* d_col_of_chunk, size_t n,
+                        const int32_t* d_heights, uint16_t* d_ids, hb_palette_cube* d_cubes) {
+    if (n == 0) return cudaSuccess;
+    ChunkList cl{d_pts, d_col_of_chunk};
+    if (d_ids) k_fill<ChunkList><<<(unsigned)n, kThreads, 0, s>>>(cl, d_heights, d_ids);
+    if (d_cubes) k_fill_cubes<ChunkList><<<(unsigned)n, kThreads, 0, s>>>(cl, d_heights, d_cubes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_region(cudaStream_t s, const RegionDev& r, const int32_t* d_heights, uint16_t* d_ids) {
+    const size_t n = (size_t)(r.ix_end - r.ix_begin) * r.ncz * r.ncy;
+    if (n == 0) return cudaSuccess;
+    k_fill<ChunkRegion><<<(unsigned)n, kThreads, 0, s>>>(ChunkRegion{r}, d_heights, d_ids);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_noise3d(cudaStream_t s, const WorldDev& w, float sx, float sy, float sz, int nx, int ny, int nz,
+                           float fx, float fy, float fz, float* d_out) {
+    const size_t total = (size_t)nx * ny * nz;
+    if (total == 0) return cudaSuccess;
+    size_t blocks = (total + kThreads - 1) / kThreads;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    k_noise3d<<<(unsigned)blocks, kThreads, 0, s>>>(w, sx, sy, sz, nx, ny, nz, fx, fy, fz, d_out);
+    return cudaGetLastError();
+}
+
+}  // namespace hb

@@ -1,0 +1,645 @@
+// mesh.cu -- chunk meshing kernels (sm_100a): visible-face culling incl. cross-chunk borders,
+// ambient occlusion, per-face colour, atomics-free compaction into packed Instance3d buffers.
+//
+// Replaces, for a whole batch per launch:
+//   - the in-chunk face flags CubeMesh::set maintains        server/src/chunk/mesh.rs:125-232
+//   - CubeMesh::cull_shared_faces across chunk borders         server/src/chunk/mesh.rs:76-123
+//   - client generate_mesh / facial_ao / Instance3d::new        client/src/world/chunk.rs:176-276,
+//                                                               client/src/video/world/vertex.rs:53-68
+//
+// Data layout.  A chunk (plus its one-voxel halo from the 26 neighbours) is staged in shared memory
+// as an OCCUPANCY TILE: 34x34 columns of 64-bit words, bit (y+1) of occ[x+1][z+1] = voxel (x,y,z)
+// solid (y is the fastest voxel axis, so one word is one vertical run).  Absent neighbour chunks
+// contribute zero bits, which yields the reference's semantics for unloaded chunks (border faces
+// emitted, AO probes "empty").  Face visibility is then six 32-bit mask expressions per column,
+// counting is popc, and the per-chunk compaction is a warp-shuffle scan + one block-level combine
+// in the reference's emission order (ascending L = x*1024+z*32+y, then face order) -- no atomics.
+//
+// Emission: visible faces -> 32-bit descriptors in shared memory (L | face<<15 | ao<<18), then one
+// thread per quad expands a descriptor to the 100-byte Instance3d in a shared staging buffer
+// (stride 25 words: bank-conflict free), and the CTA streams the staging buffer to HBM with
+// 128-bit coalesced stores.  Each chunk's output starts on a 4-instance (400 B) boundary so every
+// vector store is 16-byte aligned.
+#include "common.cuh"
+
+namespace hb {
+
+namespace {
+
+constexpr int kT = 256;         // threads per CTA
+constexpr int kCtasPerSm = 4;   // limited by ~48 KB of shared memory per CTA
+constexpr int kTile = 34;
+constexpr int kTileN = kTile * kTile;
+constexpr int kDescCap = 2048;  // descriptors staged per round
+constexpr int kStageCap = kT;   // quads expanded per window (one per thread)
+
+typedef unsigned long long u64;
+
+struct MeshSmem {
+    u64 occ[kTileN];                            // 9248 B
+    __align__(16) float stage[kStageCap * 25];  // 25600 B
+    uint32_t desc[kDescCap];                    // 8192 B
+    int hts[kTileN];                            // 4624 B (region kernels: heights halo tile)
+    float face_mat[6][12];
+    float ao_lut[4];
+    uint32_t warp_tot[32];
+    u64 rng_seed;
+    int nbr[27];
+    int red[2][8];
+};
+
+// ---- SipHash-1-3 with zero keys over the 12 bytes of ChunkPt: std DefaultHasher as used at
+// client/src/world/chunk.rs:182-184 ----
+__device__ __forceinline__ u64 rotl64(u64 x, int b) { return (x << b) | (x >> (64 - b)); }
+#define HB_SIPROUND                                                   \
+    do {                                                              \
+        v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0; v0 = rotl64(v0, 32); \
+        v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;                      \
+        v0 += v3; v3 = rotl64(v3, 21); v3 ^= v0;                      \
+        v2 += v1; v1 = rotl64(v1, 17); v1 ^= v2; v2 = rotl64(v2, 32); \
+    } while (0)
+__device__ u64 siphash13_chunk(int x, int y, int z) {
+    u64 v0 = 0x736f6d6570736575ULL, v1 = 0x646f72616e646f6dULL;
+    u64 v2 = 0x6c7967656e657261ULL, v3 = 0x7465646279746573ULL;
+    const u64 m0 = (u64)(uint32_t)x | ((u64)(uint32_t)y << 32);
+    v3 ^= m0; HB_SIPROUND; v0 ^= m0;
+    const u64 b = ((u64)12 << 56) | (u64)(uint32_t)z;
+    v3 ^= b; HB_SIPROUND; v0 ^= b;
+    v2 ^= 0xff;
+    HB_SIPROUND; HB_SIPROUND; HB_SIPROUND;
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+
+// fastrand 2.3.0 wyrand in counter form: the reference draws 6 f32 per voxel in index order
+// (client/src/world/chunk.rs:195, lib/src/spatial/face.rs:430-442), so draw n = 6*L + face uses
+// state seed + (n+1)*0x2d358dccaa6c78a5.  Returns Rng::f32().
+__device__ __forceinline__ float wyrand_f32_at(u64 seed, uint32_t n) {
+    const u64 s = seed + (u64)(n + 1u) * 0x2d358dccaa6c78a5ULL;
+    const u64 b = s ^ 0x8bb84b93962eacc9ULL;
+    const u64 r = (s * b) ^ __umul64hi(s, b);
+    return __fsub_rn(__uint_as_float(0x3F800000u | ((uint32_t)r >> 9)), 1.0f);
+}
+
+// generator/mod.rs:85-91 with d = h - y
+__device__ __forceinline__ uint32_t block_id(int d) { return d > 6 ? 1u : (d > 1 ? 2u : (d > 0 ? 3u : 0u)); }
+
+// vertex_ao, client/src/world/chunk.rs:251-253
+__device__ __forceinline__ uint32_t vao(uint32_t s1, uint32_t s2, uint32_t c) { return (s1 & s2) ? 3u : s1 + s2 + c; }
+
+// facial_ao (chunk.rs:255-276) for the face whose orthonormal_basis (lib/src/spatial/face.rs:84-93)
+// is u=(UX,UY,UZ), v=(VX,VY,VZ), n=(NX,NY,NZ); probes read the occupancy tile.
+template <int UX, int UY, int UZ, int VX, int VY, int VZ, int NX, int NY, int NZ>
+__device__ __forceinline__ uint32_t ao_bits(const u64* __restrict__ occ, int x, int y, int z) {
+#define HB_P(a, b)                                                                                  \
+    ((uint32_t)(occ[(x + 1 + NX + (a) * UX + (b) * VX) * kTile + (z + 1 + NZ + (a) * UZ + (b) * VZ)] >> \
+                (y + 1 + NY + (a) * UY + (b) * VY)) & 1u)
+    const uint32_t tl = HB_P(-1, -1), tc = HB_P(0, -1), tr = HB_P(1, -1);
+    const uint32_t ml = HB_P(-1, 0), mr = HB_P(1, 0);
+    const uint32_t bl = HB_P(-1, 1), bc = HB_P(0, 1), br = HB_P(1, 1);
+#undef HB_P
+    return vao(ml, tc, tl) | (vao(ml, bc, bl) << 2) | (vao(mr, tc, tr) << 4) | (vao(mr, bc, br) << 6);
+}
+
+__device__ __forceinline__ uint32_t ao_for_face(const u64* occ, int f, int x, int y, int z) {
+    switch (f) {
+        case 0: return ao_bits<0, 0, -1, 0, 1, 0, 1, 0, 0>(occ, x, y, z);   // East  (-Z,  Y,  X)
+        case 1: return ao_bits<0, 0, 1, 0, 1, 0, -1, 0, 0>(occ, x, y, z);   // West  ( Z,  Y, -X)
+        case 2: return ao_bits<1, 0, 0, 0, 0, -1, 0, 1, 0>(occ, x, y, z);   // Up    ( X, -Z,  Y)
+        case 3: return ao_bits<1, 0, 0, 0, 0, 1, 0, -1, 0>(occ, x, y, z);   // Down  ( X,  Z, -Y)
+        case 4: return ao_bits<1, 0, 0, 0, 1, 0, 0, 0, 1>(occ, x, y, z);    // North ( X,  Y,  Z)
+        default: return ao_bits<-1, 0, 0, 0, 1, 0, 0, 0, -1>(occ, x, y, z); // South (-X,  Y, -Z)
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Meshes the occupancy tile in sm.occ (already built and synchronised).  Column mapping: thread t
+// owns columns (x = k*8 + t/32, z = t%32), k = 0..3, so a warp reads 32 consecutive tile words.
+// Returns the chunk's quad count (all threads).  EMIT additionally writes the instances at `out`
+// (16-byte aligned), zero-filling up to the next multiple of 4 instances.
+template <bool EMIT, class MatFn>
+__device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, int bx, int by, int bz,
+                                              const MaterialsDev* __restrict__ mats, float* __restrict__ out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t m[4][6], cnt[4], incl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = k * 8 + warp, z = lane;
+        const u64* o = sm.occ + (x + 1) * kTile + (z + 1);
+        const u64 C = o[0];
+        const uint32_t cen = (uint32_t)(C >> 1);
+        uint32_t c = 0;
+        if (cen) {
+            m[k][0] = cen & ~(uint32_t)(o[kTile] >> 1);   // East : (x+1, y, z) empty
+            m[k][1] = cen & ~(uint32_t)(o[-kTile] >> 1);  // West
+            m[k][2] = cen & ~(uint32_t)(C >> 2);          // Up   : (x, y+1, z)
+            m[k][3] = cen & ~(uint32_t)C;                 // Down : (x, y-1, z)
+            m[k][4] = cen & ~(uint32_t)(o[1] >> 1);       // North: (x, y, z+1)
+            m[k][5] = cen & ~(uint32_t)(o[-1] >> 1);      // South
+#pragma unroll
+            for (int f = 0; f < 6; ++f) c += __popc(m[k][f]);
+        } else {
+#pragma unroll
+            for (int f = 0; f < 6; ++f) m[k][f] = 0;
+        }
+        cnt[k] = c;
+        incl[k] = warp_incl_scan(c, lane);
+        if (lane == 31) sm.warp_tot[k * 8 + warp] = incl[k];
+    }
+    __syncthreads();
+    // 32 (k, warp) totals in column order; every warp scans them redundantly (no second barrier)
+    const uint32_t wt = sm.warp_tot[lane];
+    const uint32_t ws = warp_incl_scan(wt, lane);
+    const uint32_t total = __shfl_sync(0xffffffffu, ws, 31);
+    if constexpr (EMIT) {
+    uint32_t base[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = k * 8 + warp;
+        base[k] = __shfl_sync(0xffffffffu, ws, idx) - __shfl_sync(0xffffffffu, wt, idx) + incl[k] - cnt[k];
+    }
+
+    for (uint32_t d0 = 0; d0 < total; d0 += kDescCap) {
+        // (a) visible faces of my columns -> descriptors, in emission order
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t o = base[k];
+            if (cnt[k] == 0 || o >= d0 + kDescCap || o + cnt[k] <= d0) continue;
+            const int x = k * 8 + warp, z = lane;
+            uint32_t any = m[k][0] | m[k][1] | m[k][2] | m[k][3] | m[k][4] | m[k][5];
+            while (any) {
+                const int y = __ffs(any) - 1;
+                any &= any - 1;
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    if ((m[k][f] >> y) & 1u) {
+                        if (o >= d0 && o < d0 + kDescCap) {
+                            const uint32_t ao = ao_for_face(sm.occ, f, x, y, z);
+                            sm.desc[o - d0] = (uint32_t)((x << 10) | (z << 5) | y) | ((uint32_t)f << 15) | (ao << 18);
+                        }
+                        ++o;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nd = min((uint32_t)kDescCap, total - d0);
+        // (b) expand descriptors window by window and stream them out
+        for (uint32_t w0 = 0; w0 < nd; w0 += kStageCap) {
+            const uint32_t nw = min((uint32_t)kStageCap, nd - w0);
+            const uint32_t nw4 = (nw + 3u) & ~3u;
+            if ((uint32_t)tid < nw4) {
+                float* s = sm.stage + tid * 25;
+                if ((uint32_t)tid < nw) {
+                    const uint32_t d = sm.desc[w0 + tid];
+                    const uint32_t L = d & 0x7FFFu, f = (d >> 15) & 7u, ao = (d >> 18) & 0xFFu;
+                    const int x = L >> 10, z = (L >> 5) & 31, y = L & 31;
+                    const uint32_t id = mat(L, x, y, z);
+                    // Material::get_color(perms[face]) (server/src/chunk/material.rs:67-71)
+                    const float p = wyrand_f32_at(sm.rng_seed, 6u * L + f);
+                    const int nc = mats->n_colors[id - 1];
+                    const int ci = __float2int_rz(__fmul_rn(__int2float_rn(nc > 0 ? nc - 1 : 0), p));
+                    const float4 rgba = *reinterpret_cast<const float4*>(mats->rgba[id - 1][ci]);
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) s[i] = sm.face_mat[f][i];
+                    s[12] = __int2float_rn(bx + x);  // (chunk_position + position).cast::<f32>()
+                    s[13] = __int2float_rn(by + y);
+                    s[14] = __int2float_rn(bz + z);
+                    s[15] = 1.0f;
+                    s[16] = rgba.x; s[17] = rgba.y; s[18] = rgba.z; s[19] = rgba.w;
+                    s[20] = __uint_as_float(0u);  // light = 0 (chunk.rs:207)
+                    s[21] = sm.ao_lut[ao & 3u];
+                    s[22] = sm.ao_lut[(ao >> 2) & 3u];
+                    s[23] = sm.ao_lut[(ao >> 4) & 3u];
+                    s[24] = sm.ao_lut[(ao >> 6) & 3u];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 25; ++i) s[i] = 0.0f;
+                }
+            }
+            __syncthreads();
+            const uint32_t nvec = nw4 * 25u / 4u;
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)(d0 + w0) * 25u);
+            const float4* src = reinterpret_cast<const float4*>(sm.stage);
+            for (uint32_t i = tid; i < nvec; i += kT) __stcs(dst + i, src[i]);
+            __syncthreads();
+        }
+    }
+    }  // if constexpr (EMIT)
+    return total;
+}
+
+__device__ __forceinline__ void load_tables(MeshSmem& sm, const MeshTables& tb) {
+    for (int i = threadIdx.x; i < 72; i += kT) (&sm.face_mat[0][0])[i] = (&tb.face_mat[0][0])[i];
+    if (threadIdx.x < 4) sm.ao_lut[threadIdx.x] = tb.ao_lut[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------
+// General path: arbitrary block arrays.
+// ------------------------------------------------------------------------------------------------
+
+// K3a: u16 ids -> 1 bit per voxel (bitmap[c] for column c = x*32+z, bit y) + a per-chunk summary
+// word: bit0 any solid, bit1 all solid, bit(2+f) boundary slab at face f entirely solid.
+// One 128-bit streaming load per thread per 8 voxels; the chunk's 64 KiB are read exactly once.
+__global__ void __launch_bounds__(kT) k_pack(const uint16_t* __restrict__ ids, size_t n, int n_materials,
+                                             uint32_t* __restrict__ bitmaps, uint32_t* __restrict__ summary,
+                                             u64* __restrict__ total) {
+    __shared__ uint32_t s_red[8][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(ids + chunk * HB_CHUNK_VOLUME);
+        uint32_t any = 0, all = ~0u, fE = ~0u, fW = ~0u, fN = ~0u, fS = ~0u, bad = 0;
+        const uint32_t nm = (uint32_t)n_materials;
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+            const int u = it * kT + tid;
+            const uint4 v = __ldcs(src + u);
+            const uint32_t h[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
+                                   v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+            uint32_t m8 = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                m8 |= (h[e] != 0u ? 1u : 0u) << e;
+                bad |= (h[e] > nm) ? 1u : 0u;
+            }
+            uint32_t w = m8 << ((u & 3) * 8);
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            const int c = u >> 2, x = c >> 5, z = c & 31;
+            if ((lane & 3) == 0) bitmaps[chunk * HB_CHUNK_AREA + c] = w;
+            any |= w;
+            all &= w;
+            if (x == 31) fE &= w;
+            if (x == 0) fW &= w;
+            if (z == 31) fN &= w;
+            if (z == 0) fS &= w;
+        }
+        any = __reduce_or_sync(0xffffffffu, any);
+        all = __reduce_and_sync(0xffffffffu, all);
+        fE = __reduce_and_sync(0xffffffffu, fE);
+        fW = __reduce_and_sync(0xffffffffu, fW);
+        fN = __reduce_and_sync(0xffffffffu, fN);
+        fS = __reduce_and_sync(0xffffffffu, fS);
+        bad = __reduce_or_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            s_red[warp][0] = any; s_red[warp][1] = all; s_red[warp][2] = fE; s_red[warp][3] = fW;
+            s_red[warp][4] = fN; s_red[warp][5] = fS; s_red[warp][6] = bad;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t a = 0, l = ~0u, e = ~0u, w_ = ~0u, nn = ~0u, s = ~0u, b = 0;
+            for (int i = 0; i < 8; ++i) {
+                a |= s_red[i][0]; l &= s_red[i][1]; e &= s_red[i][2]; w_ &= s_red[i][3];
+                nn &= s_red[i][4]; s &= s_red[i][5]; b |= s_red[i][6];
+            }
+            uint32_t sw = (a ? 1u : 0u) | (l == ~0u ? 2u : 0u);
+            sw |= (e == ~0u ? 1u : 0u) << 2;          // East slab (x = 31)
+            sw |= (w_ == ~0u ? 1u : 0u) << 3;         // West slab (x = 0)
+            sw |= ((l >> 31) & 1u) << 4;              // Up slab (y = 31 of every column)
+            sw |= (l & 1u) << 5;                      // Down slab (y = 0)
+            sw |= (nn == ~0u ? 1u : 0u) << 6;         // North slab (z = 31)
+            sw |= (s == ~0u ? 1u : 0u) << 7;          // South slab (z = 0)
+            summary[chunk] = sw;
+            if (b) atomicOr(total + 2, 2ULL);         // error path only: unknown material id
+        }
+        __syncthreads();
+    }
+}
+
+struct MatIds {
+    const uint16_t* ids;  // centre chunk
+    __device__ __forceinline__ uint32_t operator()(uint32_t L, int, int, int) const { return __ldg(ids + L); }
+};
+
+// shell index (dx+1)*9 + (dy+1)*3 + (dz+1) of the face neighbour (client/src/world/chunk.rs:158-174)
+__device__ __forceinline__ int face_shell_index(int f) {
+    const int t[6] = {22, 4, 16, 10, 14, 12};
+    return t[f];
+}
+
+// K3b/K3c: count (EMIT=false) or emit (EMIT=true) for arbitrary block arrays, persistent CTAs.
+template <bool EMIT>
+__global__ void __launch_bounds__(kT, kCtasPerSm)
+k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_chunk_pt* __restrict__ pts, size_t n,
+           const uint16_t* __restrict__ ids, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
+           const uint32_t* __restrict__ summary, uint32_t* __restrict__ counts, const u64* __restrict__ offsets,
+           float* __restrict__ out, u64 capacity, u64* __restrict__ total) {
+    __shared__ MeshSmem sm;
+    const int tid = threadIdx.x;
+    if (EMIT) load_tables(sm, tb);
+    for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        // block-uniform early outs from the summaries
+        const uint32_t s = summary[chunk];
+        bool trivial = !(s & 1u);
+        if (!trivial && (s & 2u)) {
+            trivial = true;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+                const int nb = nbr[chunk * 27 + face_shell_index(f)];
+                if (nb < 0 || !((summary[nb] >> (2 + (f ^ 1))) & 1u)) trivial = false;
+            }
+        }
+        if (trivial) {
+            if (!EMIT && tid == 0) counts[chunk] = 0;
+            continue;
+        }
+        u64 off = 0;
+        if (EMIT) {
+            off = offsets[chunk];
+            const u64 span = ((u64)counts[chunk] + 3ULL) & ~3ULL;
+            if (off + span > capacity) {
+                if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
+                continue;
+            }
+        }
+        __syncthreads();  // previous chunk's readers of sm.nbr / sm.occ are done
+        if (tid < 27) sm.nbr[tid] = nbr[chunk * 27 + tid];
+        const hb_chunk_pt pt = pts[chunk];
+        if (EMIT && tid == 32) sm.rng_seed = siphash13_chunk(pt.x, pt.y, pt.z);
+        __syncthreads();
+        for (int i = tid; i < kTileN; i += kT) {
+            const int xi = i / kTile, zi = i - xi * kTile;
+            const int dx = (xi == 0) ? -1 : (xi == kTile - 1 ? 1 : 0);
+            const int dz = (zi == 0) ? -1 : (zi == kTile - 1 ? 1 : 0);
+            const int c = ((xi - 1) & 31) * 32 + ((zi - 1) & 31);
+            const int sb = (dx + 1) * 9 + (dz + 1);
+            u64 v = 0;
+            const int n0 = sm.nbr[sb + 3];  // dy = 0
+            if (n0 >= 0) v |= (u64)__ldg(bitmaps + (size_t)n0 * HB_CHUNK_AREA + c) << 1;
+            const int nd = sm.nbr[sb];      // dy = -1: its y = 31
+            if (nd >= 0) v |= (u64)(__ldg(bitmaps + (size_t)nd * HB_CHUNK_AREA + c) >> 31);
+            const int nu = sm.nbr[sb + 6];  // dy = +1: its y = 0
+            if (nu >= 0) v |= (u64)(__ldg(bitmaps + (size_t)nu * HB_CHUNK_AREA + c) & 1u) << 33;
+            sm.occ[i] = v;
+        }
+        __syncthreads();
+        const MatIds mat{ids + chunk * HB_CHUNK_VOLUME};
+        const uint32_t q = mesh_tile<EMIT>(sm, mat, pt.x * 32, pt.y * 32, pt.z * 32, mats,
+                                           EMIT ? out + off * 25ULL : nullptr);
+        if (!EMIT && tid == 0) counts[chunk] = q;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused path: heightmap terrain straight from the heights tiles (no block-array round trip).
+// One work item = one chunk column; the 34x34 heights halo is staged once and reused for all cy.
+// ------------------------------------------------------------------------------------------------
+
+struct MatHeights {
+    const int* hts;
+    long long wy0;
+    __device__ __forceinline__ uint32_t operator()(uint32_t, int x, int y, int z) const {
+        long long dl = (long long)hts[(x + 1) * kTile + (z + 1)] - (wy0 + y);
+        dl = dl > 16 ? 16 : dl;
+        return block_id((int)dl);
+    }
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kT, kCtasPerSm)
+k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const RegionDev r,
+              const int32_t* __restrict__ heights, uint32_t* __restrict__ counts, const u64* __restrict__ offsets,
+              float* __restrict__ out, u64 capacity, u64* __restrict__ total) {
+    __shared__ MeshSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (EMIT) load_tables(sm, tb);
+    const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
+    for (int colw = blockIdx.x; colw < ncols; colw += gridDim.x) {
+        const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
+        __syncthreads();  // previous column's readers of sm.hts / sm.red are done
+        int cmax = INT32_MIN, hmin = INT32_MAX;
+        for (int i = tid; i < kTileN; i += kT) {
+            const int xi = i / kTile, zi = i - xi * kTile;
+            const int gx = ix * 32 + xi - 1, gz = iz * 32 + zi - 1;  // region voxel coordinates, >= -1
+            const int cix = (gx + 32) / 32 - 1, ciz = (gz + 32) / 32 - 1;
+            int h = kHeightAbsent;
+            if (cix >= 0 && cix < r.ncx && ciz >= 0 && ciz < r.ncz)
+                h = __ldg(heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA + (gx & 31) * 32 + (gz & 31));
+            sm.hts[i] = h;
+            hmin = min(hmin, h);
+            if (xi >= 1 && xi <= 32 && zi >= 1 && zi <= 32) cmax = max(cmax, h);
+        }
+        cmax = __reduce_max_sync(0xffffffffu, cmax);
+        hmin = __reduce_min_sync(0xffffffffu, hmin);
+        if (lane == 0) { sm.red[0][warp] = cmax; sm.red[1][warp] = hmin; }
+        __syncthreads();
+        cmax = sm.red[0][0]; hmin = sm.red[1][0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { cmax = max(cmax, sm.red[0][i]); hmin = min(hmin, sm.red[1][i]); }
+
+        for (int iy = 0; iy < r.ncy; ++iy) {
+            const size_t chunk = (size_t)colw * r.ncy + iy;  // slab-relative chunk index
+            const int cy = r.cy0 + iy;
+            const long long wy0 = (long long)cy * 32;
+            // block-uniform early outs: centre all air, or the whole 34^3 neighbourhood solid
+            const bool empty = (long long)cmax <= wy0;
+            const bool buried = (long long)hmin >= wy0 + 33 && iy > 0 && iy < r.ncy - 1;
+            if (empty || buried) {
+                if (!EMIT && tid == 0) counts[chunk] = 0;
+                continue;
+            }
+            u64 off = 0;
+            if (EMIT) {
+                off = offsets[chunk];
+                const u64 span = ((u64)counts[chunk] + 3ULL) & ~3ULL;
+                if (off + span > capacity) {
+                    if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
+                    continue;
+                }
+            }
+            __syncthreads();  // previous chunk's readers of sm.occ are done
+            for (int i = tid; i < kTileN; i += kT) {
+                long long d = (long long)sm.hts[i] - (wy0 - 1);  // solid voxels at tile bits 0..33
+                d = d < 0 ? 0 : (d > 34 ? 34 : d);
+                u64 v = (d >= 34) ? 0x3FFFFFFFFULL : ((1ULL << d) - 1ULL);
+                if (iy == 0) v &= ~1ULL;                 // chunk below is outside the region: absent
+                if (iy == r.ncy - 1) v &= ~(1ULL << 33);  // chunk above absent
+                sm.occ[i] = v;
+            }
+            if (EMIT && tid == 32) sm.rng_seed = siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
+            __syncthreads();
+            const MatHeights mat{sm.hts, wy0};
+            const uint32_t q = mesh_tile<EMIT>(sm, mat, (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32, mats,
+                                               EMIT ? out + off * 25ULL : nullptr);
+            if (!EMIT && tid == 0) counts[chunk] = q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// counts -> offsets.  Each chunk's span is its count rounded up to 4 instances.  Three small
+// kernels (tile sums, scan of tile sums, offsets); no atomics, deterministic.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanT = 256;
+constexpr int kScanPer = 8;
+constexpr int kScanTile = kScanT * kScanPer;
+
+__device__ __forceinline__ u64 block_sum_u64(u64 v, u64* s_tmp) {
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    u64 t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_tmp[i];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(kScanT) k_tile_sums(const uint32_t* __restrict__ counts, size_t n,
+                                                       u64* __restrict__ tile_span, u64* __restrict__ tile_quads) {
+    __shared__ u64 s_tmp[8];
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanPer;
+    u64 span = 0, quads = 0;
+#pragma unroll
+    for (int e = 0; e < kScanPer; ++e) {
+        if (base + e < n) {
+            const uint32_t c = counts[base + e];
+            quads += c;
+            span += ((u64)c + 3ULL) & ~3ULL;
+        }
+    }
+    span = block_sum_u64(span, s_tmp);
+    quads = block_sum_u64(quads, s_tmp);
+    if (threadIdx.x == 0) { tile_span[blockIdx.x] = span; tile_quads[blockIdx.x] = quads; }
+}
+
+// single CTA: exclusive scan of tile spans in place; totals to total[0] (span) and total[1] (quads)
+__global__ void __launch_bounds__(1024) k_scan_sums(u64* __restrict__ tile_span, const u64* __restrict__ tile_quads,
+                                                     size_t ntiles, u64* __restrict__ total) {
+    __shared__ u64 s_w[32];
+    __shared__ u64 s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    u64 quads = 0;
+    __syncthreads();
+    for (size_t b0 = 0; b0 < ntiles; b0 += 1024) {
+        const size_t i = b0 + tid;
+        const u64 v = i < ntiles ? tile_span[i] : 0;
+        if (i < ntiles) quads += tile_quads[i];
+        u64 s = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += t;
+        }
+        if (lane == 31) s_w[warp] = s;
+        __syncthreads();
+        u64 wbase = 0;
+        for (int k = 0; k < warp; ++k) wbase += s_w[k];
+        const u64 carry = s_carry;
+        if (i < ntiles) tile_span[i] = carry + wbase + s - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + wbase + s;
+        __syncthreads();
+    }
+    quads = block_sum_u64(quads, s_w);
+    if (tid == 0) { total[0] = s_carry; total[1] = quads; }
+}
+
+__global__ void __launch_bounds__(kScanT) k_offsets(const uint32_t* __restrict__ counts, size_t n,
+                                                     const u64* __restrict__ tile_base, u64* __restrict__ offsets) {
+    __shared__ u64 s_w[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)tid * kScanPer;
+    u64 sp[kScanPer];
+    u64 mine = 0;
+#pragma unroll
+    for (int e = 0; e < kScanPer; ++e) {
+        sp[e] = (base + e < n) ? (((u64)counts[base + e] + 3ULL) & ~3ULL) : 0ULL;
+        mine += sp[e];
+    }
+    u64 s = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += t;
+    }
+    if (lane == 31) s_w[warp] = s;
+    __syncthreads();
+    u64 run = tile_base[blockIdx.x] + s - mine;
+    for (int k = 0; k < warp; ++k) run += s_w[k];
+#pragma unroll
+    for (int e = 0; e < kScanPer; ++e) {
+        if (base + e < n) offsets[base + e] = run;
+        run += sp[e];
+    }
+}
+
+int g_num_sms = 0;
+
+}  // namespace
+
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        g_num_sms = v;
+    }
+    return g_num_sms;
+}
+
+cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_materials, uint32_t* d_bitmaps,
+                        uint32_t* d_summary, uint64_t* d_total) {
+    if (n == 0) return cudaSuccess;
+    size_t grid = (size_t)num_sms() * 8;
+    if (grid > n) grid = n;
+    k_pack<<<(unsigned)grid, kT, 0, s>>>(d_ids, n, n_materials, d_bitmaps, d_summary, (u64*)d_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
+                            const hb_chunk_pt* d_pts, size_t n, const uint16_t* d_ids, const int32_t* d_nbr,
+                            const uint32_t* d_bitmaps, const uint32_t* d_summary, uint32_t* d_counts,
+                            const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity, uint64_t* d_total) {
+    if (n == 0) return cudaSuccess;
+    size_t grid = (size_t)num_sms() * kCtasPerSm;
+    if (grid > n) grid = n;
+    if (emit)
+        k_mesh_ids<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, d_pts, n, d_ids, d_nbr, d_bitmaps, d_summary, d_counts,
+                                                       (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total);
+    else
+        k_mesh_ids<false><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, d_pts, n, d_ids, d_nbr, d_bitmaps, d_summary, d_counts,
+                                                        (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
+                               const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
+                               const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
+                               uint64_t* d_total) {
+    const size_t ncols = (size_t)(r.ix_end - r.ix_begin) * r.ncz;
+    if (ncols == 0 || r.ncy == 0) return cudaSuccess;
+    size_t grid = (size_t)num_sms() * kCtasPerSm;
+    if (grid > ncols) grid = ncols;
+    if (emit)
+        k_mesh_region<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
+                                                          (float*)d_out, capacity, (u64*)d_total);
+    else
+        k_mesh_region<false><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
+                                                           (float*)d_out, capacity, (u64*)d_total);
+    return cudaGetLastError();
+}
+
+size_t scan_workspace_bytes(size_t n) {
+    const size_t ntiles = (n + kScanTile - 1) / kScanTile;
+    return 2 * (ntiles + 1) * sizeof(u64);
+}
+
+cudaError_t launch_scan(cudaStream_t s, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* d_ws,
+                        uint64_t* d_total) {
+    if (n == 0) return cudaMemsetAsync(d_total, 0, 2 * sizeof(u64), s);
+    const size_t ntiles = (n + kScanTile - 1) / kScanTile;
+    u64* tile_span = (u64*)d_ws;
+    u64* tile_quads = tile_span + ntiles + 1;
+    k_tile_sums<<<(unsigned)ntiles, kScanT, 0, s>>>(d_counts, n, tile_span, tile_quads);
+    k_scan_sums<<<1, 1024, 0, s>>>(tile_span, tile_quads, ntiles, (u64*)d_total);
+    k_offsets<<<(unsigned)ntiles, kScanT, 0, s>>>(d_counts, n, tile_span, (u64*)d_offsets);
+    return cudaGetLastError();
+}
+
+}  // namespace hb

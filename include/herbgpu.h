@@ -1,0 +1,198 @@
+/*
+ * herbgpu.h -- C ABI of libherbgpu.so: herbolution's chunk pipeline (terrain generation +
+ * chunk meshing) as hand-written sm_100a CUDA.  This is the drop-in boundary: plain pointers
+ * and sizes, no C++/torch types.  A Rust host binds it with a ~100-line `extern "C"` block
+ * (INTEGRATION.md); the Python mirror in herbolution_b200/ binds it with ctypes.
+ *
+ * Reference citations are relative to the herbolution source tree.
+ *
+ * Conventions
+ *   - chunk = 32^3 voxels (lib/src/world.rs:4-7); voxel index L = x*1024 + z*32 + y
+ *     (lib/src/vector.rs:1274-1276).
+ *   - block id: u16, 0 = air (Option<PaletteMaterialId>::None), k = palette index k-1
+ *     (server/src/chunk/material.rs:215-226).  Generated terrain uses 1 = stone, 2 = dirt,
+ *     3 = grass (server/src/generator/mod.rs:64-72).
+ *   - face order / bit: East(+x)=0, West(-x)=1, Up(+y)=2, Down(-y)=3, North(+z)=4, South(-z)=5
+ *     (lib/src/spatial/face.rs:13-25,118-123).
+ *   - every call returns HB_OK (0) or a negative hb_status; nothing unwinds across the ABI;
+ *     hb_last_error() gives a thread-local message.
+ *   - one hb_ctx per GPU (one process or one host thread per GPU); calls on one ctx are
+ *     serialised by an internal mutex, so rayon workers may share it.
+ *   - there is NO CPU fallback: without a CUDA device hb_create fails with HB_ERR_CUDA.
+ */
+#ifndef HERBGPU_H
+#define HERBGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_CHUNK_LENGTH 32
+#define HB_CHUNK_AREA 1024
+#define HB_CHUNK_VOLUME 32768
+#define HB_MAX_MATERIALS 16
+#define HB_MAX_COLORS 8
+/* Chunk coordinates must satisfy |c| <= HB_MAX_CHUNK_COORD so that world block coordinates are
+ * exact in f32, as the reference's tile walk assumes (crates/simd-noise/src/noise/f32.rs:87-112). */
+#define HB_MAX_CHUNK_COORD 262143
+
+typedef enum hb_status {
+    HB_OK = 0,
+    HB_ERR_INVALID = -1,   /* bad argument (null pointer, unknown material id, ...) */
+    HB_ERR_CUDA = -2,      /* CUDA runtime error, or no device */
+    HB_ERR_CAPACITY = -3,  /* output buffer too small; *out_total holds the required size */
+    HB_ERR_RANGE = -4,     /* chunk coordinate outside +-HB_MAX_CHUNK_COORD */
+    HB_ERR_NOMEM = -5
+} hb_status;
+
+typedef struct hb_ctx hb_ctx;
+
+/* == lib::point::ChunkPt (repr of Vec3<i32>), lib/src/point.rs:34-35 */
+typedef struct hb_chunk_pt { int32_t x, y, z; } hb_chunk_pt;
+
+/* == client Instance3d, client/src/video/world/vertex.rs:41-51: 100 bytes, 4-byte aligned */
+typedef struct hb_instance3d {
+    float model[16];  /* model_0..model_3 (columns) */
+    float rgba[4];
+    uint32_t light;
+    float ao[4];
+} hb_instance3d;
+
+/* == PaletteCube = Cube<Option<PaletteMaterialId>>, server/src/chunk/cube.rs:5-10 (repr(C)), 8 bytes */
+typedef struct hb_palette_cube {
+    uint16_t material;
+    uint16_t _pad;
+    uint32_t flags;   /* CubeFlags: bit0 opaque tag, bits1..6 faces (cube.rs:27-72) */
+} hb_palette_cube;
+
+/* A box of chunks: cx in [cx0,cx0+ncx), cz in [cz0,cz0+ncz), cy in [cy0,cy0+ncy).
+ * Chunk index inside a region = ((ix*ncz)+iz)*ncy+iy.  Chunks outside the region are ABSENT:
+ * border faces toward them are emitted and AO probes into them read "empty", exactly like
+ * unloaded chunks in the reference (client/src/world/chunk.rs:158-174,225-236). */
+typedef struct hb_region { int32_t cx0, cz0, ncx, ncz, cy0, ncy; } hb_region;
+
+/* ---- lifetime ---- */
+int hb_create(int device, hb_ctx **out);
+void hb_destroy(hb_ctx *ctx);
+const char *hb_last_error(void);
+const char *hb_version(void);
+
+/* World parameters; defaults are the reference's hard-coded values
+ * (server/src/generator/mod.rs:103-108): freq 0.001, 6 octaves, lacunarity 2.0, gain 0.6.
+ * seed is GenerationParams::seed (i64). */
+int hb_set_world(hb_ctx *ctx, int64_t seed, float freq, int32_t octaves, float lacunarity, float gain);
+
+/* Palette colours, Material::texture (server/src/chunk/material.rs:27-71): material id m (1-based)
+ * has n_colors[m-1] colours, rgba[(m-1)*HB_MAX_COLORS + c][4].  Default = stone, dirt, grass. */
+int hb_set_materials(hb_ctx *ctx, int32_t n_materials, const int32_t *n_colors, const float *rgba);
+
+/* Pinned host memory for full-speed async copies (optional; any host pointer is accepted). */
+int hb_host_alloc(hb_ctx *ctx, size_t bytes, void **out);
+int hb_host_free(hb_ctx *ctx, void *p);
+
+/* ---- generation ---- */
+
+/* Replaces GenerationParams::get_noise (server/src/generator/mod.rs:98-111) for n chunk columns.
+ * cols_xz: n x {cx, cz}.  out_noise: n x 1024 f32, index x + z*32 (the crate's tile order,
+ * crates/simd-noise/src/noise/f32.rs:69-129).  out_heights (nullable): n x 1024 i32,
+ * h = trunc(noise*32) (generator/mod.rs:79), index x*32 + z. */
+int hb_noise_tiles(hb_ctx *ctx, const int32_t *cols_xz, size_t n, float *out_noise, int32_t *out_heights);
+
+/* get_3d_noise (crates/simd-noise/src/noise/f32.rs:131-198) with FbmNoise: nx*ny*nz samples starting
+ * at (sx,sy,sz), step 1, multiplied by freq[3]; out index x + y*nx + z*nx*ny.  Uses the ctx's seed,
+ * octaves, lacunarity, gain. */
+int hb_noise_fbm3d(hb_ctx *ctx, float sx, float sy, float sz, int32_t nx, int32_t ny, int32_t nz,
+                   const float *freq3, float *out);
+
+/* Replaces ChunkGenerator::request/dequeue + GenerationParams::generate
+ * (server/src/generator/mod.rs:32-48,63-95) for a batch of n chunks.
+ * out_ids: n x 32768 u16.  out_cubes (nullable): n x 32768 hb_palette_cube = CubeMesh::data right
+ * after generate() (in-chunk face flags as CubeMesh::set leaves them, server/src/chunk/mesh.rs:125-232;
+ * cross-chunk culling not yet applied).  out_noise (nullable): n x 1024 f32 as hb_noise_tiles. */
+int hb_generate(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, uint16_t *out_ids,
+                hb_palette_cube *out_cubes, float *out_noise);
+
+/* ---- meshing ---- */
+
+/* Host helper (no GPU work): out[i*27 + (dx+1)*9 + (dy+1)*3 + (dz+1)] = index of chunk pts[i]+(dx,dy,dz)
+ * in pts, or -1.  Same shell order as create_chunk_shell (client/src/world/chunk.rs:158-174). */
+int hb_build_neighbor_index(const hb_chunk_pt *pts, size_t n, int32_t *out);
+
+/* Replaces the remesh loop of client ChunkMap::update + generate_mesh
+ * (client/src/world/chunk.rs:66-75,176-276) together with the server-side face culling it relies on
+ * (CubeMesh::set in-chunk flags, cull_shared_faces across borders: server/src/chunk/mesh.rs:76-232).
+ * ids: n x 32768 u16.  neighbor_index: n x 27 as above (-1 = absent chunk).
+ * Output: chunk i's instances are out[out_offsets[i] .. out_offsets[i]+out_counts[i]) in the
+ * reference's emission order (ascending L, then face order).  out_offsets[i] is a multiple of 4;
+ * the gap after each chunk is zero-filled.  *out_total = instances spanned (incl. gaps).
+ * If out_capacity (in instances) is too small nothing is written to `out`, *out_total holds the
+ * requirement and HB_ERR_CAPACITY is returned (out may be NULL with capacity 0 to query). */
+int hb_mesh(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, const uint16_t *ids,
+            const int32_t *neighbor_index, hb_instance3d *out, uint64_t out_capacity,
+            uint64_t *out_offsets, uint32_t *out_counts, uint64_t *out_total);
+
+/* ---- fused generate + mesh of a region ---- */
+
+/* Sink for hb_generate_mesh_region: called once per slab (a contiguous range of region chunk
+ * indices [first_chunk, first_chunk+n_chunks)), in order, from the calling thread.  Pointers are
+ * pinned host buffers owned by the library and valid only during the call.  offsets are relative
+ * to `instances`.  ids is NULL unless want_ids. */
+typedef void (*hb_region_sink)(void *user, uint64_t first_chunk, uint64_t n_chunks,
+                               const uint64_t *offsets, const uint32_t *counts,
+                               const hb_instance3d *instances, uint64_t n_instances,
+                               const uint16_t *ids);
+
+/* Generate and mesh every chunk of `region` without a block-array round trip; results stream back
+ * through pinned double-buffered async copies.  Equivalent to hb_generate + hb_mesh over the same
+ * chunk set.  total_* (nullable) receive the sums. */
+int hb_generate_mesh_region(hb_ctx *ctx, const hb_region *region, int want_ids,
+                            hb_region_sink sink, void *user,
+                            uint64_t *total_chunks, uint64_t *total_quads);
+
+/* ---- device-resident pipeline (kernel-only measurement, chaining with other CUDA work) ----
+ * A plan owns the device buffers for region chunks with ix in [ix_begin, ix_end).  Stages only
+ * ENQUEUE kernels on `stream` (a cudaStream_t passed as void*; NULL = the ctx stream). */
+typedef struct hb_region_plan hb_region_plan;
+enum {
+    HB_STAGE_HEIGHTS = 1,  /* noise -> heights tiles */
+    HB_STAGE_COUNT = 2,    /* visible faces per chunk */
+    HB_STAGE_SCAN = 4,     /* exclusive scan -> offsets */
+    HB_STAGE_EMIT = 8,     /* write hb_instance3d */
+    HB_STAGE_FILL = 16,    /* write u16 block ids (plan created with want_ids) */
+    HB_STAGE_ALL_MESH = 15
+};
+/* quad_capacity 0 = size the instance buffer by running HEIGHTS+COUNT+SCAN once (synchronous). */
+int hb_region_plan_create(hb_ctx *ctx, const hb_region *region, int32_t ix_begin, int32_t ix_end,
+                          uint64_t quad_capacity, int want_ids, hb_region_plan **out);
+void hb_region_plan_destroy(hb_region_plan *plan);
+int hb_region_plan_enqueue(hb_region_plan *plan, int stages, void *stream);
+/* Synchronises `stream`, then reports totals and device pointers (any out pointer may be NULL). */
+int hb_region_plan_result(hb_region_plan *plan, void *stream, uint64_t *n_chunks, uint64_t *total_quads,
+                          uint64_t *total_span, const hb_instance3d **d_instances,
+                          const uint64_t **d_offsets, const uint32_t **d_counts,
+                          const uint16_t **d_ids, const int32_t **d_heights);
+/* Number of kernel launches a given stage mask enqueues (for launch accounting). */
+int hb_region_plan_launches(const hb_region_plan *plan, int stages);
+/* Blocking device->host copy of plan / hb_dev_* results (synchronises the ctx device). */
+int hb_dev_download(hb_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes);
+
+/* Device-pointer forms of hb_generate / hb_mesh: all pointers are device memory, kernels are
+ * enqueued on `stream`, nothing is synchronised.
+ * hb_dev_generate: d_cols_xz (ncol x 2), d_col_of_chunk (n), d_heights (ncol x 1024 i32 scratch/out). */
+int hb_dev_generate(hb_ctx *ctx, void *stream, const int32_t *d_cols_xz, size_t ncol,
+                    const hb_chunk_pt *d_pts, const int32_t *d_col_of_chunk, size_t n,
+                    int32_t *d_heights, float *d_noise, uint16_t *d_ids, hb_palette_cube *d_cubes);
+/* hb_dev_mesh: d_workspace of hb_dev_mesh_workspace_bytes(n) bytes.  d_total[0] = span (instances),
+ * d_total[1] = quads, d_total[2] = error flags (1 = capacity exceeded, 2 = unknown material id). */
+size_t hb_dev_mesh_workspace_bytes(size_t n);
+int hb_dev_mesh(hb_ctx *ctx, void *stream, const hb_chunk_pt *d_pts, size_t n, const uint16_t *d_ids,
+                const int32_t *d_neighbor_index, void *d_workspace, hb_instance3d *d_out,
+                uint64_t out_capacity, uint64_t *d_offsets, uint32_t *d_counts, uint64_t *d_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HERBGPU_H */

@@ -1,0 +1,137 @@
+/*
+ * hb_oracle.h -- CPU restatement ("oracle") of herbolution's chunk pipeline.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (herbolution_b200/,
+ * include/, libherbgpu.so) may include, link or call this.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * use it, and only as the checker / the CPU arm.
+ *
+ * PARITY PINNING STATUS
+ *   The reference (Rust nightly, un-vendored deps) cannot be compiled here and
+ *   ships no tests, golden vectors or fixtures for this path.
+ *   => "parity unpinned" by the reference itself.  What IS pinned:
+ *     - SipHash-1-3 (std DefaultHasher) against CPython's siphash13 with a
+ *       zero key (tests/test_oracle_hash.py);
+ *     - the literal CubeMesh::set / cull_shared_faces transcription against
+ *       the closed-form visibility rule (tests/test_oracle_gen.py);
+ *     - noise against the survey's independent float32 numpy restatement
+ *       values and structural invariants.
+ *   wyrand (fastrand 2.3.0, un-vendored, Cargo.lock:712-715) is restated from
+ *   its published algorithm and is unpinned: the colour channel is therefore
+ *   compared/reported separately from geometry everywhere.
+ *
+ * Every function cites the reference file:line (relative to /root/reference)
+ * it follows.
+ */
+#ifndef HB_ORACLE_H
+#define HB_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBO_CHUNK_LENGTH 32      /* lib/src/world.rs:5 */
+#define HBO_CHUNK_AREA 1024      /* lib/src/world.rs:6 */
+#define HBO_CHUNK_VOLUME 32768   /* lib/src/world.rs:7 */
+
+/* Face order == CubeFace discriminants, lib/src/spatial/face.rs:13-25 */
+enum { HBO_EAST = 0, HBO_WEST, HBO_UP, HBO_DOWN, HBO_NORTH, HBO_SOUTH };
+
+/* server/src/generator/mod.rs:98-111 (hard-coded there; parameters here) */
+typedef struct hbo_world {
+    int64_t seed;
+    float freq;        /* 0.001 */
+    int32_t octaves;   /* 6 */
+    float lacunarity;  /* 2.0 */
+    float gain;        /* 0.6 */
+    int32_t fused;     /* 1: AVX2/NEON column (true FMA at neg_mul_add),
+                          0: SSE/Scalar column (unfused)  simd/ops/f32.rs:141-162 */
+} hbo_world;
+
+/* == Cube<Option<PaletteMaterialId>>, server/src/chunk/cube.rs:5-10 (repr(C)) */
+typedef struct hbo_cube {
+    uint16_t material; /* 0 = None, else NonZeroU16(index+1) material.rs:215-226 */
+    uint16_t pad;
+    uint32_t flags;    /* CubeFlags, cube.rs:27-89 */
+} hbo_cube;
+
+/* == Instance3d, client/src/video/world/vertex.rs:41-51 (100 bytes) */
+typedef struct hbo_instance {
+    float model[16];
+    float rgba[4];
+    uint32_t light;
+    float ao[4];
+} hbo_instance;
+
+/* server/src/chunk/material.rs:17-71: colours per material; index 0 unused (air) */
+#define HBO_MAX_COLORS 8
+typedef struct hbo_material {
+    int32_t n_colors;
+    float rgba[HBO_MAX_COLORS][4];
+} hbo_material;
+
+typedef struct hbo_palette {
+    int32_t n_materials;           /* ids 1..n */
+    hbo_material mat[16];          /* mat[id-1] */
+} hbo_palette;
+
+/* == CubeMesh, server/src/chunk/mesh.rs:12-19 (palette implicit) */
+typedef struct hbo_cube_mesh {
+    int32_t pos[3];
+    hbo_cube data[HBO_CHUNK_VOLUME];
+    uint64_t n_updated;            /* updated_positions.len() */
+} hbo_cube_mesh;
+
+/* ---- noise (crates/simd-noise) ---- */
+float hbo_simplex2(float x, float y, int64_t seed, int fused);
+float hbo_fbm2(float x, float y, const hbo_world *w);
+void  hbo_noise_tile2(const hbo_world *w, int32_t cx, int32_t cz, float out[HBO_CHUNK_AREA]);
+float hbo_simplex3(float x, float y, float z, int64_t seed);
+float hbo_fbm3(float x, float y, float z, const hbo_world *w);
+/* get_3d_noise_helper_f32: out index x + y*X + z*X*Y */
+void  hbo_noise_tile3(const hbo_world *w, float sx, float sy, float sz,
+                      int nx, int ny, int nz, float fx, float fy, float fz, float *out);
+
+/* ---- generation ---- */
+int32_t hbo_height(float noise);                                /* generator/mod.rs:79 */
+void hbo_default_palette(hbo_palette *p);                       /* material.rs:27-61 */
+void hbo_mesh_init(hbo_cube_mesh *m, int32_t cx, int32_t cy, int32_t cz); /* mesh.rs:22-30 */
+void hbo_mesh_set(hbo_cube_mesh *m, int x, int y, int z, uint16_t material); /* mesh.rs:125-186 */
+void hbo_generate_literal(const hbo_world *w, hbo_cube_mesh *m); /* generator/mod.rs:63-95 via set() */
+/* closed form: ids only (index L = x*1024+z*32+y) */
+void hbo_generate_ids(const hbo_world *w, int32_t cx, int32_t cy, int32_t cz, uint16_t *ids);
+/* closed form of the PaletteCube image after generate() (in-chunk flags only) */
+void hbo_cubes_from_ids(const uint16_t *ids, hbo_cube *out);
+void hbo_cull_shared_faces(hbo_cube_mesh *a, hbo_cube_mesh *b); /* mesh.rs:76-123 */
+
+/* ---- meshing ---- */
+uint64_t hbo_siphash13_chunk(int32_t x, int32_t y, int32_t z);  /* client/src/world/chunk.rs:182-184 */
+uint64_t hbo_wyrand_next(uint64_t *state);                      /* fastrand 2.3.0 Rng::gen_u64 */
+float hbo_wyrand_f32(uint64_t *state);                          /* fastrand 2.3.0 Rng::f32 */
+void hbo_face_matrix(int face, float out12[12]);                /* face.rs:60-69 + rotation.rs + vertex.rs:53-58 */
+float hbo_ao_value(int k);                                      /* chunk.rs:271-275 */
+/* literal generate_mesh: shell[27] of cube arrays (NULL = absent); flags are READ from cubes.
+ * Returns number of instances; writes at most cap. client/src/world/chunk.rs:176-223 */
+size_t hbo_generate_mesh(const hbo_cube *const shell[27], const int32_t center_pos[3],
+                         const hbo_palette *pal, hbo_instance *out, size_t cap);
+/* closed form: shell of u16 id arrays; visibility recomputed from ids */
+size_t hbo_mesh_ids(const uint16_t *const shell[27], const int32_t center_pos[3],
+                    const hbo_palette *pal, hbo_instance *out, size_t cap);
+
+/* ---- region pipeline (CPU baseline driver; one chunk per task like the reference) ----
+ * chunk index = ((ix*ncz)+iz)*ncy+iy.  literal!=0: set()-path + cull_shared_faces + flag mesher.
+ * counts[n] receives per-chunk quad counts; if out!=NULL instances are concatenated in
+ * chunk-index order (cap instances).  Returns total quads.  secs[3] = gen, cull, mesh wall s. */
+uint64_t hbo_region_pipeline(const hbo_world *w, const hbo_palette *pal,
+                             int32_t cx0, int32_t cz0, int32_t ncx, int32_t ncz,
+                             int32_t cy0, int32_t ncy, int literal, int threads,
+                             uint32_t *counts, hbo_instance *out, size_t cap,
+                             uint16_t *ids_out, double secs[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,380 @@
+"""GPU parity tests: libherbgpu (through its C ABI) against the CPU oracle on identical inputs.
+
+Bar: noise bit-exact (tolerance stated by north_star is 1e-5 relative; we assert 0 ulp and report),
+block ids / PaletteCube images / quad sets bit-exact INCLUDING order.  The colour channel (wyrand,
+unpinned -- see oracle/hb_oracle.h) is asserted separately from geometry.
+"""
+import numpy as np
+import pytest
+
+import herbolution_b200 as hb
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SEEDS = [0, 5, 12345, -7]
+
+
+def split_chunks(out):
+    return [out["instances"][int(o):int(o) + int(n)] for o, n in zip(out["offsets"], out["counts"])]
+
+
+def assert_instances_equal(got, want, what=""):
+    assert got.shape == want.shape, f"{what}: quad count {got.shape[0]} != {want.shape[0]}"
+    geo = ("model", "light", "ao")
+    for f in geo:
+        assert got[f].tobytes() == want[f].tobytes(), f"{what}: geometry field {f} differs"
+    assert got["rgba"].tobytes() == want["rgba"].tobytes(), f"{what}: colour channel differs (geometry matched)"
+
+
+def region_points(reg):
+    cx0, cz0, ncx, ncz, cy0, ncy = reg
+    return hb.Region(cx0, cz0, ncx, ncz, cy0, ncy).chunk_points()
+
+
+# ---------------------------------------------------------------- noise
+@pytest.mark.parametrize("seed", SEEDS)
+def test_noise_tiles_bit_exact(ctx, seed):
+    ctx.set_world(seed)
+    rng = np.random.default_rng(seed & 0xFFFF)
+    cols = np.concatenate([
+        np.array([[0, 0], [-1, -1], [3, -5], [-512, 511], [262143, -262143], [-262143, 262143]]),
+        rng.integers(-4000, 4000, size=(26, 2)),
+    ]).astype(np.int32)
+    noise, heights = ctx.noise_tiles(cols, want_heights=True)
+    w = O.world(seed)
+    max_rel = 0.0
+    for i, (cx, cz) in enumerate(cols):
+        ref = O.noise_tile2(w, int(cx), int(cz))
+        rel = np.abs(noise[i] - ref) / np.maximum(np.abs(ref), 1e-30)
+        max_rel = max(max_rel, float(rel.max()))
+        assert noise[i].view(np.uint32).tolist() == ref.view(np.uint32).tolist(), f"column {cx},{cz} max rel {rel.max()}"
+        h = O.heights_from_noise(ref).reshape(32, 32).T.ravel()  # noise index x+z*32 -> heights index x*32+z
+        assert (heights[i] == h).all()
+    assert max_rel <= 1e-5  # the tolerance north_star states; achieved: 0
+
+
+def test_noise_custom_params(ctx):
+    ctx.set_world(99, freq=0.0123, octaves=3, lacunarity=2.5, gain=0.45)
+    w = O.world(99, freq=0.0123, octaves=3, lacunarity=2.5, gain=0.45)
+    noise = ctx.noise_tiles([[7, -9], [100, 100]])
+    for i, (cx, cz) in enumerate([(7, -9), (100, 100)]):
+        assert noise[i].tobytes() == O.noise_tile2(w, cx, cz).tobytes()
+    ctx.set_world(0)
+
+
+def test_noise_range_error(ctx):
+    with pytest.raises(hb.HerbGpuError) as e:
+        ctx.noise_tiles([[262144, 0]])
+    assert e.value.code == -4
+
+
+def test_noise_fbm3d(ctx):
+    for seed in (0, 5):
+        ctx.set_world(seed)
+        w = O.world(seed)
+        got = ctx.noise_fbm3d((-17.0, 40.0, 3.0), (33, 9, 5), (0.01, 0.02, 0.013))
+        ref = O.noise_tile3(w, (-17.0, 40.0, 3.0), (33, 9, 5), (0.01, 0.02, 0.013))
+        assert got.tobytes() == ref.tobytes()
+    with pytest.raises(hb.HerbGpuError):
+        ctx.noise_fbm3d((0.5, 0, 0), (4, 4, 4), (0.1, 0.1, 0.1))
+    ctx.set_world(0)
+
+
+# ---------------------------------------------------------------- generation
+@pytest.mark.parametrize("seed", [0, 5])
+def test_generate_c2_full(ctx, seed):
+    """BASELINE config 2: 4096 chunks (32x32 columns, cy in [-2,2)), ids bit-exact vs the oracle."""
+    ctx.set_world(seed)
+    pts = region_points((-16, -16, 32, 32, -2, 4))
+    out = ctx.generate(pts, want_noise=True)
+    w = O.world(seed)
+    p3 = np.stack([pts["x"], pts["y"], pts["z"]], axis=1)
+    ref = O.generate_ids(w, p3)
+    mism = int((out["ids"] != ref).sum())
+    assert mism == 0, f"{mism} voxels differ"
+    # threshold-adjacent voxels (north_star asks for the count): |v*32 - round| tiny
+    v32 = out["noise"].astype(np.float64) * 32.0
+    near = int((np.abs(v32 - np.round(v32)) <= 1e-5 * 32).sum())
+    print(f"seed {seed}: 0 id mismatches; {near} noise samples within 1e-5*32 of an integer height")
+    ctx.set_world(0)
+
+
+def test_generate_cubes_vs_literal_set_path(ctx):
+    """PaletteCube image == state left by CubeMesh::set (server/src/chunk/mesh.rs:125-232)."""
+    ctx.set_world(0)
+    w = O.world(0)
+    pts = [(0, 0, 0), (0, -1, 0), (1, 0, -1), (-3, 1, 2), (5, -1, 5), (5, 0, 5), (-8, -2, 7), (31, 1, -31)]
+    out = ctx.generate(pts, want_cubes=True)
+    for i, p in enumerate(pts):
+        m = O.generate_literal(w, p)
+        ref = O.mesh_cubes(m)
+        assert out["cubes"][i].tobytes() == ref.tobytes(), f"chunk {p}"
+        assert (out["ids"][i] == ref["material"]).all()
+
+
+def test_generate_empty_and_dups(ctx):
+    assert ctx.generate(np.zeros((0, 3), dtype=np.int64))["ids"].shape == (0, 32768)
+    out = ctx.generate([(2, 0, 2), (2, 0, 2), (2, -1, 2)])
+    assert (out["ids"][0] == out["ids"][1]).all()
+    with pytest.raises(hb.HerbGpuError) as e:
+        ctx.generate([(0, 0, 10**6)])
+    assert e.value.code == -4
+
+
+def test_generator_mirror(ctx):
+    params = hb.GenerationParams(5, ctx=ctx)
+    gen = hb.ChunkGenerator(params)
+    want = [(0, 0, 0), (1, -1, 2)]
+    for p in want:
+        gen.request(p)
+    meshes = list(gen.dequeue())
+    assert [tuple(m.position) for m in meshes] == want
+    ref = O.generate_ids(O.world(5), want)
+    for m, r in zip(meshes, ref):
+        assert (m.ids == r).all()
+    assert list(gen.dequeue()) == []
+    assert params.get_noise((3, 4)).tobytes() == O.noise_tile2(O.world(5), 3, 4).tobytes()
+    ctx.set_world(0)
+
+
+# ---------------------------------------------------------------- meshing
+@pytest.mark.parametrize("seed", [0, 5])
+def test_mesh_vs_literal_pipeline(ctx, seed):
+    """gen (set path) + cull_shared_faces + generate_mesh from flags, vs hb_mesh from ids."""
+    ctx.set_world(seed)
+    reg = (-3, -3, 6, 6, -3, 6)
+    ref = O.region_pipeline(O.world(seed), reg, literal=True, threads=8, want_ids=True)
+    pts = region_points(reg)
+    out = ctx.mesh(pts, ref["ids"])
+    assert (out["counts"] == ref["counts"]).all()
+    assert (out["offsets"] % 4 == 0).all()
+    got = np.concatenate(split_chunks(out))
+    assert_instances_equal(got, ref["instances"], "region")
+    ctx.set_world(0)
+
+
+def toggled_ids(reg, seed, p=0.01, nmat=3):
+    ids = O.region_pipeline(O.world(seed), reg, literal=False, threads=8, want_instances=False, want_ids=True)["ids"]
+    rng = np.random.default_rng(1234 + seed)
+    flip = rng.random(ids.shape) < p
+    mats = rng.integers(1, nmat + 1, size=ids.shape).astype(np.uint16)
+    out = ids.copy()
+    out[flip & (ids != 0)] = 0
+    out[flip & (ids == 0)] = mats[flip & (ids == 0)]
+    return out
+
+
+def oracle_mesh_all(pts, ids, nbr, pal=None):
+    res = []
+    for i in range(len(pts)):
+        shell = [ids[j] if j >= 0 else None for j in nbr[i]]
+        res.append(O.mesh_ids(shell, (pts["x"][i], pts["y"][i], pts["z"][i]), pal))
+    return res
+
+
+def test_mesh_toggled_caves(ctx):
+    """BASELINE config 3 variant: heightmap ids with 1% of voxels toggled (overhangs / caves)."""
+    reg = (-2, 1, 4, 4, -2, 3)
+    ids = toggled_ids(reg, 0)
+    pts = region_points(reg)
+    nbr = ctx.build_neighbor_index(pts)
+    out = ctx.mesh(pts, ids, nbr)
+    ref = oracle_mesh_all(pts, ids, nbr)
+    for i, (g, r) in enumerate(zip(split_chunks(out), ref)):
+        assert_instances_equal(g, r, f"chunk {i}")
+
+
+def test_mesh_sparse_set_and_custom_neighbors(ctx):
+    """Arbitrary chunk sets: missing neighbours are absent (faces emitted, AO empty)."""
+    rng = np.random.default_rng(7)
+    pts_all = region_points((0, 0, 3, 3, 0, 3))
+    keep = rng.random(len(pts_all)) < 0.6
+    keep[13] = True
+    pts = pts_all[keep]
+    ids = (rng.random((len(pts), 32768)) < 0.5).astype(np.uint16) * rng.integers(1, 4, size=(len(pts), 32768)).astype(np.uint16)
+    nbr = ctx.build_neighbor_index(pts)
+    out = ctx.mesh(pts, ids, nbr)
+    ref = oracle_mesh_all(pts, ids, nbr)
+    for i, (g, r) in enumerate(zip(split_chunks(out), ref)):
+        assert_instances_equal(g, r, f"chunk {i}")
+
+
+def test_mesh_edge_cases(ctx):
+    one = np.array([(0, 0, 0)])
+    # empty batch
+    e = ctx.mesh(np.zeros((0, 3), dtype=np.int64), np.zeros((0, 32768), dtype=np.uint16))
+    assert e["instances"].shape == (0,)
+    # all air
+    a = ctx.mesh(one, np.zeros((1, 32768), dtype=np.uint16))
+    assert a["counts"][0] == 0 and a["instances"].shape == (0,)
+    # all solid, alone: 6 * 1024 boundary faces
+    s = ctx.mesh(one, np.full((1, 32768), 2, dtype=np.uint16))
+    assert s["counts"][0] == 6144
+    assert_instances_equal(split_chunks(s)[0], O.mesh_ids([None] * 13 + [np.full(32768, 2, np.uint16)] + [None] * 13, (0, 0, 0)))
+    # 3x3x3 all solid: the centre chunk is fully buried
+    pts = region_points((0, 0, 3, 3, 0, 3))
+    b = ctx.mesh(pts, np.full((27, 32768), 1, dtype=np.uint16))
+    assert b["counts"][13] == 0 and b["counts"].sum() == 54 * 1024
+    # 3-D checkerboard: the maximum, 16384 voxels * 6 faces = 98304 quads (many descriptor rounds)
+    L = np.arange(32768)
+    x, z, y = L >> 10, (L >> 5) & 31, L & 31
+    chk = (((x + y + z) & 1) == 0).astype(np.uint16) * 3
+    c = ctx.mesh(one, chk[None, :])
+    assert c["counts"][0] == 98304
+    assert_instances_equal(split_chunks(c)[0], O.mesh_ids([None] * 13 + [chk] + [None] * 13, (0, 0, 0)))
+
+
+def test_mesh_errors(ctx):
+    ids = np.full((1, 32768), 9, dtype=np.uint16)  # material 9 with a 3-entry palette
+    with pytest.raises(hb.HerbGpuError) as e:
+        ctx.mesh([(0, 0, 0)], ids)
+    assert e.value.code == -1
+    with pytest.raises(hb.HerbGpuError) as e:
+        ctx.mesh([(0, 0, 0)], np.zeros((1, 32768), np.uint16), np.full((1, 27), 5, dtype=np.int32))
+    assert e.value.code == -1
+
+
+def test_mesh_custom_materials(ctx):
+    colors = [[(0.1, 0.2, 0.3, 1.0)], [(0.5, 0.5, 0.5, 1.0), (0.6, 0.6, 0.6, 1.0), (0.7, 0.7, 0.7, 1.0), (0.8, 0.8, 0.8, 0.5),
+                                        (0.9, 0.9, 0.9, 0.25)]]
+    ctx.set_materials(colors)
+    try:
+        rng = np.random.default_rng(3)
+        ids = (rng.random((1, 32768)) < 0.3).astype(np.uint16) * rng.integers(1, 3, size=(1, 32768)).astype(np.uint16)
+        out = ctx.mesh([(4, -2, 9)], ids)
+        ref = O.mesh_ids([None] * 13 + [ids[0]] + [None] * 13, (4, -2, 9), O.make_palette(colors))
+        assert_instances_equal(split_chunks(out)[0], ref)
+    finally:
+        ctx.set_materials([[(0.5, 0.5, 0.5, 1.0), (0.6, 0.6, 0.6, 1.0), (0.7, 0.7, 0.7, 1.0)],
+                           [(0.4, 0.3, 0.2, 1.0), (0.5, 0.4, 0.3, 1.0), (0.6, 0.5, 0.4, 1.0)],
+                           [(0.1, 0.8, 0.1, 1.0), (0.2, 0.9, 0.2, 1.0), (0.3, 1.0, 0.3, 1.0)]])
+
+
+def test_mesher_mirror(ctx):
+    ctx.set_world(0)
+    reg = (0, 0, 2, 2, -1, 2)
+    pts = region_points(reg)
+    ids = ctx.generate(pts)["ids"]
+    cm = hb.ChunkMap(ctx)
+    for p, a in zip(pts, ids):
+        cm.insert((p["x"], p["y"], p["z"]), a)
+    assert cm.update() == len(pts)
+    ref = O.region_pipeline(O.world(0), reg, literal=False, threads=4, want_ids=False)
+    off = np.concatenate([[0], np.cumsum(ref["counts"].astype(np.int64))])
+    for i, p in enumerate(pts):
+        key = hb.ChunkPt(int(p["x"]), int(p["y"]), int(p["z"]))
+        assert_instances_equal(cm.meshes[key], ref["instances"][off[i]:off[i + 1]], str(key))
+    # single-chunk drop-in signature
+    shell = hb.create_chunk_shell(cm.map, hb.ChunkPt(0, 0, 0))
+    inst = []
+    hb.generate_mesh(ctx, shell, inst)
+    assert_instances_equal(inst[0], cm.meshes[hb.ChunkPt(0, 0, 0)])
+
+
+@pytest.mark.parametrize("seed", [0, 5])
+def test_mesh_c3_full(ctx, seed):
+    """BASELINE config 3: 4096 pre-generated chunks incl. cross-chunk borders, bit-exact quad set."""
+    ctx.set_world(seed)
+    reg = (-16, -16, 32, 32, -2, 4)
+    pts = region_points(reg)
+    ids = ctx.generate(pts)["ids"]
+    out = ctx.mesh(pts, ids)
+    ref = O.region_pipeline(O.world(seed), reg, literal=False, threads=8)
+    assert (out["counts"] == ref["counts"]).all()
+    got = np.concatenate(split_chunks(out))
+    assert_instances_equal(got, ref["instances"], "C3")
+    ctx.set_world(0)
+
+
+# ---------------------------------------------------------------- fused region
+def collect_region(ctx, region, want_ids=False):
+    chunks = {}
+
+    def sink(first, off, cnt, inst, ids):
+        for k in range(len(cnt)):
+            o, n = int(off[k]), int(cnt[k])
+            chunks[first + k] = (inst[o:o + n].copy(), None if ids is None else ids[k].copy())
+
+    tot = ctx.generate_mesh_region(region, want_ids=want_ids, sink=sink)
+    return tot, chunks
+
+
+@pytest.mark.parametrize("seed,reg", [(0, (-3, -3, 6, 6, -3, 6)), (5, (10, -20, 5, 3, -1, 2)), (0, (0, 0, 1, 1, 0, 1))])
+def test_region_fused_vs_oracle(ctx, seed, reg):
+    ctx.set_world(seed)
+    ref = O.region_pipeline(O.world(seed), reg, literal=True, threads=8, want_ids=True)
+    tot, chunks = collect_region(ctx, hb.Region(*reg), want_ids=True)
+    n = reg[2] * reg[3] * reg[5]
+    assert tot["chunks"] == n and tot["quads"] == ref["total"]
+    off = np.concatenate([[0], np.cumsum(ref["counts"].astype(np.int64))])
+    for i in range(n):
+        inst, ids = chunks[i]
+        assert_instances_equal(inst, ref["instances"][off[i]:off[i + 1]], f"chunk {i}")
+        assert (ids == ref["ids"][i]).all()
+    ctx.set_world(0)
+
+
+def test_region_plan_slabs_equal_whole(ctx):
+    """A region processed as x-slabs (how it is sharded across GPUs) equals the whole region."""
+    ctx.set_world(0)
+    region = hb.Region(-4, -2, 7, 4, -3, 6)
+    _, whole = collect_region(ctx, region)
+    ncz, ncy = region.ncz, region.ncy
+    for (a, b) in [(0, 3), (3, 4), (4, 7)]:
+        plan = ctx.region_plan(region, ix_begin=a, ix_end=b)
+        plan.enqueue(hb.STAGE_ALL_MESH)
+        res = plan.result()
+        n = res["n_chunks"]
+        assert n == (b - a) * ncz * ncy
+        off = ctx.download(res["d_offsets"], np.uint64, n)
+        cnt = ctx.download(res["d_counts"], np.uint32, n)
+        inst = ctx.download(res["d_instances"], hb.INSTANCE_DTYPE, res["span"])
+        for k in range(n):
+            g = inst[int(off[k]):int(off[k]) + int(cnt[k])]
+            assert_instances_equal(g, whole[a * ncz * ncy + k][0], f"slab {a}:{b} chunk {k}")
+        plan.close()
+
+
+def test_region_c4_properties(ctx):
+    """BASELINE config 4 at a reduced but still multi-slab size (64x64 columns x 6): size-independent
+    properties -- quad total equals the sum over independently meshed sub-blocks' interior-consistent
+    counts is not available, so we check: (1) fused == hb_generate + hb_mesh on a random sample of
+    columns with their full neighbourhoods, (2) every offset is 4-aligned and spans do not overlap."""
+    ctx.set_world(0)
+    region = hb.Region(-32, -32, 64, 64, -3, 6)
+    counts = {}
+    keep = {}
+    rng = np.random.default_rng(11)
+    sample = set(int(v) for v in rng.integers(0, region.n_chunks, size=64))
+
+    def sink(first, off, cnt, inst, ids):
+        assert (off % 4 == 0).all()
+        ends = off + ((cnt.astype(np.uint64) + 3) // 4) * 4
+        assert (ends[:-1] <= off[1:]).all() and (len(inst) == 0 or ends[-1] <= len(inst))
+        for k in range(len(cnt)):
+            counts[first + k] = int(cnt[k])
+            if first + k in sample:
+                keep[first + k] = inst[int(off[k]):int(off[k]) + int(cnt[k])].copy()
+
+    tot = ctx.generate_mesh_region(region, sink=sink)
+    assert tot["chunks"] == region.n_chunks == len(counts)
+    assert tot["quads"] == sum(counts.values())
+    pts = region.chunk_points()
+    for c in sorted(sample):
+        # gather the 27-neighbourhood inside the region, generate + mesh it with the general path
+        ix, rem = divmod(c, region.ncz * region.ncy)
+        iz, iy = divmod(rem, region.ncy)
+        sel = []
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    jx, jy, jz = ix + dx, iy + dy, iz + dz
+                    if 0 <= jx < region.ncx and 0 <= jy < region.ncy and 0 <= jz < region.ncz:
+                        sel.append((jx * region.ncz + jz) * region.ncy + jy)
+        sub = pts[sel]
+        ids = ctx.generate(sub)["ids"]
+        out = ctx.mesh(sub, ids)
+        k = sel.index(c)
+        g = out["instances"][int(out["offsets"][k]):int(out["offsets"][k]) + int(out["counts"][k])]
+        assert_instances_equal(keep[c], g, f"chunk {c}")
