@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--columns", type=int, default=256, help="region is columns x columns chunk columns per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (rank 0, N=1 only anyway)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-API leg (profiling runs only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -277,21 +278,22 @@ def main():
         stats["span"] += len(inst)
         stats["chunks"] += len(cnt)
 
-    ctx.generate_mesh_region(reg, sink=sink)  # warm-up: pinned staging is allocated here
     e2e_steps = max(1, min(args.e2e_steps, steps))
-    stats["span"] = stats["chunks"] = 0
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.generate_mesh_region(reg, sink=sink)
-    torch.cuda.synchronize()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    d2h = (stats["span"] * 100 + stats["chunks"] * 12) / e2e_steps
-    e2e = {"value": total_chunks * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 24,
-           "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
-           "api": "hb_generate_mesh_region (C ABI, host sink, pinned double-buffered D2H)",
-           "note": "input is the 24-byte region descriptor; output is every Instance3d (100 B/quad) + offsets/counts"}
+    if not args.no_e2e:
+        ctx.generate_mesh_region(reg, sink=sink)  # warm-up: pinned staging is allocated here
+        stats["span"] = stats["chunks"] = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.generate_mesh_region(reg, sink=sink)
+        torch.cuda.synchronize()
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        d2h = (stats["span"] * 100 + stats["chunks"] * 12) / e2e_steps
+        e2e = {"value": total_chunks * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 24,
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
+               "api": "hb_generate_mesh_region (C ABI, host sink, pinned double-buffered D2H)",
+               "note": "input is the 24-byte region descriptor; output is every Instance3d (100 B/quad) + offsets/counts"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None

@@ -40,9 +40,9 @@ struct ColRegion {
 template <class Cols>
 __global__ void __launch_bounds__(kThreads) k_heights(WorldDev w, Cols cols, int32_t* __restrict__ heights,
                                                        float* __restrict__ noise) {
-    __shared__ __align__(16) uint8_t s_perm[256];
-    __shared__ int s_h[HB_CHUNK_AREA];
-    load_perm(s_perm);
+    __shared__ NoiseTables s_tab;
+    __shared__ int s_h[32][33];  // padded: the transposed store below is bank-conflict free
+    load_noise_tables(s_tab, w.seed_lo);
     const int col = blockIdx.x;
     int cx, cz;
     cols.get(col, cx, cz);
@@ -58,20 +58,20 @@ __global__ void __launch_bounds__(kThreads) k_heights(WorldDev w, Cols cols, int
         const int i = threadIdx.x + k * kThreads;
         const float x = __fadd_rn(start_x, __int2float_rn(i & 31));
         const float z = __fadd_rn(start_z, __int2float_rn(i >> 5));
-        v[k] = fbm2(s_perm, __fmul_rn(x, w.freq), __fmul_rn(z, w.freq), w);
+        v[k] = fbm2(s_tab, __fmul_rn(x, w.freq), __fmul_rn(z, w.freq), w);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int i = threadIdx.x + k * kThreads;
         if (noise) noise[(size_t)col * HB_CHUNK_AREA + i] = v[k];
-        s_h[(i & 31) * 32 + (i >> 5)] = height_from_noise(v[k]);
+        s_h[i & 31][i >> 5] = height_from_noise(v[k]);
     }
     __syncthreads();
     if (heights) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int i = threadIdx.x + k * kThreads;
-            heights[(size_t)col * HB_CHUNK_AREA + i] = s_h[i];
+            heights[(size_t)col * HB_CHUNK_AREA + i] = s_h[i >> 5][i & 31];
         }
     }
 }

@@ -16,9 +16,9 @@
 // in the reference's emission order (ascending L = x*1024+z*32+y, then face order) -- no atomics.
 //
 // Emission: visible faces -> 32-bit descriptors in shared memory (L | face<<15 | ao<<18), then one
-// thread per quad expands a descriptor to the 100-byte Instance3d in a shared staging buffer
-// (stride 25 words: bank-conflict free), and the CTA streams the staging buffer to HBM with
-// 128-bit coalesced stores.  Each chunk's output starts on a 4-instance (400 B) boundary so every
+// lane per quad expands a descriptor to the 100-byte Instance3d in a warp-private shared staging
+// buffer (stride 25 words: bank-conflict free), and one lane hands the 3200-byte window to the TMA
+// engine as a 1-D bulk shared->global copy (cp.async.bulk, SASS UBLKCP).  Each chunk's output starts on a 4-instance (400 B) boundary so every
 // vector store is 16-byte aligned.
 #include "common.cuh"
 
@@ -40,8 +40,9 @@ struct MeshSmem {
     __align__(16) float stage[kStageCap * 25];  // 25600 B
     uint32_t desc[kDescCap];                    // 8192 B
     int hts[kTileN];                            // 4624 B (region kernels: heights halo tile)
-    float face_mat[6][12];
+    __align__(16) float face_mat[6][12];
     float ao_lut[4];
+    __align__(16) int ao_tab[6][8];             // per face: 8 AO probes as (tile index offset)*4 + (bit offset + 1)
     uint32_t warp_tot[32];
     u64 rng_seed;
     int nbr[27];
@@ -86,29 +87,39 @@ __device__ __forceinline__ uint32_t block_id(int d) { return d > 6 ? 1u : (d > 1
 // vertex_ao, client/src/world/chunk.rs:251-253
 __device__ __forceinline__ uint32_t vao(uint32_t s1, uint32_t s2, uint32_t c) { return (s1 & s2) ? 3u : s1 + s2 + c; }
 
-// facial_ao (chunk.rs:255-276) for the face whose orthonormal_basis (lib/src/spatial/face.rs:84-93)
-// is u=(UX,UY,UZ), v=(VX,VY,VZ), n=(NX,NY,NZ); probes read the occupancy tile.
-template <int UX, int UY, int UZ, int VX, int VY, int VZ, int NX, int NY, int NZ>
-__device__ __forceinline__ uint32_t ao_bits(const u64* __restrict__ occ, int x, int y, int z) {
-#define HB_P(a, b)                                                                                  \
-    ((uint32_t)(occ[(x + 1 + NX + (a) * UX + (b) * VX) * kTile + (z + 1 + NZ + (a) * UZ + (b) * VZ)] >> \
-                (y + 1 + NY + (a) * UY + (b) * VY)) & 1u)
-    const uint32_t tl = HB_P(-1, -1), tc = HB_P(0, -1), tr = HB_P(1, -1);
-    const uint32_t ml = HB_P(-1, 0), mr = HB_P(1, 0);
-    const uint32_t bl = HB_P(-1, 1), bc = HB_P(0, 1), br = HB_P(1, 1);
-#undef HB_P
-    return vao(ml, tc, tl) | (vao(ml, bc, bl) << 2) | (vao(mr, tc, tr) << 4) | (vao(mr, bc, br) << 6);
+// facial_ao (chunk.rs:255-276), table driven so that one thread per quad can evaluate it without
+// divergence.  orthonormal_basis (lib/src/spatial/face.rs:84-93) gives (u, v, n) per face; the 8
+// probes are position + n + a*u + b*v for (a, b) in the order tl, tc, tr, ml, mr, bl, bc, br.
+__device__ const signed char kBasis[6][9] = {
+    // ux uy uz  vx vy vz  nx ny nz
+    {0, 0, -1, 0, 1, 0, 1, 0, 0},   // East  (-Z,  Y,  X)
+    {0, 0, 1, 0, 1, 0, -1, 0, 0},   // West  ( Z,  Y, -X)
+    {1, 0, 0, 0, 0, -1, 0, 1, 0},   // Up    ( X, -Z,  Y)
+    {1, 0, 0, 0, 0, 1, 0, -1, 0},   // Down  ( X,  Z, -Y)
+    {1, 0, 0, 0, 1, 0, 0, 0, 1},    // North ( X,  Y,  Z)
+    {-1, 0, 0, 0, 1, 0, 0, 0, -1},  // South (-X,  Y, -Z)
+};
+__device__ const signed char kProbeAB[8][2] = {{-1, -1}, {0, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
+
+// entry = (dx*kTile + dz)*4 + (dy + 1); decode: index offset = e >> 2 (arithmetic), bit offset = (e & 3) - 1
+__device__ __forceinline__ int ao_tab_entry(int f, int p) {
+    const int a = kProbeAB[p][0], b = kProbeAB[p][1];
+    const int dx = kBasis[f][6] + a * kBasis[f][0] + b * kBasis[f][3];
+    const int dy = kBasis[f][7] + a * kBasis[f][1] + b * kBasis[f][4];
+    const int dz = kBasis[f][8] + a * kBasis[f][2] + b * kBasis[f][5];
+    return (dx * kTile + dz) * 4 + (dy + 1);
 }
 
-__device__ __forceinline__ uint32_t ao_for_face(const u64* occ, int f, int x, int y, int z) {
-    switch (f) {
-        case 0: return ao_bits<0, 0, -1, 0, 1, 0, 1, 0, 0>(occ, x, y, z);   // East  (-Z,  Y,  X)
-        case 1: return ao_bits<0, 0, 1, 0, 1, 0, -1, 0, 0>(occ, x, y, z);   // West  ( Z,  Y, -X)
-        case 2: return ao_bits<1, 0, 0, 0, 0, -1, 0, 1, 0>(occ, x, y, z);   // Up    ( X, -Z,  Y)
-        case 3: return ao_bits<1, 0, 0, 0, 0, 1, 0, -1, 0>(occ, x, y, z);   // Down  ( X,  Z, -Y)
-        case 4: return ao_bits<1, 0, 0, 0, 1, 0, 0, 0, 1>(occ, x, y, z);    // North ( X,  Y,  Z)
-        default: return ao_bits<-1, 0, 0, 0, 1, 0, 0, 0, -1>(occ, x, y, z); // South (-X,  Y, -Z)
-    }
+// Returns the four vertex_ao values (2 bits each: bl, tl, br, tr order of chunk.rs:266-269).
+__device__ __forceinline__ uint32_t ao_bits(const u64* __restrict__ occ, const int* __restrict__ tab, int x, int y, int z) {
+    const int base = (x + 1) * kTile + (z + 1);
+    const int4 t0 = *reinterpret_cast<const int4*>(tab);
+    const int4 t1 = *reinterpret_cast<const int4*>(tab + 4);
+#define HB_P(e) ((uint32_t)(occ[base + ((e) >> 2)] >> (y + ((e) & 3))) & 1u)
+    const uint32_t tl = HB_P(t0.x), tc = HB_P(t0.y), tr = HB_P(t0.z), ml = HB_P(t0.w);
+    const uint32_t mr = HB_P(t1.x), bl = HB_P(t1.y), bc = HB_P(t1.z), br = HB_P(t1.w);
+#undef HB_P
+    return vao(ml, tc, tl) | (vao(ml, bc, bl) << 2) | (vao(mr, tc, tr) << 4) | (vao(mr, bc, br) << 6);
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -120,6 +131,32 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
+// ---- TMA 1-D bulk copy shared -> global (cp.async.bulk; SASS: UBLKCP).  dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// The six visible-face masks (bit y) of column (x, z) of the occupancy tile.
+__device__ __forceinline__ void column_masks(const u64* __restrict__ occ, int x, int z, uint32_t m[6]) {
+    const u64* o = occ + (x + 1) * kTile + (z + 1);
+    const u64 C = o[0];
+    const uint32_t cen = (uint32_t)(C >> 1);
+    if (cen) {
+        m[0] = cen & ~(uint32_t)(o[kTile] >> 1);   // East : (x+1, y, z) empty
+        m[1] = cen & ~(uint32_t)(o[-kTile] >> 1);  // West
+        m[2] = cen & ~(uint32_t)(C >> 2);          // Up   : (x, y+1, z)
+        m[3] = cen & ~(uint32_t)C;                 // Down : (x, y-1, z)
+        m[4] = cen & ~(uint32_t)(o[1] >> 1);       // North: (x, y, z+1)
+        m[5] = cen & ~(uint32_t)(o[-1] >> 1);      // South
+    } else {
+        m[0] = m[1] = m[2] = m[3] = m[4] = m[5] = 0u;
+    }
+}
+
 // Meshes the occupancy tile in sm.occ (already built and synchronised).  Column mapping: thread t
 // owns columns (x = k*8 + t/32, z = t%32), k = 0..3, so a warp reads 32 consecutive tile words.
 // Returns the chunk's quad count (all threads).  EMIT additionally writes the instances at `out`
@@ -128,27 +165,12 @@ template <bool EMIT, class MatFn>
 __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, int bx, int by, int bz,
                                               const MaterialsDev* __restrict__ mats, float* __restrict__ out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t m[4][6], cnt[4], incl[4];
+    uint32_t cnt[4], incl[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int x = k * 8 + warp, z = lane;
-        const u64* o = sm.occ + (x + 1) * kTile + (z + 1);
-        const u64 C = o[0];
-        const uint32_t cen = (uint32_t)(C >> 1);
-        uint32_t c = 0;
-        if (cen) {
-            m[k][0] = cen & ~(uint32_t)(o[kTile] >> 1);   // East : (x+1, y, z) empty
-            m[k][1] = cen & ~(uint32_t)(o[-kTile] >> 1);  // West
-            m[k][2] = cen & ~(uint32_t)(C >> 2);          // Up   : (x, y+1, z)
-            m[k][3] = cen & ~(uint32_t)C;                 // Down : (x, y-1, z)
-            m[k][4] = cen & ~(uint32_t)(o[1] >> 1);       // North: (x, y, z+1)
-            m[k][5] = cen & ~(uint32_t)(o[-1] >> 1);      // South
-#pragma unroll
-            for (int f = 0; f < 6; ++f) c += __popc(m[k][f]);
-        } else {
-#pragma unroll
-            for (int f = 0; f < 6; ++f) m[k][f] = 0;
-        }
+        uint32_t m[6];
+        column_masks(sm.occ, k * 8 + warp, lane, m);
+        const uint32_t c = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]) + __popc(m[5]);
         cnt[k] = c;
         incl[k] = warp_incl_scan(c, lane);
         if (lane == 31) sm.warp_tot[k * 8 + warp] = incl[k];
@@ -166,24 +188,24 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
         base[k] = __shfl_sync(0xffffffffu, ws, idx) - __shfl_sync(0xffffffffu, wt, idx) + incl[k] - cnt[k];
     }
 
+    float* const ws = sm.stage + warp * (32 * 25);  // warp-private staging: 32 quads = 3200 B
     for (uint32_t d0 = 0; d0 < total; d0 += kDescCap) {
-        // (a) visible faces of my columns -> descriptors, in emission order
+        // (a) visible faces of my columns -> descriptors (L | face << 15), in emission order
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             uint32_t o = base[k];
             if (cnt[k] == 0 || o >= d0 + kDescCap || o + cnt[k] <= d0) continue;
-            const int x = k * 8 + warp, z = lane;
-            uint32_t any = m[k][0] | m[k][1] | m[k][2] | m[k][3] | m[k][4] | m[k][5];
+            const uint32_t Lc = (uint32_t)(((k * 8 + warp) << 10) | (lane << 5));
+            uint32_t m[6];
+            column_masks(sm.occ, k * 8 + warp, lane, m);  // cheap to recompute; keeps registers free
+            uint32_t any = m[0] | m[1] | m[2] | m[3] | m[4] | m[5];
             while (any) {
                 const int y = __ffs(any) - 1;
                 any &= any - 1;
 #pragma unroll
                 for (int f = 0; f < 6; ++f) {
-                    if ((m[k][f] >> y) & 1u) {
-                        if (o >= d0 && o < d0 + kDescCap) {
-                            const uint32_t ao = ao_for_face(sm.occ, f, x, y, z);
-                            sm.desc[o - d0] = (uint32_t)((x << 10) | (z << 5) | y) | ((uint32_t)f << 15) | (ao << 18);
-                        }
+                    if ((m[f] >> y) & 1u) {
+                        if (o >= d0 && o < d0 + kDescCap) sm.desc[o - d0] = Lc | (uint32_t)y | ((uint32_t)f << 15);
                         ++o;
                     }
                 }
@@ -191,46 +213,53 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
         }
         __syncthreads();
         const uint32_t nd = min((uint32_t)kDescCap, total - d0);
-        // (b) expand descriptors window by window and stream them out
-        for (uint32_t w0 = 0; w0 < nd; w0 += kStageCap) {
-            const uint32_t nw = min((uint32_t)kStageCap, nd - w0);
+        // (b) each warp expands windows of 32 descriptors (one quad per lane: AO, colour, matrix) into its
+        //     private staging buffer and streams them out; no block-level barrier inside this loop
+        for (uint32_t q0 = warp * 32u; q0 < nd; q0 += (kT / 32) * 32u) {
+            const uint32_t nw = min(32u, nd - q0);
             const uint32_t nw4 = (nw + 3u) & ~3u;
-            if ((uint32_t)tid < nw4) {
-                float* s = sm.stage + tid * 25;
-                if ((uint32_t)tid < nw) {
-                    const uint32_t d = sm.desc[w0 + tid];
-                    const uint32_t L = d & 0x7FFFu, f = (d >> 15) & 7u, ao = (d >> 18) & 0xFFu;
-                    const int x = L >> 10, z = (L >> 5) & 31, y = L & 31;
-                    const uint32_t id = mat(L, x, y, z);
-                    // Material::get_color(perms[face]) (server/src/chunk/material.rs:67-71)
-                    const float p = wyrand_f32_at(sm.rng_seed, 6u * L + f);
-                    const int nc = mats->n_colors[id - 1];
-                    const int ci = __float2int_rz(__fmul_rn(__int2float_rn(nc > 0 ? nc - 1 : 0), p));
-                    const float4 rgba = *reinterpret_cast<const float4*>(mats->rgba[id - 1][ci]);
+            float* sq = ws + lane * 25;
+            if ((uint32_t)lane < nw) {
+                const uint32_t d = sm.desc[q0 + lane];
+                const uint32_t L = d & 0x7FFFu, f = d >> 15;
+                const int x = L >> 10, z = (L >> 5) & 31, y = L & 31;
+                const uint32_t ao = ao_bits(sm.occ, sm.ao_tab[f], x, y, z);
+                const uint32_t id = mat(L, x, y, z);
+                // Material::get_color(perms[face]) (server/src/chunk/material.rs:67-71)
+                const float p = wyrand_f32_at(sm.rng_seed, 6u * L + f);
+                const int nc = __ldg(&mats->n_colors[id - 1]);
+                const int ci = __float2int_rz(__fmul_rn(__int2float_rn(nc > 0 ? nc - 1 : 0), p));
+                const float4 rgba = __ldg(reinterpret_cast<const float4*>(mats->rgba[id - 1][ci]));
+                const float4* fm = reinterpret_cast<const float4*>(sm.face_mat[f]);
+                const float4 m0 = fm[0], m1 = fm[1], m2 = fm[2];
+                sq[0] = m0.x; sq[1] = m0.y; sq[2] = m0.z; sq[3] = m0.w;
+                sq[4] = m1.x; sq[5] = m1.y; sq[6] = m1.z; sq[7] = m1.w;
+                sq[8] = m2.x; sq[9] = m2.y; sq[10] = m2.z; sq[11] = m2.w;
+                sq[12] = __int2float_rn(bx + x);  // (chunk_position + position).cast::<f32>()
+                sq[13] = __int2float_rn(by + y);
+                sq[14] = __int2float_rn(bz + z);
+                sq[15] = 1.0f;
+                sq[16] = rgba.x; sq[17] = rgba.y; sq[18] = rgba.z; sq[19] = rgba.w;
+                sq[20] = __uint_as_float(0u);  // light = 0 (chunk.rs:207)
+                sq[21] = sm.ao_lut[ao & 3u];
+                sq[22] = sm.ao_lut[(ao >> 2) & 3u];
+                sq[23] = sm.ao_lut[(ao >> 4) & 3u];
+                sq[24] = sm.ao_lut[(ao >> 6) & 3u];
+            } else if ((uint32_t)lane < nw4) {
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) s[i] = sm.face_mat[f][i];
-                    s[12] = __int2float_rn(bx + x);  // (chunk_position + position).cast::<f32>()
-                    s[13] = __int2float_rn(by + y);
-                    s[14] = __int2float_rn(bz + z);
-                    s[15] = 1.0f;
-                    s[16] = rgba.x; s[17] = rgba.y; s[18] = rgba.z; s[19] = rgba.w;
-                    s[20] = __uint_as_float(0u);  // light = 0 (chunk.rs:207)
-                    s[21] = sm.ao_lut[ao & 3u];
-                    s[22] = sm.ao_lut[(ao >> 2) & 3u];
-                    s[23] = sm.ao_lut[(ao >> 4) & 3u];
-                    s[24] = sm.ao_lut[(ao >> 6) & 3u];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 25; ++i) s[i] = 0.0f;
-                }
+                for (int i = 0; i < 25; ++i) sq[i] = 0.0f;
             }
-            __syncthreads();
-            const uint32_t nvec = nw4 * 25u / 4u;
-            float4* dst = reinterpret_cast<float4*>(out + (size_t)(d0 + w0) * 25u);
-            const float4* src = reinterpret_cast<const float4*>(sm.stage);
-            for (uint32_t i = tid; i < nvec; i += kT) __stcs(dst + i, src[i]);
-            __syncthreads();
+            // hand the window to the TMA engine: one bulk shared->global copy (UBLKCP) per warp instead of
+            // 200 LDS.128 + STG.128 through the LSU.  Generic-proxy writes must be fenced for the async proxy.
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(out + (size_t)(d0 + q0) * 25u, ws, nw4 * 100u);
+                bulk_wait_read();  // the staging buffer may be rewritten once the engine has read it
+            }
+            __syncwarp();
         }
+        if (d0 + kDescCap < total) __syncthreads();  // descriptors are rewritten in the next round
     }
     }  // if constexpr (EMIT)
     return total;
@@ -239,6 +268,10 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
 __device__ __forceinline__ void load_tables(MeshSmem& sm, const MeshTables& tb) {
     for (int i = threadIdx.x; i < 72; i += kT) (&sm.face_mat[0][0])[i] = (&tb.face_mat[0][0])[i];
     if (threadIdx.x < 4) sm.ao_lut[threadIdx.x] = tb.ao_lut[threadIdx.x];
+    if (threadIdx.x >= 64 && threadIdx.x < 112) {
+        const int e = threadIdx.x - 64;
+        sm.ao_tab[e >> 3][e & 7] = ao_tab_entry(e >> 3, e & 7);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -385,6 +418,7 @@ k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
                                            EMIT ? out + off * 25ULL : nullptr);
         if (!EMIT && tid == 0) counts[chunk] = q;
     }
+    if (EMIT) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -471,6 +505,7 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
             if (!EMIT && tid == 0) counts[chunk] = q;
         }
     }
+    if (EMIT) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -28,33 +28,43 @@ __device__ const uint8_t kPerm[256] = {
     181, 199, 106, 157, 184, 84,  204, 176, 115, 121, 50,  45,  127, 4,   150, 254, 138, 236, 205, 93,  222, 114,
     67,  29,  24,  72,  243, 141, 128, 195, 78,  66,  215, 61,  156, 180};
 
-// Cooperative load of the permutation table into shared memory (call from all threads, then sync).
-__device__ __forceinline__ void load_perm(uint8_t* s_perm) {
-    for (int i = threadIdx.x; i < 64; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(s_perm)[i] = reinterpret_cast<const uint32_t*>(kPerm)[i];
-}
-
 // simplex_32.rs:6-15
 #define HB_F2 0.36602540378f
 #define HB_G2 0.2113248654f
 #define HB_G22 (0.2113248654f * 2.0f)
 
-// functions/gradient_32.rs:13-30.  Returns gx*x + gy*y with the reference's two multiplies and one
-// add.  mask.blendv(a, b) = mask ? b : a (simd/overloads.rs:588-591).
-__device__ __forceinline__ float grad2_dot(int seed_lo, int hash, float x, float y) {
+// functions/gradient_32.rs:13-30: the gradient (gx, gy) selected by a hash value.
+// mask.blendv(a, b) = mask ? b : a (simd/overloads.rs:588-591).
+__device__ __forceinline__ float2 grad2_of(int seed_lo, int hash) {
     const int h = (hash ^ seed_lo) & 7;
     const bool lt4 = h < 4;
     const float xm = lt4 ? 1.0f : 2.0f;
     const float ym = lt4 ? 2.0f : 1.0f;
     const bool b1 = (h & 1) == 0;
     const bool b2 = (h & 2) == 0;
-    const float gx = (lt4 ? b1 : b2) ? xm : -xm;  // 0.0 - m == -m exactly
-    const float gy = (lt4 ? b2 : b1) ? ym : -ym;
-    return __fadd_rn(__fmul_rn(gx, x), __fmul_rn(gy, y));
+    return make_float2((lt4 ? b1 : b2) ? xm : -xm,   // 0.0 - m == -m exactly
+                       (lt4 ? b2 : b1) ? ym : -ym);
+}
+
+// Shared-memory tables for the 2-D path: the permutation (256 B) and, per permutation slot, the
+// gradient it selects for this seed (G[i] = grad2(P[i]), 2 KB).  A corner's gradient is then two
+// dependent shared loads instead of a load plus ~12 select/logic instructions.
+struct NoiseTables {
+    __align__(16) uint8_t perm[256];
+    __align__(16) float2 grad[256];
+};
+
+// Cooperative table setup (call from all threads, then __syncthreads()).
+__device__ __forceinline__ void load_noise_tables(NoiseTables& t, int seed_lo) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int p = kPerm[i];
+        t.perm[i] = (uint8_t)p;
+        t.grad[i] = grad2_of(seed_lo, p);
+    }
 }
 
 // functions/simplex_32.rs:103-170 (value half of simplex_2d_deriv)
-__device__ __forceinline__ float simplex2(const uint8_t* __restrict__ P, float x, float y, int seed_lo) {
+__device__ __forceinline__ float simplex2(const NoiseTables& T, float x, float y) {
     const float s = __fmul_rn(HB_F2, __fadd_rn(x, y));
     const float ips = floorf(__fadd_rn(x, s));
     const float jps = floorf(__fadd_rn(y, s));
@@ -71,39 +81,44 @@ __device__ __forceinline__ float simplex2(const uint8_t* __restrict__ P, float x
     const float x2 = __fadd_rn(__fadd_rn(x0, -1.0f), HB_G22);
     const float y2 = __fadd_rn(__fadd_rn(y0, -1.0f), HB_G22);
 
-    const int ii = i & 0xff;
-    const int jj = j & 0xff;
-    const int gi0 = P[(ii + P[jj]) & 255];
-    const int gi1 = P[(ii + (xge ? 1 : 0) + P[(jj + (ygt ? 1 : 0)) & 255]) & 255];
-    const int gi2 = P[(ii + 1 + P[(jj + 1) & 255]) & 255];
+    // gi_k = P[(ii + di) + P[jj + dj]] (simplex_32.rs:137-141); indices are taken mod 256 because the
+    // reference's 512-entry table is the permutation twice
+    const int pj0 = T.perm[j & 255];
+    const int pj1 = T.perm[(j + 1) & 255];
+    const float2 g0 = T.grad[(i + pj0) & 255];
+    const float2 g1 = T.grad[(i + (xge ? 1 : 0) + (ygt ? pj1 : pj0)) & 255];
+    const float2 g2 = T.grad[(i + 1 + pj1) & 255];
 
     // neg_mul_add(a, b, c) = fma(-a, b, c): _mm256_fnmadd_ps (simd/ops/f32.rs:141-145)
     float t0 = __fmaf_rn(-y0, y0, __fmaf_rn(-x0, x0, 0.5f));
     float t1 = __fmaf_rn(-y1, y1, __fmaf_rn(-x1, x1, 0.5f));
     float t2 = __fmaf_rn(-y2, y2, __fmaf_rn(-x2, x2, 0.5f));
-    t0 = (t0 >= 0.0f) ? t0 : 0.0f;  // t &= t.cmp_gte(0)
-    t1 = (t1 >= 0.0f) ? t1 : 0.0f;
-    t2 = (t2 >= 0.0f) ? t2 : 0.0f;
+    // t &= t.cmp_gte(0): negative -> +0.  fmaxf(t, 0) differs only for t = -0 (keeps/loses the sign
+    // of zero), and t is squared next, so the result is identical.
+    t0 = fmaxf(t0, 0.0f);
+    t1 = fmaxf(t1, 0.0f);
+    t2 = fmaxf(t2, 0.0f);
 
     const float t20 = __fmul_rn(t0, t0), t40 = __fmul_rn(t20, t20);
     const float t21 = __fmul_rn(t1, t1), t41 = __fmul_rn(t21, t21);
     const float t22 = __fmul_rn(t2, t2), t42 = __fmul_rn(t22, t22);
 
-    const float n0 = __fmul_rn(t40, grad2_dot(seed_lo, gi0, x0, y0));
-    const float n1 = __fmul_rn(t41, grad2_dot(seed_lo, gi1, x1, y1));
-    const float n2 = __fmul_rn(t42, grad2_dot(seed_lo, gi2, x2, y2));
+    // g = gx*x + gy*y: two multiplies and one add, as the operator overloads do (never fused)
+    const float n0 = __fmul_rn(t40, __fadd_rn(__fmul_rn(g0.x, x0), __fmul_rn(g0.y, y0)));
+    const float n1 = __fmul_rn(t41, __fadd_rn(__fmul_rn(g1.x, x1), __fmul_rn(g1.y, y1)));
+    const float n2 = __fmul_rn(t42, __fadd_rn(__fmul_rn(g2.x, x2), __fmul_rn(g2.y, y2)));
     return __fmul_rn(__fadd_rn(n0, __fadd_rn(n1, n2)), 45.26450774985561631259f);
 }
 
 // functions/fbm_32.rs:18-31
-__device__ __forceinline__ float fbm2(const uint8_t* __restrict__ P, float x, float y, const WorldDev& w) {
-    float result = simplex2(P, x, y, w.seed_lo);
+__device__ __forceinline__ float fbm2(const NoiseTables& T, float x, float y, const WorldDev& w) {
+    float result = simplex2(T, x, y);
     float amp = 1.0f;
     for (int o = 1; o < w.octaves; ++o) {
         x = __fmul_rn(x, w.lacunarity);
         y = __fmul_rn(y, w.lacunarity);
         amp = __fmul_rn(amp, w.gain);
-        result = __fadd_rn(__fmul_rn(simplex2(P, x, y, w.seed_lo), amp), result);
+        result = __fadd_rn(__fmul_rn(simplex2(T, x, y), amp), result);
     }
     return result;
 }
