@@ -40,8 +40,9 @@ UNIT = "chunks/s"
 
 def region_for_rank(columns: int, rank: int, world: int):
     # global region: x in [-columns*world/2, +columns*world/2), z in [-columns/2, columns/2)
-    cx0 = -(columns * world) // 2 + rank * columns
-    return (cx0, -(columns // 2), columns, columns, CY0, NCY)
+    from herbolution_b200.sharding import weak_scaling_region
+    r = weak_scaling_region(columns, rank, world, CY0, NCY)
+    return (r.cx0, r.cz0, r.ncx, r.ncz, r.cy0, r.ncy)
 
 
 def cpu_sample_region(columns: int):
@@ -201,19 +202,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from herbolution_b200.sharding import reduce_max, reduce_sum
+
     def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return reduce_max(x, device="cuda")
 
     def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_sum(x, device="cuda")
 
     ctx = hb.Context(device=local_rank, seed=SEED)
     reg = hb.Region(*region_for_rank(cols, rank, world))

@@ -1,7 +1,6 @@
-"""Build libherbgpu.so (sm_100a CUDA, in-tree) and, for the tests/bench only, the CPU oracle.
+"""Build libherbgpu.so (sm_100a CUDA, in-tree).
 
-    python -m herbolution_b200.build            # both
-    python -m herbolution_b200.build --force
+    python -m herbolution_b200.build [--force]
 
 nvcc cross-compiles for sm_100a without a GPU.  -fmad=false is global: the noise path must not
 contract mul+add (only the six explicit __fmaf_rn sites fuse, see csrc/noise.cuh).
@@ -16,8 +15,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "herbolution_b200", "csrc")
 LIB = os.path.join(ROOT, "herbolution_b200", "libherbgpu.so")
-ORACLE_SRC = os.path.join(ROOT, "oracle", "hb_oracle.c")
-ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 
 CUDA_SOURCES = ["gen.cu", "mesh.cu", "api.cu"]
 CUDA_DEPS = CUDA_SOURCES + ["common.cuh", "noise.cuh", os.path.join("..", "..", "include", "herbgpu.h")]
@@ -25,13 +22,10 @@ CUDA_DEPS = CUDA_SOURCES + ["common.cuh", "noise.cuh", os.path.join("..", "..", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O2,-Wall",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden",
     "-Xptxas", "-v",
     "-shared", "-cudart", "static",
 ]
-
-ORACLE_FLAGS = ["-O2", "-std=gnu11", "-ffp-contract=off", "-mavx2", "-mfma", "-fPIC", "-shared", "-pthread",
-                "-Wall", "-Wextra"]
 
 
 def _nvcc() -> str:
@@ -64,21 +58,6 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_oracle(force: bool = False) -> str:
-    """The CPU restatement used by tests / smoke / bench's CPU arm only (never by the product)."""
-    deps = [ORACLE_SRC, os.path.join(ROOT, "oracle", "hb_oracle.h")]
-    if not force and not _stale(ORACLE_LIB, deps):
-        return ORACLE_LIB
-    os.makedirs(os.path.dirname(ORACLE_LIB), exist_ok=True)
-    cmd = ["gcc", *ORACLE_FLAGS, "-o", ORACLE_LIB, ORACLE_SRC, "-lm"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("gcc failed building the oracle")
-    return ORACLE_LIB
-
-
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_cuda(force=force, verbose=True))
-    print(build_oracle(force=force))

@@ -219,17 +219,27 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
             const uint32_t nw = min(32u, nd - q0);
             const uint32_t nw4 = (nw + 3u) & ~3u;
             float* sq = ws + lane * 25;
-            if ((uint32_t)lane < nw) {
+            const bool active = (uint32_t)lane < nw;
+            // register phase first: it overlaps the TMA engine still reading this warp's previous window
+            uint32_t f = 0, ao = 0;
+            int x = 0, y = 0, z = 0;
+            float4 rgba = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) {
                 const uint32_t d = sm.desc[q0 + lane];
-                const uint32_t L = d & 0x7FFFu, f = d >> 15;
-                const int x = L >> 10, z = (L >> 5) & 31, y = L & 31;
-                const uint32_t ao = ao_bits(sm.occ, sm.ao_tab[f], x, y, z);
+                const uint32_t L = d & 0x7FFFu;
+                f = d >> 15;
+                x = L >> 10; z = (L >> 5) & 31; y = L & 31;
+                ao = ao_bits(sm.occ, sm.ao_tab[f], x, y, z);
                 const uint32_t id = mat(L, x, y, z);
                 // Material::get_color(perms[face]) (server/src/chunk/material.rs:67-71)
                 const float p = wyrand_f32_at(sm.rng_seed, 6u * L + f);
                 const int nc = __ldg(&mats->n_colors[id - 1]);
                 const int ci = __float2int_rz(__fmul_rn(__int2float_rn(nc > 0 ? nc - 1 : 0), p));
-                const float4 rgba = __ldg(reinterpret_cast<const float4*>(mats->rgba[id - 1][ci]));
+                rgba = __ldg(reinterpret_cast<const float4*>(mats->rgba[id - 1][ci]));
+            }
+            if (lane == 0) bulk_wait_read();  // previous window of this warp has left the staging buffer
+            __syncwarp();
+            if (active) {
                 const float4* fm = reinterpret_cast<const float4*>(sm.face_mat[f]);
                 const float4 m0 = fm[0], m1 = fm[1], m2 = fm[2];
                 sq[0] = m0.x; sq[1] = m0.y; sq[2] = m0.z; sq[3] = m0.w;
@@ -253,11 +263,7 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
             // 200 LDS.128 + STG.128 through the LSU.  Generic-proxy writes must be fenced for the async proxy.
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                bulk_store(out + (size_t)(d0 + q0) * 25u, ws, nw4 * 100u);
-                bulk_wait_read();  // the staging buffer may be rewritten once the engine has read it
-            }
-            __syncwarp();
+            if (lane == 0) bulk_store(out + (size_t)(d0 + q0) * 25u, ws, nw4 * 100u);
         }
         if (d0 + kDescCap < total) __syncthreads();  // descriptors are rewritten in the next round
     }
@@ -436,6 +442,89 @@ struct MatHeights {
     }
 };
 
+// Stages the 34x34 heights halo tile of region column (ix, iz): the column's own 32x32 tile plus one
+// row/column from each of the 8 neighbouring columns; columns outside the region are ABSENT.
+// Also returns this thread's partial max over the centre and min over the whole tile.
+__device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int32_t* __restrict__ heights, int ix, int iz,
+                                                  int* __restrict__ hts, int& cmax, int& hmin) {
+    for (int i = threadIdx.x; i < kTileN; i += kT) {
+        const int xi = i / kTile, zi = i - xi * kTile;
+        const int gx = ix * 32 + xi - 1, gz = iz * 32 + zi - 1;  // region voxel coordinates, >= -1
+        const int cix = (gx + 32) / 32 - 1, ciz = (gz + 32) / 32 - 1;
+        int h = kHeightAbsent;
+        if (cix >= 0 && cix < r.ncx && ciz >= 0 && ciz < r.ncz)
+            h = __ldg(heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA + (gx & 31) * 32 + (gz & 31));
+        hts[i] = h;
+        hmin = min(hmin, h);
+        if (xi >= 1 && xi <= 32 && zi >= 1 && zi <= 32) cmax = max(cmax, h);
+    }
+}
+
+// Heightmap terrain, closed-form face count (the fused path's COUNT stage).  With solid(y) = y < h the
+// six mask popcounts of column_masks() collapse to interval arithmetic.  For a chunk layer starting at
+// world y = a, let r = clamp(h - a, 0, 32) be the column's solid voxels inside the chunk and rf the same
+// for the lateral neighbour f (absent neighbour -> 0).  Then
+//   side f : max(0, r - rf)          (y in [a, a+32) with y < h and y >= hf)
+//   up     : r > 0 and (h <= a + 32 or the chunk above is absent)
+//   down   : r > 0 and the chunk below is absent            (inside the terrain y-1 is always solid)
+// which is exactly what k_mesh_region<EMIT> emits from the occupancy tile (parity tests cover both).
+__global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const int32_t* __restrict__ heights,
+                                                      uint32_t* __restrict__ counts) {
+    __shared__ uint32_t s_part[8][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int colw = blockIdx.x;
+    const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
+    // heights relative to the region's lowest voxel, clamped so the per-layer arithmetic stays in 32 bits
+    // (absent columns become -1: never solid).  Each thread reads its columns and their four lateral
+    // neighbours straight from the (L2/L1-resident) height tiles: rows of 32 ints, fully coalesced.
+    const long long a0 = (long long)r.cy0 * 32;
+    const int top = 32 * r.ncy + 1;
+    auto relh = [&](int xi, int zi) -> int {  // xi, zi in [-1, 32]
+        int cix = ix, ciz = iz;
+        if (xi < 0) { --cix; xi = 31; } else if (xi > 31) { ++cix; xi = 0; }
+        if (zi < 0) { --ciz; zi = 31; } else if (zi > 31) { ++ciz; zi = 0; }
+        if (cix < 0 || cix >= r.ncx || ciz < 0 || ciz >= r.ncz) return -1;
+        const int h = __ldg(heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA + xi * 32 + zi);
+        const long long d = (long long)h - a0;
+        return (int)(d < -1 ? -1 : (d > top ? top : d));
+    };
+    int hc[4], hE[4], hW[4], hN[4], hS[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = k * 8 + warp, z = lane;
+        hc[k] = relh(x, z); hE[k] = relh(x + 1, z); hW[k] = relh(x - 1, z); hN[k] = relh(x, z + 1); hS[k] = relh(x, z - 1);
+    }
+    for (int iy0 = 0; iy0 < r.ncy; iy0 += 8) {
+        const int nl = min(8, r.ncy - iy0);
+        for (int j = 0; j < nl; ++j) {
+            const int iy = iy0 + j;
+            const int a = iy * 32;
+            const bool top_absent = iy == r.ncy - 1, bottom_absent = iy == 0;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rc = min(max(hc[k] - a, 0), 32);
+                if (rc > 0) {
+                    sum += max(0, rc - min(max(hE[k] - a, 0), 32)) + max(0, rc - min(max(hW[k] - a, 0), 32)) +
+                           max(0, rc - min(max(hN[k] - a, 0), 32)) + max(0, rc - min(max(hS[k] - a, 0), 32));
+                    sum += (hc[k] - a <= 32 || top_absent) ? 1u : 0u;
+                    sum += bottom_absent ? 1u : 0u;
+                }
+            }
+            sum = __reduce_add_sync(0xffffffffu, sum);
+            if (lane == 0) s_part[j][warp] = sum;
+        }
+        __syncthreads();
+        if (tid < nl) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int wq = 0; wq < 8; ++wq) t += s_part[tid][wq];
+            counts[(size_t)colw * r.ncy + iy0 + tid] = t;
+        }
+        __syncthreads();
+    }
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(kT, kCtasPerSm)
 k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const RegionDev r,
@@ -449,17 +538,7 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
         const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
         __syncthreads();  // previous column's readers of sm.hts / sm.red are done
         int cmax = INT32_MIN, hmin = INT32_MAX;
-        for (int i = tid; i < kTileN; i += kT) {
-            const int xi = i / kTile, zi = i - xi * kTile;
-            const int gx = ix * 32 + xi - 1, gz = iz * 32 + zi - 1;  // region voxel coordinates, >= -1
-            const int cix = (gx + 32) / 32 - 1, ciz = (gz + 32) / 32 - 1;
-            int h = kHeightAbsent;
-            if (cix >= 0 && cix < r.ncx && ciz >= 0 && ciz < r.ncz)
-                h = __ldg(heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA + (gx & 31) * 32 + (gz & 31));
-            sm.hts[i] = h;
-            hmin = min(hmin, h);
-            if (xi >= 1 && xi <= 32 && zi >= 1 && zi <= 32) cmax = max(cmax, h);
-        }
+        load_heights_tile(r, heights, ix, iz, sm.hts, cmax, hmin);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
         hmin = __reduce_min_sync(0xffffffffu, hmin);
         if (lane == 0) { sm.red[0][warp] = cmax; sm.red[1][warp] = hmin; }
@@ -655,8 +734,7 @@ cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, 
         k_mesh_region<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
                                                           (float*)d_out, capacity, (u64*)d_total);
     else
-        k_mesh_region<false><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
-                                                           (float*)d_out, capacity, (u64*)d_total);
+        k_count_region<<<(unsigned)ncols, kT, 0, s>>>(r, d_heights, d_counts);
     return cudaGetLastError();
 }
 

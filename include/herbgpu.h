@@ -30,6 +30,13 @@
 extern "C" {
 #endif
 
+/* Only the entry points below are exported from libherbgpu.so (it is built with -fvisibility=hidden). */
+#if defined(__GNUC__)
+#define HB_API __attribute__((visibility("default")))
+#else
+#define HB_API
+#endif
+
 #define HB_CHUNK_LENGTH 32
 #define HB_CHUNK_AREA 1024
 #define HB_CHUNK_VOLUME 32768
@@ -75,23 +82,23 @@ typedef struct hb_palette_cube {
 typedef struct hb_region { int32_t cx0, cz0, ncx, ncz, cy0, ncy; } hb_region;
 
 /* ---- lifetime ---- */
-int hb_create(int device, hb_ctx **out);
-void hb_destroy(hb_ctx *ctx);
-const char *hb_last_error(void);
-const char *hb_version(void);
+HB_API int hb_create(int device, hb_ctx **out);
+HB_API void hb_destroy(hb_ctx *ctx);
+HB_API const char *hb_last_error(void);
+HB_API const char *hb_version(void);
 
 /* World parameters; defaults are the reference's hard-coded values
  * (server/src/generator/mod.rs:103-108): freq 0.001, 6 octaves, lacunarity 2.0, gain 0.6.
  * seed is GenerationParams::seed (i64). */
-int hb_set_world(hb_ctx *ctx, int64_t seed, float freq, int32_t octaves, float lacunarity, float gain);
+HB_API int hb_set_world(hb_ctx *ctx, int64_t seed, float freq, int32_t octaves, float lacunarity, float gain);
 
 /* Palette colours, Material::texture (server/src/chunk/material.rs:27-71): material id m (1-based)
  * has n_colors[m-1] colours, rgba[(m-1)*HB_MAX_COLORS + c][4].  Default = stone, dirt, grass. */
-int hb_set_materials(hb_ctx *ctx, int32_t n_materials, const int32_t *n_colors, const float *rgba);
+HB_API int hb_set_materials(hb_ctx *ctx, int32_t n_materials, const int32_t *n_colors, const float *rgba);
 
 /* Pinned host memory for full-speed async copies (optional; any host pointer is accepted). */
-int hb_host_alloc(hb_ctx *ctx, size_t bytes, void **out);
-int hb_host_free(hb_ctx *ctx, void *p);
+HB_API int hb_host_alloc(hb_ctx *ctx, size_t bytes, void **out);
+HB_API int hb_host_free(hb_ctx *ctx, void *p);
 
 /* ---- generation ---- */
 
@@ -99,12 +106,12 @@ int hb_host_free(hb_ctx *ctx, void *p);
  * cols_xz: n x {cx, cz}.  out_noise: n x 1024 f32, index x + z*32 (the crate's tile order,
  * crates/simd-noise/src/noise/f32.rs:69-129).  out_heights (nullable): n x 1024 i32,
  * h = trunc(noise*32) (generator/mod.rs:79), index x*32 + z. */
-int hb_noise_tiles(hb_ctx *ctx, const int32_t *cols_xz, size_t n, float *out_noise, int32_t *out_heights);
+HB_API int hb_noise_tiles(hb_ctx *ctx, const int32_t *cols_xz, size_t n, float *out_noise, int32_t *out_heights);
 
 /* get_3d_noise (crates/simd-noise/src/noise/f32.rs:131-198) with FbmNoise: nx*ny*nz samples starting
  * at (sx,sy,sz), step 1, multiplied by freq[3]; out index x + y*nx + z*nx*ny.  Uses the ctx's seed,
  * octaves, lacunarity, gain. */
-int hb_noise_fbm3d(hb_ctx *ctx, float sx, float sy, float sz, int32_t nx, int32_t ny, int32_t nz,
+HB_API int hb_noise_fbm3d(hb_ctx *ctx, float sx, float sy, float sz, int32_t nx, int32_t ny, int32_t nz,
                    const float *freq3, float *out);
 
 /* Replaces ChunkGenerator::request/dequeue + GenerationParams::generate
@@ -112,14 +119,14 @@ int hb_noise_fbm3d(hb_ctx *ctx, float sx, float sy, float sz, int32_t nx, int32_
  * out_ids: n x 32768 u16.  out_cubes (nullable): n x 32768 hb_palette_cube = CubeMesh::data right
  * after generate() (in-chunk face flags as CubeMesh::set leaves them, server/src/chunk/mesh.rs:125-232;
  * cross-chunk culling not yet applied).  out_noise (nullable): n x 1024 f32 as hb_noise_tiles. */
-int hb_generate(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, uint16_t *out_ids,
+HB_API int hb_generate(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, uint16_t *out_ids,
                 hb_palette_cube *out_cubes, float *out_noise);
 
 /* ---- meshing ---- */
 
 /* Host helper (no GPU work): out[i*27 + (dx+1)*9 + (dy+1)*3 + (dz+1)] = index of chunk pts[i]+(dx,dy,dz)
  * in pts, or -1.  Same shell order as create_chunk_shell (client/src/world/chunk.rs:158-174). */
-int hb_build_neighbor_index(const hb_chunk_pt *pts, size_t n, int32_t *out);
+HB_API int hb_build_neighbor_index(const hb_chunk_pt *pts, size_t n, int32_t *out);
 
 /* Replaces the remesh loop of client ChunkMap::update + generate_mesh
  * (client/src/world/chunk.rs:66-75,176-276) together with the server-side face culling it relies on
@@ -130,7 +137,7 @@ int hb_build_neighbor_index(const hb_chunk_pt *pts, size_t n, int32_t *out);
  * the gap after each chunk is zero-filled.  *out_total = instances spanned (incl. gaps).
  * If out_capacity (in instances) is too small nothing is written to `out`, *out_total holds the
  * requirement and HB_ERR_CAPACITY is returned (out may be NULL with capacity 0 to query). */
-int hb_mesh(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, const uint16_t *ids,
+HB_API int hb_mesh(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, const uint16_t *ids,
             const int32_t *neighbor_index, hb_instance3d *out, uint64_t out_capacity,
             uint64_t *out_offsets, uint32_t *out_counts, uint64_t *out_total);
 
@@ -148,7 +155,7 @@ typedef void (*hb_region_sink)(void *user, uint64_t first_chunk, uint64_t n_chun
 /* Generate and mesh every chunk of `region` without a block-array round trip; results stream back
  * through pinned double-buffered async copies.  Equivalent to hb_generate + hb_mesh over the same
  * chunk set.  total_* (nullable) receive the sums. */
-int hb_generate_mesh_region(hb_ctx *ctx, const hb_region *region, int want_ids,
+HB_API int hb_generate_mesh_region(hb_ctx *ctx, const hb_region *region, int want_ids,
                             hb_region_sink sink, void *user,
                             uint64_t *total_chunks, uint64_t *total_quads);
 
@@ -165,30 +172,30 @@ enum {
     HB_STAGE_ALL_MESH = 15
 };
 /* quad_capacity 0 = size the instance buffer by running HEIGHTS+COUNT+SCAN once (synchronous). */
-int hb_region_plan_create(hb_ctx *ctx, const hb_region *region, int32_t ix_begin, int32_t ix_end,
+HB_API int hb_region_plan_create(hb_ctx *ctx, const hb_region *region, int32_t ix_begin, int32_t ix_end,
                           uint64_t quad_capacity, int want_ids, hb_region_plan **out);
-void hb_region_plan_destroy(hb_region_plan *plan);
-int hb_region_plan_enqueue(hb_region_plan *plan, int stages, void *stream);
+HB_API void hb_region_plan_destroy(hb_region_plan *plan);
+HB_API int hb_region_plan_enqueue(hb_region_plan *plan, int stages, void *stream);
 /* Synchronises `stream`, then reports totals and device pointers (any out pointer may be NULL). */
-int hb_region_plan_result(hb_region_plan *plan, void *stream, uint64_t *n_chunks, uint64_t *total_quads,
+HB_API int hb_region_plan_result(hb_region_plan *plan, void *stream, uint64_t *n_chunks, uint64_t *total_quads,
                           uint64_t *total_span, const hb_instance3d **d_instances,
                           const uint64_t **d_offsets, const uint32_t **d_counts,
                           const uint16_t **d_ids, const int32_t **d_heights);
 /* Number of kernel launches a given stage mask enqueues (for launch accounting). */
-int hb_region_plan_launches(const hb_region_plan *plan, int stages);
+HB_API int hb_region_plan_launches(const hb_region_plan *plan, int stages);
 /* Blocking device->host copy of plan / hb_dev_* results (synchronises the ctx device). */
-int hb_dev_download(hb_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes);
+HB_API int hb_dev_download(hb_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes);
 
 /* Device-pointer forms of hb_generate / hb_mesh: all pointers are device memory, kernels are
  * enqueued on `stream`, nothing is synchronised.
  * hb_dev_generate: d_cols_xz (ncol x 2), d_col_of_chunk (n), d_heights (ncol x 1024 i32 scratch/out). */
-int hb_dev_generate(hb_ctx *ctx, void *stream, const int32_t *d_cols_xz, size_t ncol,
+HB_API int hb_dev_generate(hb_ctx *ctx, void *stream, const int32_t *d_cols_xz, size_t ncol,
                     const hb_chunk_pt *d_pts, const int32_t *d_col_of_chunk, size_t n,
                     int32_t *d_heights, float *d_noise, uint16_t *d_ids, hb_palette_cube *d_cubes);
 /* hb_dev_mesh: d_workspace of hb_dev_mesh_workspace_bytes(n) bytes.  d_total[0] = span (instances),
  * d_total[1] = quads, d_total[2] = error flags (1 = capacity exceeded, 2 = unknown material id). */
-size_t hb_dev_mesh_workspace_bytes(size_t n);
-int hb_dev_mesh(hb_ctx *ctx, void *stream, const hb_chunk_pt *d_pts, size_t n, const uint16_t *d_ids,
+HB_API size_t hb_dev_mesh_workspace_bytes(size_t n);
+HB_API int hb_dev_mesh(hb_ctx *ctx, void *stream, const hb_chunk_pt *d_pts, size_t n, const uint16_t *d_ids,
                 const int32_t *d_neighbor_index, void *d_workspace, hb_instance3d *d_out,
                 uint64_t out_capacity, uint64_t *d_offsets, uint32_t *d_counts, uint64_t *d_total);
 

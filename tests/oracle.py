@@ -13,7 +13,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from herbolution_b200._lib import CHUNK_AREA, CHUNK_VOLUME, CUBE_DTYPE, INSTANCE_DTYPE  # noqa: E402  (dtypes only)
-from herbolution_b200.build import ORACLE_LIB, build_oracle  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from build_oracle import ORACLE_LIB, build_oracle  # noqa: E402
 
 
 class World(C.Structure):
@@ -43,9 +44,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if os.path.exists(os.path.join(ROOT, "oracle", "hb_oracle.c")):
-            build_oracle()
-        L = C.CDLL(ORACLE_LIB)
+        L = C.CDLL(build_oracle())
         L.hbo_simplex2.restype = C.c_float
         L.hbo_simplex2.argtypes = [C.c_float, C.c_float, C.c_int64, C.c_int]
         L.hbo_fbm2.restype = C.c_float

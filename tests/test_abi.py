@@ -1,0 +1,132 @@
+"""CPU tests of the drop-in boundary: libherbgpu.so loads, exports every symbol include/herbgpu.h
+declares, the POD layouts match the reference's repr(C) types, host-only helpers work, and the product
+fails loudly without a GPU (no CPU fallback, no dependency on oracle/)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import herbolution_b200 as hb
+from herbolution_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "herbgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(n for n in names if n not in ("hb_region_sink",)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _lib.load()
+    declared = header_functions()
+    assert len(declared) >= 20
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = set(re.findall(r"\bT (hb_[a-z0-9_]+)", nm))
+    for name in declared:
+        assert name in exported, f"{name} declared in herbgpu.h but not exported"
+        assert hasattr(lib, name)
+    assert sorted(_lib.PROTOTYPES) == declared, "python binding table out of sync with the header"
+    # C ABI only: nothing mangled is exported except what the C++ runtime drags in
+    assert not [s for s in re.findall(r"\bT (\S+)", nm) if s.startswith("_ZN2hb")]
+
+
+def test_pod_layouts_match_reference_types():
+    assert hb.INSTANCE_DTYPE.itemsize == 100      # Instance3d, client/src/video/world/vertex.rs:41-51
+    assert hb.INSTANCE_DTYPE.fields["rgba"][1] == 64 and hb.INSTANCE_DTYPE.fields["light"][1] == 80
+    assert hb.INSTANCE_DTYPE.fields["ao"][1] == 84
+    assert hb.CUBE_DTYPE.itemsize == 8            # PaletteCube, server/src/chunk/cube.rs:5-10
+    assert hb.CUBE_DTYPE.fields["flags"][1] == 4
+    assert hb.CHUNK_PT_DTYPE.itemsize == 12       # ChunkPt = Vec3<i32>
+    assert C.sizeof(hb.Region) == 24
+
+
+def test_version_and_error_channel():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.hb_version()
+    rc = lib.hb_create(0, None)
+    assert rc == _lib.HB_ERR_INVALID and b"null" in lib.hb_last_error()
+
+
+def test_build_neighbor_index_host_helper():
+    """hb_build_neighbor_index is pure host code (no GPU): shell order of create_chunk_shell
+    (client/src/world/chunk.rs:158-174), centre = 13, -1 = absent."""
+    lib = _lib.load()
+    pts = hb.Region(0, 0, 2, 2, 0, 2).chunk_points()
+    out = np.empty((len(pts), 27), dtype=np.int32)
+    assert lib.hb_build_neighbor_index(pts.ctypes.data, len(pts), out.ctypes.data) == 0
+    lut = {(int(p["x"]), int(p["y"]), int(p["z"])): i for i, p in enumerate(pts)}
+    for i, p in enumerate(pts):
+        k = 0
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    want = lut.get((int(p["x"]) + dx, int(p["y"]) + dy, int(p["z"]) + dz), -1)
+                    assert out[i, k] == want
+                    k += 1
+        assert out[i, 13] == i
+    assert lib.hb_build_neighbor_index(None, 0, None) == 0
+
+
+def test_region_chunk_points_order():
+    r = hb.Region(-1, 5, 2, 3, -2, 2)
+    pts = r.chunk_points()
+    assert len(pts) == 12
+    for ix in range(2):
+        for iz in range(3):
+            for iy in range(2):
+                p = pts[(ix * 3 + iz) * 2 + iy]
+                assert (p["x"], p["y"], p["z"]) == (-1 + ix, -2 + iy, 5 + iz)
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(hb.HerbGpuError) as e:
+        hb.Context()
+    assert e.value.code == _lib.HB_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_references_the_oracle():
+    """The oracle is test infrastructure: nothing under herbolution_b200/ or include/ may import, link
+    or execute it."""
+    bad = []
+    for base in ("herbolution_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    txt = open(os.path.join(dp, fn)).read()
+                    for m in re.finditer(r"oracle", txt):
+                        line = txt[txt.rfind("\n", 0, m.start()) + 1:txt.find("\n", m.end())]
+                        if re.search(r"import|include|CDLL|dlopen|build_oracle|liboracle|hbo_", line):
+                            bad.append((fn, line.strip()))
+    assert not bad, bad
+    ldd = subprocess.check_output(["ldd", _lib.LIB_PATH], text=True)
+    assert "oracle" not in ldd
+    nm = subprocess.check_output(["nm", "-D", _lib.LIB_PATH], text=True)
+    assert "hbo_" not in nm
+
+
+def test_host_mirror_api_surface():
+    """The mirror keeps the reference's names (server/src/generator/mod.rs, client/src/world/chunk.rs)."""
+    for name in ("ChunkGenerator", "GenerationParams", "CubeMesh", "ChunkPt", "ChunkMap", "ChunkData",
+                 "create_chunk_shell", "generate_mesh"):
+        assert hasattr(hb, name)
+    assert {"request", "dequeue"} <= set(dir(hb.ChunkGenerator))
+    assert {"generate", "get_noise"} <= set(dir(hb.GenerationParams))
+    shell = hb.create_chunk_shell({hb.ChunkPt(0, 0, 0): hb.ChunkData(hb.ChunkPt(0, 0, 0), np.zeros(32768, np.uint16))},
+                                  hb.ChunkPt(0, 0, 0))
+    assert len(shell) == 27 and shell[13] is not None and sum(s is not None for s in shell) == 1
