@@ -44,7 +44,9 @@ static_assert(sizeof(hb_palette_cube) == 8, "PaletteCube must be 8 bytes");
 // ---- launch wrappers implemented in gen.cu / mesh.cu (all enqueue-only) ----
 cudaError_t launch_heights(cudaStream_t s, const WorldDev& w, const int32_t* d_cols_xz, size_t ncol,
                            int32_t* d_heights, float* d_noise);
-cudaError_t launch_heights_region(cudaStream_t s, const WorldDev& w, const RegionDev& r, int32_t* d_heights);
+// columns [col_begin, col_end) of the heights buffer (column = (ix - r.hx_begin) * r.ncz + iz)
+cudaError_t launch_heights_region(cudaStream_t s, const WorldDev& w, const RegionDev& r, int32_t* d_heights,
+                                  size_t col_begin, size_t col_end);
 cudaError_t launch_fill(cudaStream_t s, const hb_chunk_pt* d_pts, const int32_t* d_col_of_chunk, size_t n,
                         const int32_t* d_heights, uint16_t* d_ids, hb_palette_cube* d_cubes);
 cudaError_t launch_fill_region(cudaStream_t s, const RegionDev& r, const int32_t* d_heights, uint16_t* d_ids);
@@ -60,11 +62,12 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
 cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
                                const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
                                const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
-                               uint64_t* d_total);
-// counts -> offsets (each chunk's start rounded up to 4 instances); d_total[0]=span, d_total[1]=quads
+                               uint64_t* d_total, int ctas_per_sm = 0);
+// counts -> offsets (each chunk's start rounded up to 4 instances); d_total[0]=span, d_total[1]=quads.
+// accumulate: offsets start at the current d_total[0] and the totals are advanced (slab chaining).
 size_t scan_workspace_bytes(size_t n);
 cudaError_t launch_scan(cudaStream_t s, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* d_ws,
-                        uint64_t* d_total);
+                        uint64_t* d_total, bool accumulate);
 int num_sms();
 
 }  // namespace hb

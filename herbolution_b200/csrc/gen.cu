@@ -20,6 +20,7 @@ constexpr int kThreads = 256;
 
 struct ColList {
     const int32_t* cols_xz;
+    __device__ __forceinline__ int first() const { return 0; }
     __device__ __forceinline__ void get(int col, int& cx, int& cz) const {
         cx = cols_xz[2 * col];
         cz = cols_xz[2 * col + 1];
@@ -27,6 +28,8 @@ struct ColList {
 };
 struct ColRegion {
     RegionDev r;
+    int col0;  // first heights-buffer column of this launch
+    __device__ __forceinline__ int first() const { return col0; }
     __device__ __forceinline__ void get(int col, int& cx, int& cz) const {
         const int ix = r.hx_begin + col / r.ncz;
         const int iz = col % r.ncz;
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) k_heights(WorldDev w, Cols cols, int
     __shared__ NoiseTables s_tab;
     __shared__ int s_h[32][33];  // padded: the transposed store below is bank-conflict free
     load_noise_tables(s_tab, w.seed_lo);
-    const int col = blockIdx.x;
+    const int col = cols.first() + blockIdx.x;
     int cx, cz;
     cols.get(col, cx, cz);
     // chunk.position.xz().cast() * CHUNK_LENGTH as f32 (generator/mod.rs:74); lane coordinate =
@@ -205,10 +208,10 @@ cudaError_t launch_heights(cudaStream_t s, const WorldDev& w, const int32_t* d_c
     return cudaGetLastError();
 }
 
-cudaError_t launch_heights_region(cudaStream_t s, const WorldDev& w, const RegionDev& r, int32_t* d_heights) {
-    const size_t ncol = (size_t)(r.hx_end - r.hx_begin) * r.ncz;
-    if (ncol == 0) return cudaSuccess;
-    k_heights<ColRegion><<<(unsigned)ncol, kThreads, 0, s>>>(w, ColRegion{r}, d_heights, nullptr);
+cudaError_t launch_heights_region(cudaStream_t s, const WorldDev& w, const RegionDev& r, int32_t* d_heights,
+                                  size_t col_begin, size_t col_end) {
+    if (col_end <= col_begin) return cudaSuccess;
+    k_heights<ColRegion><<<(unsigned)(col_end - col_begin), kThreads, 0, s>>>(w, ColRegion{r, (int)col_begin}, d_heights, nullptr);
     return cudaGetLastError();
 }
 

@@ -27,7 +27,8 @@ namespace hb {
 namespace {
 
 constexpr int kT = 256;         // threads per CTA
-constexpr int kCtasPerSm = 4;   // limited by ~48 KB of shared memory per CTA
+constexpr int kCtasPerSm = 4;   // register/smem budget the mesh kernels are compiled for (<= 64 regs, 48.5 KB)
+
 constexpr int kTile = 34;
 constexpr int kTileN = kTile * kTile;
 constexpr int kDescCap = 2048;  // descriptors staged per round
@@ -133,9 +134,9 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 
 // ---- TMA 1-D bulk copy shared -> global (cp.async.bulk; SASS: UBLKCP).  dst/src 16-byte aligned, bytes % 16 == 0.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc_shared, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
-                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+                 :: "l"(gdst), "r"(ssrc_shared), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -189,6 +190,8 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
     }
 
     float* const ws = sm.stage + warp * (32 * 25);  // warp-private staging: 32 quads = 3200 B
+    const uint32_t ws_shared = (uint32_t)__cvta_generic_to_shared(ws);
+    char* const out_bytes = reinterpret_cast<char*>(out);
     for (uint32_t d0 = 0; d0 < total; d0 += kDescCap) {
         // (a) visible faces of my columns -> descriptors (L | face << 15), in emission order
 #pragma unroll
@@ -202,12 +205,14 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
             while (any) {
                 const int y = __ffs(any) - 1;
                 any &= any - 1;
-#pragma unroll
-                for (int f = 0; f < 6; ++f) {
-                    if ((m[f] >> y) & 1u) {
-                        if (o >= d0 && o < d0 + kDescCap) sm.desc[o - d0] = Lc | (uint32_t)y | ((uint32_t)f << 15);
-                        ++o;
-                    }
+                uint32_t b = ((m[0] >> y) & 1u) | (((m[1] >> y) & 1u) << 1) | (((m[2] >> y) & 1u) << 2) |
+                             (((m[3] >> y) & 1u) << 3) | (((m[4] >> y) & 1u) << 4) | (((m[5] >> y) & 1u) << 5);
+                const uint32_t Ly = Lc | (uint32_t)y;
+                while (b) {  // faces of this voxel in bit order E, W, U, D, N, S
+                    const uint32_t f = (uint32_t)__ffs(b) - 1u;
+                    b &= b - 1u;
+                    if (o - d0 < (uint32_t)kDescCap) sm.desc[o - d0] = Ly | (f << 15);  // unsigned: also rejects o < d0
+                    ++o;
                 }
             }
         }
@@ -263,7 +268,7 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
             // 200 LDS.128 + STG.128 through the LSU.  Generic-proxy writes must be fenced for the async proxy.
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) bulk_store(out + (size_t)(d0 + q0) * 25u, ws, nw4 * 100u);
+            if (lane == 0) bulk_store(out_bytes + (d0 + q0) * 100u, ws_shared, nw4 * 100u);  // < 2^24 bytes per chunk
         }
         if (d0 + kDescCap < total) __syncthreads();  // descriptors are rewritten in the next round
     }
@@ -442,21 +447,41 @@ struct MatHeights {
     }
 };
 
-// Stages the 34x34 heights halo tile of region column (ix, iz): the column's own 32x32 tile plus one
-// row/column from each of the 8 neighbouring columns; columns outside the region are ABSENT.
-// Also returns this thread's partial max over the centre and min over the whole tile.
+// Stages the 34x34 heights halo tile of region column (ix, iz): the column's own 32x32 tile (one
+// 128-bit load per thread) plus one row/column from each of the 4 edge neighbours and one value from
+// each of the 4 corner neighbours; columns outside the region are ABSENT.  Also returns this
+// thread's partial max over the centre and min over the whole tile.  Needs kT == 256.
 __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int32_t* __restrict__ heights, int ix, int iz,
                                                   int* __restrict__ hts, int& cmax, int& hmin) {
-    for (int i = threadIdx.x; i < kTileN; i += kT) {
-        const int xi = i / kTile, zi = i - xi * kTile;
-        const int gx = ix * 32 + xi - 1, gz = iz * 32 + zi - 1;  // region voxel coordinates, >= -1
-        const int cix = (gx + 32) / 32 - 1, ciz = (gz + 32) / 32 - 1;
-        int h = kHeightAbsent;
-        if (cix >= 0 && cix < r.ncx && ciz >= 0 && ciz < r.ncz)
-            h = __ldg(heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA + (gx & 31) * 32 + (gz & 31));
-        hts[i] = h;
+    const int tid = threadIdx.x;
+    auto tile_of = [&](int cix, int ciz) -> const int32_t* {
+        if (cix < 0 || cix >= r.ncx || ciz < 0 || ciz >= r.ncz) return nullptr;
+        return heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA;
+    };
+    {   // centre: element e = x*32 + z, 4 consecutive z per thread
+        const int4 v = __ldg(reinterpret_cast<const int4*>(tile_of(ix, iz)) + tid);
+        const int x = tid >> 3, z = (tid & 7) * 4;
+        int* o = hts + (x + 1) * kTile + (z + 1);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        const int mx = max(max(v.x, v.y), max(v.z, v.w)), mn = min(min(v.x, v.y), min(v.z, v.w));
+        cmax = max(cmax, mx);
+        hmin = min(hmin, mn);
+    }
+    if (tid < 128) {  // edges: west (x = -1), east (x = 32), south (z = -1), north (z = 32); 32 values each
+        const int side = tid >> 5, j = tid & 31;
+        const int32_t* t = side == 0 ? tile_of(ix - 1, iz) : side == 1 ? tile_of(ix + 1, iz)
+                         : side == 2 ? tile_of(ix, iz - 1) : tile_of(ix, iz + 1);
+        const int src = side == 0 ? 31 * 32 + j : side == 1 ? j : side == 2 ? j * 32 + 31 : j * 32;
+        const int dst = side == 0 ? (j + 1) : side == 1 ? 33 * kTile + (j + 1) : side == 2 ? (j + 1) * kTile : (j + 1) * kTile + 33;
+        const int h = t ? __ldg(t + src) : kHeightAbsent;
+        hts[dst] = h;
         hmin = min(hmin, h);
-        if (xi >= 1 && xi <= 32 && zi >= 1 && zi <= 32) cmax = max(cmax, h);
+    } else if (tid < 132) {  // corners
+        const int c = tid - 128, dx = (c & 1) ? 1 : -1, dz = (c & 2) ? 1 : -1;
+        const int32_t* t = tile_of(ix + dx, iz + dz);
+        const int h = t ? __ldg(t + (dx < 0 ? 31 : 0) * 32 + (dz < 0 ? 31 : 0)) : kHeightAbsent;
+        hts[(dx < 0 ? 0 : 33) * kTile + (dz < 0 ? 0 : 33)] = h;
+        hmin = min(hmin, h);
     }
 }
 
@@ -470,55 +495,63 @@ __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int3
 // which is exactly what k_mesh_region<EMIT> emits from the occupancy tile (parity tests cover both).
 __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const int32_t* __restrict__ heights,
                                                       uint32_t* __restrict__ counts) {
-    __shared__ uint32_t s_part[8][8];
+    __shared__ uint32_t s_acc[kT / 32][32];  // per warp, per layer of the current group of 32 layers
+    __shared__ int s_h[kTileN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int colw = blockIdx.x;
     const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
+    int cmax = INT32_MIN, hmin = INT32_MAX;
+    load_heights_tile(r, heights, ix, iz, s_h, cmax, hmin);
+    __syncthreads();
     // heights relative to the region's lowest voxel, clamped so the per-layer arithmetic stays in 32 bits
-    // (absent columns become -1: never solid).  Each thread reads its columns and their four lateral
-    // neighbours straight from the (L2/L1-resident) height tiles: rows of 32 ints, fully coalesced.
+    // (absent columns become -1: never solid)
     const long long a0 = (long long)r.cy0 * 32;
     const int top = 32 * r.ncy + 1;
     auto relh = [&](int xi, int zi) -> int {  // xi, zi in [-1, 32]
-        int cix = ix, ciz = iz;
-        if (xi < 0) { --cix; xi = 31; } else if (xi > 31) { ++cix; xi = 0; }
-        if (zi < 0) { --ciz; zi = 31; } else if (zi > 31) { ++ciz; zi = 0; }
-        if (cix < 0 || cix >= r.ncx || ciz < 0 || ciz >= r.ncz) return -1;
-        const int h = __ldg(heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA + xi * 32 + zi);
-        const long long d = (long long)h - a0;
+        const long long d = (long long)s_h[(xi + 1) * kTile + (zi + 1)] - a0;
         return (int)(d < -1 ? -1 : (d > top ? top : d));
     };
-    int hc[4], hE[4], hW[4], hN[4], hS[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int x = k * 8 + warp, z = lane;
-        hc[k] = relh(x, z); hE[k] = relh(x + 1, z); hW[k] = relh(x - 1, z); hN[k] = relh(x, z + 1); hS[k] = relh(x, z - 1);
-    }
-    for (int iy0 = 0; iy0 < r.ncy; iy0 += 8) {
-        const int nl = min(8, r.ncy - iy0);
-        for (int j = 0; j < nl; ++j) {
-            const int iy = iy0 + j;
-            const int a = iy * 32;
-            const bool top_absent = iy == r.ncy - 1, bottom_absent = iy == 0;
-            uint32_t sum = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int rc = min(max(hc[k] - a, 0), 32);
+    const int last = r.ncy - 1;
+    for (int iy0 = 0; iy0 < r.ncy; iy0 += 32) {
+        const int nl = min(32, r.ncy - iy0);
+        s_acc[warp][lane] = 0;
+        __syncwarp();
+        for (int k = 0; k < 4; ++k) {
+            const int x = k * 8 + warp, z = lane;
+            const int hc = relh(x, z), hE = relh(x + 1, z), hW = relh(x - 1, z), hN = relh(x, z + 1), hS = relh(x, z - 1);
+            // Layers below `lo` see this column and its four neighbours completely solid; layers above `hi`
+            // see the column empty.  Only the warp-wide union [wlo, whi] needs the full formula; outside it
+            // the only faces are the region's bottom (layer 0, Down) and top (last layer, Up) boundary faces.
+            int lo = min(min(hc - 1, hE), min(min(hW, hN), hS));
+            lo = hc > 0 ? (lo < 0 ? 0 : lo >> 5) : INT32_MAX;
+            const int hi = hc > 0 ? (hc - 1) >> 5 : -1;
+            const int wlo = __reduce_min_sync(0xffffffffu, lo);
+            const int whi = __reduce_max_sync(0xffffffffu, hi);
+            const int nsolid = __popc(__ballot_sync(0xffffffffu, hc > 0));
+            const int j1 = min(min(whi, last), iy0 + nl - 1);
+            for (int j = max(wlo, iy0); j <= j1; ++j) {  // warp-uniform bounds
+                const int a = j * 32;
+                const int rc = min(max(hc - a, 0), 32);
+                uint32_t v = 0;
                 if (rc > 0) {
-                    sum += max(0, rc - min(max(hE[k] - a, 0), 32)) + max(0, rc - min(max(hW[k] - a, 0), 32)) +
-                           max(0, rc - min(max(hN[k] - a, 0), 32)) + max(0, rc - min(max(hS[k] - a, 0), 32));
-                    sum += (hc[k] - a <= 32 || top_absent) ? 1u : 0u;
-                    sum += bottom_absent ? 1u : 0u;
+                    v = max(0, rc - min(max(hE - a, 0), 32)) + max(0, rc - min(max(hW - a, 0), 32)) +
+                        max(0, rc - min(max(hN - a, 0), 32)) + max(0, rc - min(max(hS - a, 0), 32));
+                    v += (hc - a <= 32 || j == last) ? 1u : 0u;  // up: real top, or the chunk above is absent
+                    v += (j == 0) ? 1u : 0u;                     // down: only where the chunk below is absent
                 }
+                v = __reduce_add_sync(0xffffffffu, v);
+                if (lane == 0) s_acc[warp][j - iy0] += v;
             }
-            sum = __reduce_add_sync(0xffffffffu, sum);
-            if (lane == 0) s_part[j][warp] = sum;
+            if (lane == 0 && nsolid) {
+                if (wlo > 0 && iy0 == 0) s_acc[warp][0] += nsolid * (last == 0 ? 2 : 1);             // bottom faces (+ top if 1 layer)
+                if (last > 0 && last < wlo && last >= iy0 && last < iy0 + nl) s_acc[warp][last - iy0] += nsolid;  // top faces
+            }
         }
         __syncthreads();
         if (tid < nl) {
             uint32_t t = 0;
 #pragma unroll
-            for (int wq = 0; wq < 8; ++wq) t += s_part[tid][wq];
+            for (int wq = 0; wq < kT / 32; ++wq) t += s_acc[wq][tid];
             counts[(size_t)colw * r.ncy + iy0 + tid] = t;
         }
         __syncthreads();
@@ -623,13 +656,14 @@ __global__ void __launch_bounds__(kScanT) k_tile_sums(const uint32_t* __restrict
     if (threadIdx.x == 0) { tile_span[blockIdx.x] = span; tile_quads[blockIdx.x] = quads; }
 }
 
-// single CTA: exclusive scan of tile spans in place; totals to total[0] (span) and total[1] (quads)
+// single CTA: exclusive scan of tile spans in place, starting at total[0]; total[0] (span) and total[1]
+// (quads) are advanced, so consecutive slabs of one plan chain their offsets
 __global__ void __launch_bounds__(1024) k_scan_sums(u64* __restrict__ tile_span, const u64* __restrict__ tile_quads,
                                                      size_t ntiles, u64* __restrict__ total) {
     __shared__ u64 s_w[32];
     __shared__ u64 s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) s_carry = total[0];  // running span of the slabs scanned before this one (0 after a reset)
     u64 quads = 0;
     __syncthreads();
     for (size_t b0 = 0; b0 < ntiles; b0 += 1024) {
@@ -652,7 +686,7 @@ __global__ void __launch_bounds__(1024) k_scan_sums(u64* __restrict__ tile_span,
         __syncthreads();
     }
     quads = block_sum_u64(quads, s_w);
-    if (tid == 0) { total[0] = s_carry; total[1] = quads; }
+    if (tid == 0) { total[0] = s_carry; total[1] += quads; }
 }
 
 __global__ void __launch_bounds__(kScanT) k_offsets(const uint32_t* __restrict__ counts, size_t n,
@@ -725,10 +759,11 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
 cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
                                const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
                                const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
-                               uint64_t* d_total) {
+                               uint64_t* d_total, int ctas_per_sm) {
     const size_t ncols = (size_t)(r.ix_end - r.ix_begin) * r.ncz;
     if (ncols == 0 || r.ncy == 0) return cudaSuccess;
-    size_t grid = (size_t)num_sms() * kCtasPerSm;
+    if (ctas_per_sm < 1 || ctas_per_sm > kCtasPerSm) ctas_per_sm = kCtasPerSm;
+    size_t grid = (size_t)num_sms() * ctas_per_sm;  // persistent CTAs
     if (grid > ncols) grid = ncols;
     if (emit)
         k_mesh_region<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
@@ -744,8 +779,12 @@ size_t scan_workspace_bytes(size_t n) {
 }
 
 cudaError_t launch_scan(cudaStream_t s, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* d_ws,
-                        uint64_t* d_total) {
-    if (n == 0) return cudaMemsetAsync(d_total, 0, 2 * sizeof(u64), s);
+                        uint64_t* d_total, bool accumulate) {
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(d_total, 0, 2 * sizeof(u64), s);
+        if (e != cudaSuccess) return e;
+    }
+    if (n == 0) return cudaSuccess;
     const size_t ntiles = (n + kScanTile - 1) / kScanTile;
     u64* tile_span = (u64*)d_ws;
     u64* tile_quads = tile_span + ntiles + 1;
