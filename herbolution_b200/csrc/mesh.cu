@@ -20,6 +20,8 @@
 // buffer (stride 25 words: bank-conflict free), and one lane hands the 3200-byte window to the TMA
 // engine as a 1-D bulk shared->global copy (cp.async.bulk, SASS UBLKCP).  Each chunk's output starts on a 4-instance (400 B) boundary so every
 // vector store is 16-byte aligned.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace hb {
@@ -438,12 +440,10 @@ k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
 // ------------------------------------------------------------------------------------------------
 
 struct MatHeights {
-    const int* hts;
-    long long wy0;
+    const int* hts;  // relative heights (RelHeight)
+    int a;           // the chunk's first voxel layer, relative: iy * 32
     __device__ __forceinline__ uint32_t operator()(uint32_t, int x, int y, int z) const {
-        long long dl = (long long)hts[(x + 1) * kTile + (z + 1)] - (wy0 + y);
-        dl = dl > 16 ? 16 : dl;
-        return block_id((int)dl);
+        return block_id(hts[(x + 1) * kTile + (z + 1)] - (a + y));
     }
 };
 
@@ -451,15 +451,28 @@ struct MatHeights {
 // 128-bit load per thread) plus one row/column from each of the 4 edge neighbours and one value from
 // each of the 4 corner neighbours; columns outside the region are ABSENT.  Also returns this
 // thread's partial max over the centre and min over the whole tile.  Needs kT == 256.
+// Heights relative to the region's lowest voxel (world y = cy0*32), clamped to [-1, 32*ncy + 8] so that all
+// per-layer arithmetic stays in 32 bits (the +8 keeps `h - y > 6`, the stone test, exact up to the region's
+// top voxel); absent columns (INT_MIN) become -1: never solid.
+struct RelHeight {
+    long long a0;
+    int top;
+    __device__ __forceinline__ int operator()(int h) const {
+        const long long d = (long long)h - a0;
+        return (int)(d < -1 ? -1 : (d > top ? top : d));
+    }
+};
+template <class Conv>
 __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int32_t* __restrict__ heights, int ix, int iz,
-                                                  int* __restrict__ hts, int& cmax, int& hmin) {
+                                                  int* __restrict__ hts, int& cmax, int& hmin, const Conv& conv) {
     const int tid = threadIdx.x;
     auto tile_of = [&](int cix, int ciz) -> const int32_t* {
         if (cix < 0 || cix >= r.ncx || ciz < 0 || ciz >= r.ncz) return nullptr;
         return heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA;
     };
     {   // centre: element e = x*32 + z, 4 consecutive z per thread
-        const int4 v = __ldg(reinterpret_cast<const int4*>(tile_of(ix, iz)) + tid);
+        int4 v = __ldg(reinterpret_cast<const int4*>(tile_of(ix, iz)) + tid);
+        v.x = conv(v.x); v.y = conv(v.y); v.z = conv(v.z); v.w = conv(v.w);
         const int x = tid >> 3, z = (tid & 7) * 4;
         int* o = hts + (x + 1) * kTile + (z + 1);
         o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
@@ -473,13 +486,13 @@ __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int3
                          : side == 2 ? tile_of(ix, iz - 1) : tile_of(ix, iz + 1);
         const int src = side == 0 ? 31 * 32 + j : side == 1 ? j : side == 2 ? j * 32 + 31 : j * 32;
         const int dst = side == 0 ? (j + 1) : side == 1 ? 33 * kTile + (j + 1) : side == 2 ? (j + 1) * kTile : (j + 1) * kTile + 33;
-        const int h = t ? __ldg(t + src) : kHeightAbsent;
+        const int h = conv(t ? __ldg(t + src) : kHeightAbsent);
         hts[dst] = h;
         hmin = min(hmin, h);
     } else if (tid < 132) {  // corners
         const int c = tid - 128, dx = (c & 1) ? 1 : -1, dz = (c & 2) ? 1 : -1;
         const int32_t* t = tile_of(ix + dx, iz + dz);
-        const int h = t ? __ldg(t + (dx < 0 ? 31 : 0) * 32 + (dz < 0 ? 31 : 0)) : kHeightAbsent;
+        const int h = conv(t ? __ldg(t + (dx < 0 ? 31 : 0) * 32 + (dz < 0 ? 31 : 0)) : kHeightAbsent);
         hts[(dx < 0 ? 0 : 33) * kTile + (dz < 0 ? 0 : 33)] = h;
         hmin = min(hmin, h);
     }
@@ -498,27 +511,22 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
     __shared__ uint32_t s_acc[kT / 32][32];  // per warp, per layer of the current group of 32 layers
     __shared__ int s_h[kTileN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int colw = blockIdx.x;
+    const RelHeight rel{(long long)r.cy0 * 32, 32 * r.ncy + 8};  // converted once while the tile is staged
+    const int last = r.ncy - 1;
+    const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
+    for (int colw = blockIdx.x; colw < ncols; colw += gridDim.x) {
     const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
     int cmax = INT32_MIN, hmin = INT32_MAX;
-    load_heights_tile(r, heights, ix, iz, s_h, cmax, hmin);
+    __syncthreads();  // previous column's readers of s_h are done
+    load_heights_tile(r, heights, ix, iz, s_h, cmax, hmin, rel);
     __syncthreads();
-    // heights relative to the region's lowest voxel, clamped so the per-layer arithmetic stays in 32 bits
-    // (absent columns become -1: never solid)
-    const long long a0 = (long long)r.cy0 * 32;
-    const int top = 32 * r.ncy + 1;
-    auto relh = [&](int xi, int zi) -> int {  // xi, zi in [-1, 32]
-        const long long d = (long long)s_h[(xi + 1) * kTile + (zi + 1)] - a0;
-        return (int)(d < -1 ? -1 : (d > top ? top : d));
-    };
-    const int last = r.ncy - 1;
     for (int iy0 = 0; iy0 < r.ncy; iy0 += 32) {
         const int nl = min(32, r.ncy - iy0);
         s_acc[warp][lane] = 0;
         __syncwarp();
         for (int k = 0; k < 4; ++k) {
-            const int x = k * 8 + warp, z = lane;
-            const int hc = relh(x, z), hE = relh(x + 1, z), hW = relh(x - 1, z), hN = relh(x, z + 1), hS = relh(x, z - 1);
+            const int* o = s_h + (k * 8 + warp + 1) * kTile + (lane + 1);
+            const int hc = o[0], hE = o[kTile], hW = o[-kTile], hN = o[1], hS = o[-1];
             // Layers below `lo` see this column and its four neighbours completely solid; layers above `hi`
             // see the column empty.  Only the warp-wide union [wlo, whi] needs the full formula; outside it
             // the only faces are the region's bottom (layer 0, Down) and top (last layer, Up) boundary faces.
@@ -556,6 +564,7 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
         }
         __syncthreads();
     }
+    }  // persistent column loop
 }
 
 template <bool EMIT>
@@ -566,12 +575,13 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
     __shared__ MeshSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (EMIT) load_tables(sm, tb);
+    const RelHeight rel{(long long)r.cy0 * 32, 32 * r.ncy + 8};
     const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
     for (int colw = blockIdx.x; colw < ncols; colw += gridDim.x) {
         const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
         __syncthreads();  // previous column's readers of sm.hts / sm.red are done
         int cmax = INT32_MIN, hmin = INT32_MAX;
-        load_heights_tile(r, heights, ix, iz, sm.hts, cmax, hmin);
+        load_heights_tile(r, heights, ix, iz, sm.hts, cmax, hmin, rel);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
         hmin = __reduce_min_sync(0xffffffffu, hmin);
         if (lane == 0) { sm.red[0][warp] = cmax; sm.red[1][warp] = hmin; }
@@ -583,10 +593,10 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
         for (int iy = 0; iy < r.ncy; ++iy) {
             const size_t chunk = (size_t)colw * r.ncy + iy;  // slab-relative chunk index
             const int cy = r.cy0 + iy;
-            const long long wy0 = (long long)cy * 32;
+            const int a = iy * 32;  // relative y of the chunk's first layer
             // block-uniform early outs: centre all air, or the whole 34^3 neighbourhood solid
-            const bool empty = (long long)cmax <= wy0;
-            const bool buried = (long long)hmin >= wy0 + 33 && iy > 0 && iy < r.ncy - 1;
+            const bool empty = cmax <= a;
+            const bool buried = hmin >= a + 33 && iy > 0 && iy < r.ncy - 1;
             if (empty || buried) {
                 if (!EMIT && tid == 0) counts[chunk] = 0;
                 continue;
@@ -601,17 +611,15 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
                 }
             }
             __syncthreads();  // previous chunk's readers of sm.occ are done
+            const u64 ymask = 0x3FFFFFFFFULL & ~(iy == 0 ? 1ULL : 0ULL)         // chunk below outside the region: absent
+                                             & ~(iy == r.ncy - 1 ? (1ULL << 33) : 0ULL);  // chunk above absent
             for (int i = tid; i < kTileN; i += kT) {
-                long long d = (long long)sm.hts[i] - (wy0 - 1);  // solid voxels at tile bits 0..33
-                d = d < 0 ? 0 : (d > 34 ? 34 : d);
-                u64 v = (d >= 34) ? 0x3FFFFFFFFULL : ((1ULL << d) - 1ULL);
-                if (iy == 0) v &= ~1ULL;                 // chunk below is outside the region: absent
-                if (iy == r.ncy - 1) v &= ~(1ULL << 33);  // chunk above absent
-                sm.occ[i] = v;
+                const int d = min(max(sm.hts[i] - (a - 1), 0), 34);  // solid voxels at tile bits 0..33
+                sm.occ[i] = ((1ULL << d) - 1ULL) & ymask;
             }
             if (EMIT && tid == 32) sm.rng_seed = siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
             __syncthreads();
-            const MatHeights mat{sm.hts, wy0};
+            const MatHeights mat{sm.hts, a};
             const uint32_t q = mesh_tile<EMIT>(sm, mat, (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32, mats,
                                                EMIT ? out + off * 25ULL : nullptr);
             if (!EMIT && tid == 0) counts[chunk] = q;
@@ -769,7 +777,7 @@ cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, 
         k_mesh_region<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
                                                           (float*)d_out, capacity, (u64*)d_total);
     else
-        k_count_region<<<(unsigned)ncols, kT, 0, s>>>(r, d_heights, d_counts);
+        k_count_region<<<(unsigned)std::min<size_t>(ncols, (size_t)num_sms() * 8), kT, 0, s>>>(r, d_heights, d_counts);
     return cudaGetLastError();
 }
 

@@ -301,7 +301,8 @@ def collect_region(ctx, region, want_ids=False):
 
 
 @pytest.mark.parametrize("seed,reg", [(0, (-3, -3, 6, 6, -3, 6)), (5, (10, -20, 5, 3, -1, 2)), (0, (0, 0, 1, 1, 0, 1)),
-                                      (5, (3, 3, 1, 2, -20, 40)), (0, (-1, 0, 2, 1, -1, 1)), (0, (0, 0, 2, 2, 3, 2))])
+                                      (5, (3, 3, 1, 2, -20, 40)), (0, (-1, 0, 2, 1, -1, 1)), (0, (0, 0, 2, 2, 3, 2)),
+                                      (0, (-2, -2, 3, 3, -3, 2)), (5, (0, 0, 2, 2, -2, 1))])  # region top below the terrain
 def test_region_fused_vs_oracle(ctx, seed, reg):
     ctx.set_world(seed)
     ref = O.region_pipeline(O.world(seed), reg, literal=True, threads=8, want_ids=True)
