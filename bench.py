@@ -257,8 +257,11 @@ def main():
     flops_per_column = 333824.0  # 1024 samples x 326 flops
     ncols_noise = reg.ncx * reg.ncz
     noise_tflops = flops_per_column * ncols_noise / (stage_ms["heights"] * 1e-3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture of this exact
+    # workload (profiles/r1_ncu_full_summary.csv: 0.479 GB read + 17.481 GB written per launch)
+    traffic = 17.960e9 if (cols == 256 and world == 1) else None
     roofline = {"kernel": "k_mesh_region<EMIT=true>", "bound": "hbm", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
-                "frac": emit_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "frac": emit_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": emit_bytes, "avg_launch_ms": stage_ms["emit"],
                 "share_of_step": stage_ms["emit"] / sum(stage_ms.values())}
     kernels = {"stage_ms": stage_ms,

@@ -302,19 +302,17 @@ __global__ void __launch_bounds__(kT) k_pack(const uint16_t* __restrict__ ids, s
     for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         const uint4* src = reinterpret_cast<const uint4*>(ids + chunk * HB_CHUNK_VOLUME);
         uint32_t any = 0, all = ~0u, fE = ~0u, fW = ~0u, fN = ~0u, fS = ~0u, bad = 0;
-        const uint32_t nm = (uint32_t)n_materials;
+        const uint32_t nm2 = (uint32_t)n_materials * 0x10001u;  // palette size in both halfwords
 #pragma unroll 4
         for (int it = 0; it < 16; ++it) {
             const int u = it * kT + tid;
             const uint4 v = __ldcs(src + u);
-            const uint32_t h[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
-                                   v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
-            uint32_t m8 = 0;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                m8 |= (h[e] != 0u ? 1u : 0u) << e;
-                bad |= (h[e] > nm) ? 1u : 0u;
-            }
+            // per-halfword SIMD compares: 0xFFFF where the id is non-zero / above the palette size
+            const uint32_t z0 = __vcmpne2(v.x, 0u), z1 = __vcmpne2(v.y, 0u), z2 = __vcmpne2(v.z, 0u), z3 = __vcmpne2(v.w, 0u);
+            bad |= __vcmpgtu2(v.x, nm2) | __vcmpgtu2(v.y, nm2) | __vcmpgtu2(v.z, nm2) | __vcmpgtu2(v.w, nm2);
+            // bit 0 and bit 16 of each compare word -> bits 2k and 2k+1 of the 8-bit occupancy mask
+            const uint32_t m8 = ((z0 & 1u) | ((z0 >> 15) & 2u)) | (((z1 & 1u) | ((z1 >> 15) & 2u)) << 2) |
+                                (((z2 & 1u) | ((z2 >> 15) & 2u)) << 4) | (((z3 & 1u) | ((z3 >> 15) & 2u)) << 6);
             uint32_t w = m8 << ((u & 3) * 8);
             w |= __shfl_xor_sync(0xffffffffu, w, 1);
             w |= __shfl_xor_sync(0xffffffffu, w, 2);
