@@ -84,6 +84,8 @@ PROTOTYPES = {
     "hb_build_neighbor_index": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "hb_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                           C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "hb_mesh_cubes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "hb_generate_mesh_region": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int, REGION_SINK, C.c_void_p,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_region_plan_create": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_uint64, C.c_int,

@@ -129,24 +129,28 @@ class Context:
         check(self._lib.hb_build_neighbor_index(ptr(pts), pts.shape[0], ptr(out)))
         return out
 
-    def mesh(self, positions, ids: np.ndarray, neighbor_index: Optional[np.ndarray] = None) -> dict:
+    def mesh_cubes(self, positions, cubes: np.ndarray, neighbor_index: Optional[np.ndarray] = None) -> dict:
+        """hb_mesh_cubes: literal generate_mesh, visible faces read from cube.flags (CUBE_DTYPE arrays)."""
+        return self.mesh(positions, cubes, neighbor_index, _cubes=True)
+
+    def mesh(self, positions, ids: np.ndarray, neighbor_index: Optional[np.ndarray] = None, _cubes: bool = False) -> dict:
         """Returns {"instances": INSTANCE_DTYPE[span], "offsets": u64[n], "counts": u32[n]}."""
         pts = as_chunk_pts(positions)
         n = pts.shape[0]
-        ids = np.ascontiguousarray(ids, dtype=np.uint16).reshape(n, CHUNK_VOLUME)
+        fn = self._lib.hb_mesh_cubes if _cubes else self._lib.hb_mesh
+        ids = np.ascontiguousarray(ids, dtype=CUBE_DTYPE if _cubes else np.uint16).reshape(n, CHUNK_VOLUME)
         nbr = self.build_neighbor_index(pts) if neighbor_index is None else \
             np.ascontiguousarray(neighbor_index, dtype=np.int32).reshape(n, 27)
         offsets = np.zeros(n, dtype=np.uint64)
         counts = np.zeros(n, dtype=np.uint32)
         total = C.c_uint64(0)
-        rc = self._lib.hb_mesh(self._h, ptr(pts), n, ptr(ids), ptr(nbr), None, 0, ptr(offsets), ptr(counts),
-                               C.byref(total))
+        rc = fn(self._h, ptr(pts), n, ptr(ids), ptr(nbr), None, 0, ptr(offsets), ptr(counts), C.byref(total))
         if rc not in (_lib.HB_OK, _lib.HB_ERR_CAPACITY):
             check(rc)
         inst = np.zeros(total.value, dtype=INSTANCE_DTYPE)
         if total.value:
-            check(self._lib.hb_mesh(self._h, ptr(pts), n, ptr(ids), ptr(nbr), ptr(inst), total.value, ptr(offsets),
-                                    ptr(counts), C.byref(total)))
+            check(fn(self._h, ptr(pts), n, ptr(ids), ptr(nbr), ptr(inst), total.value, ptr(offsets), ptr(counts),
+                     C.byref(total)))
         return {"instances": inst, "offsets": offsets, "counts": counts}
 
     # -- fused region ----------------------------------------------------------------------

@@ -570,61 +570,85 @@ size_t hb_dev_mesh_workspace_bytes(size_t n) {
     return a + b + scan_workspace_bytes(n) + 256;
 }
 
-int hb_dev_mesh(hb_ctx* c, void* stream, const hb_chunk_pt* d_pts, size_t n, const uint16_t* d_ids,
-                const int32_t* d_neighbor_index, void* d_workspace, hb_instance3d* d_out, uint64_t out_capacity,
-                uint64_t* d_offsets, uint32_t* d_counts, uint64_t* d_total) {
-    if (!c || !d_total) return fail(HB_ERR_INVALID, "null argument");
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+}  // extern "C"
+
+namespace {
+
+// workspace layout shared by the ids and the PaletteCube (flags) paths: bitmaps | summary | scan | [face planes]
+struct MeshWs {
+    uint32_t* bitmaps;
+    uint32_t* summary;
+    void* scan;
+    uint32_t* planes;  // only in flags mode
+};
+size_t mesh_ws_bytes(size_t n, bool flags) {
+    return hb_dev_mesh_workspace_bytes(n) + (flags ? n * 6 * HB_CHUNK_AREA * sizeof(uint32_t) : 0);
+}
+MeshWs mesh_ws(void* d_workspace, size_t n, bool flags) {
+    uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+    MeshWs w;
+    w.bitmaps = reinterpret_cast<uint32_t*>(ws);
+    ws += n * HB_CHUNK_AREA * sizeof(uint32_t);
+    w.summary = reinterpret_cast<uint32_t*>(ws);
+    ws += (n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    w.scan = ws;
+    ws += (scan_workspace_bytes(n) + 255) & ~(size_t)255;
+    w.planes = flags ? reinterpret_cast<uint32_t*>(ws) : nullptr;
+    return w;
+}
+
+// pack + count + scan (+ emit when d_out): `blocks` are u16 ids, or hb_palette_cube when flags is set
+int dev_mesh_impl(hb_ctx* c, cudaStream_t s, bool flags, const hb_chunk_pt* d_pts, size_t n, const void* d_blocks,
+                  const int32_t* d_nbr, void* d_workspace, hb_instance3d* d_out, uint64_t out_capacity, uint64_t* d_offsets,
+                  uint32_t* d_counts, uint64_t* d_total) {
     HB_CUDA(cudaMemsetAsync(d_total, 0, 4 * sizeof(uint64_t), s));
     if (n == 0) return HB_OK;
-    if (!d_pts || !d_ids || !d_neighbor_index || !d_workspace || !d_offsets || !d_counts)
-        return fail(HB_ERR_INVALID, "null argument");
-    uint8_t* ws = static_cast<uint8_t*>(d_workspace);
-    uint32_t* bitmaps = reinterpret_cast<uint32_t*>(ws);
-    ws += n * HB_CHUNK_AREA * sizeof(uint32_t);
-    uint32_t* summary = reinterpret_cast<uint32_t*>(ws);
-    ws += (n * sizeof(uint32_t) + 255) & ~(size_t)255;
-    void* scan_ws = ws;
-    HB_CUDA(launch_pack(s, d_ids, n, c->mats.n_materials, bitmaps, summary, d_total));
-    HB_CUDA(launch_mesh_ids(s, false, c->tables, c->d_mats, d_pts, n, d_ids, d_neighbor_index, bitmaps, summary, d_counts,
+    const MeshWs w = mesh_ws(d_workspace, n, flags);
+    if (flags)
+        HB_CUDA(launch_pack_cubes(s, static_cast<const hb_palette_cube*>(d_blocks), n, c->mats.n_materials, w.bitmaps, w.summary,
+                                  w.planes, d_total));
+    else
+        HB_CUDA(launch_pack(s, static_cast<const uint16_t*>(d_blocks), n, c->mats.n_materials, w.bitmaps, w.summary, d_total));
+    HB_CUDA(launch_mesh_ids(s, false, c->tables, c->d_mats, d_pts, n, d_blocks, d_nbr, w.bitmaps, w.summary, w.planes, d_counts,
                             nullptr, nullptr, 0, d_total));
-    HB_CUDA(launch_scan(s, d_counts, n, d_offsets, scan_ws, d_total, false));
+    HB_CUDA(launch_scan(s, d_counts, n, d_offsets, w.scan, d_total, false));
     if (d_out)
-        HB_CUDA(launch_mesh_ids(s, true, c->tables, c->d_mats, d_pts, n, d_ids, d_neighbor_index, bitmaps, summary, d_counts,
-                                d_offsets, d_out, out_capacity, d_total));
+        HB_CUDA(launch_mesh_ids(s, true, c->tables, c->d_mats, d_pts, n, d_blocks, d_nbr, w.bitmaps, w.summary, w.planes,
+                                d_counts, d_offsets, d_out, out_capacity, d_total));
     return HB_OK;
 }
 
-int hb_mesh(hb_ctx* c, const hb_chunk_pt* pts, size_t n, const uint16_t* ids, const int32_t* neighbor_index,
-            hb_instance3d* out, uint64_t out_capacity, uint64_t* out_offsets, uint32_t* out_counts, uint64_t* out_total) {
+// host-pointer meshing shared by hb_mesh (ids) and hb_mesh_cubes (PaletteCube with flags)
+int mesh_host_impl(hb_ctx* c, bool flags, const hb_chunk_pt* pts, size_t n, const void* blocks, const int32_t* neighbor_index,
+                   hb_instance3d* out, uint64_t out_capacity, uint64_t* out_offsets, uint32_t* out_counts, uint64_t* out_total) {
     if (!c || !out_total) return fail(HB_ERR_INVALID, "null argument");
     *out_total = 0;
     if (n == 0) return HB_OK;
-    if (!pts || !ids || !neighbor_index || !out_offsets || !out_counts) return fail(HB_ERR_INVALID, "null argument");
+    if (!pts || !blocks || !neighbor_index || !out_offsets || !out_counts) return fail(HB_ERR_INVALID, "null argument");
     for (size_t i = 0; i < n; ++i)
         if (!coord_ok(pts[i].x) || !coord_ok(pts[i].y) || !coord_ok(pts[i].z))
             return fail(HB_ERR_RANGE, "chunk %zu outside +-%d", i, HB_MAX_CHUNK_COORD);
     for (size_t i = 0; i < n * 27; ++i)
         if (neighbor_index[i] < -1 || neighbor_index[i] >= (int64_t)n)
             return fail(HB_ERR_INVALID, "neighbor_index[%zu] = %d out of range", i, neighbor_index[i]);
+    const size_t block_bytes = n * HB_CHUNK_VOLUME * (flags ? sizeof(hb_palette_cube) : sizeof(uint16_t));
     std::lock_guard<std::mutex> lk(c->mu);
     HB_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     HB_CUDA(c->d_pts.reserve(n * sizeof(hb_chunk_pt)));
-    HB_CUDA(c->d_ids.reserve(n * HB_CHUNK_VOLUME * sizeof(uint16_t)));
+    HB_CUDA(c->d_ids.reserve(block_bytes));
     HB_CUDA(c->d_nbr.reserve(n * 27 * sizeof(int32_t)));
-    HB_CUDA(c->d_bitmaps.reserve(hb_dev_mesh_workspace_bytes(n)));
+    HB_CUDA(c->d_bitmaps.reserve(mesh_ws_bytes(n, flags)));
     HB_CUDA(c->d_counts.reserve(n * sizeof(uint32_t)));
     HB_CUDA(c->d_offsets.reserve(n * sizeof(uint64_t)));
     HB_CUDA(c->d_total.reserve(4 * sizeof(uint64_t)));
     HB_CUDA(c->h_total.reserve(4 * sizeof(uint64_t)));
     HB_CUDA(cudaMemcpyAsync(c->d_pts.p, pts, n * sizeof(hb_chunk_pt), cudaMemcpyHostToDevice, s));
-    HB_CUDA(cudaMemcpyAsync(c->d_ids.p, ids, n * HB_CHUNK_VOLUME * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    HB_CUDA(cudaMemcpyAsync(c->d_ids.p, blocks, block_bytes, cudaMemcpyHostToDevice, s));
     HB_CUDA(cudaMemcpyAsync(c->d_nbr.p, neighbor_index, n * 27 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     // pass 1: pack + count + scan (no instance buffer yet)
-    int rc = hb_dev_mesh(c, s, c->d_pts.as<hb_chunk_pt>(), n, c->d_ids.as<uint16_t>(), c->d_nbr.as<int32_t>(),
-                         c->d_bitmaps.p, nullptr, 0, c->d_offsets.as<uint64_t>(), c->d_counts.as<uint32_t>(),
-                         c->d_total.as<uint64_t>());
+    int rc = dev_mesh_impl(c, s, flags, c->d_pts.as<hb_chunk_pt>(), n, c->d_ids.p, c->d_nbr.as<int32_t>(), c->d_bitmaps.p,
+                           nullptr, 0, c->d_offsets.as<uint64_t>(), c->d_counts.as<uint32_t>(), c->d_total.as<uint64_t>());
     if (rc != HB_OK) return rc;
     HB_CUDA(cudaMemcpyAsync(c->h_total.p, c->d_total.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     HB_CUDA(cudaStreamSynchronize(s));
@@ -641,16 +665,38 @@ int hb_mesh(hb_ctx* c, const hb_chunk_pt* pts, size_t n, const uint16_t* ids, co
     }
     if (tot[0]) {
         HB_CUDA(c->d_out.reserve(tot[0] * sizeof(hb_instance3d)));
-        const uint8_t* ws = c->d_bitmaps.as<uint8_t>();
-        const uint32_t* bitmaps = reinterpret_cast<const uint32_t*>(ws);
-        const uint32_t* summary = reinterpret_cast<const uint32_t*>(ws + n * HB_CHUNK_AREA * sizeof(uint32_t));
-        HB_CUDA(launch_mesh_ids(s, true, c->tables, c->d_mats, c->d_pts.as<hb_chunk_pt>(), n, c->d_ids.as<uint16_t>(),
-                                c->d_nbr.as<int32_t>(), bitmaps, summary, c->d_counts.as<uint32_t>(),
-                                c->d_offsets.as<uint64_t>(), c->d_out.as<hb_instance3d>(), tot[0], c->d_total.as<uint64_t>()));
+        const MeshWs w = mesh_ws(c->d_bitmaps.p, n, flags);
+        HB_CUDA(launch_mesh_ids(s, true, c->tables, c->d_mats, c->d_pts.as<hb_chunk_pt>(), n, c->d_ids.p, c->d_nbr.as<int32_t>(),
+                                w.bitmaps, w.summary, w.planes, c->d_counts.as<uint32_t>(), c->d_offsets.as<uint64_t>(),
+                                c->d_out.as<hb_instance3d>(), tot[0], c->d_total.as<uint64_t>()));
         HB_CUDA(cudaMemcpyAsync(out, c->d_out.p, tot[0] * sizeof(hb_instance3d), cudaMemcpyDeviceToHost, s));
     }
     HB_CUDA(cudaStreamSynchronize(s));
     return HB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_dev_mesh(hb_ctx* c, void* stream, const hb_chunk_pt* d_pts, size_t n, const uint16_t* d_ids,
+                const int32_t* d_neighbor_index, void* d_workspace, hb_instance3d* d_out, uint64_t out_capacity,
+                uint64_t* d_offsets, uint32_t* d_counts, uint64_t* d_total) {
+    if (!c || !d_total) return fail(HB_ERR_INVALID, "null argument");
+    if (n && (!d_pts || !d_ids || !d_neighbor_index || !d_workspace || !d_offsets || !d_counts))
+        return fail(HB_ERR_INVALID, "null argument");
+    return dev_mesh_impl(c, stream ? (cudaStream_t)stream : c->stream, false, d_pts, n, d_ids, d_neighbor_index, d_workspace,
+                         d_out, out_capacity, d_offsets, d_counts, d_total);
+}
+
+int hb_mesh(hb_ctx* c, const hb_chunk_pt* pts, size_t n, const uint16_t* ids, const int32_t* neighbor_index,
+            hb_instance3d* out, uint64_t out_capacity, uint64_t* out_offsets, uint32_t* out_counts, uint64_t* out_total) {
+    return mesh_host_impl(c, false, pts, n, ids, neighbor_index, out, out_capacity, out_offsets, out_counts, out_total);
+}
+
+int hb_mesh_cubes(hb_ctx* c, const hb_chunk_pt* pts, size_t n, const hb_palette_cube* cubes, const int32_t* neighbor_index,
+                  hb_instance3d* out, uint64_t out_capacity, uint64_t* out_offsets, uint32_t* out_counts, uint64_t* out_total) {
+    return mesh_host_impl(c, true, pts, n, cubes, neighbor_index, out, out_capacity, out_offsets, out_counts, out_total);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -55,10 +55,14 @@ cudaError_t launch_noise3d(cudaStream_t s, const WorldDev& w, float sx, float sy
 
 cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_materials, uint32_t* d_bitmaps,
                         uint32_t* d_summary, uint64_t* d_total);
+cudaError_t launch_pack_cubes(cudaStream_t s, const hb_palette_cube* d_cubes, size_t n, int n_materials,
+                              uint32_t* d_bitmaps, uint32_t* d_summary, uint32_t* d_planes, uint64_t* d_total);
+// d_blocks: u16 ids (d_planes == nullptr: faces recomputed) or hb_palette_cube (faces from d_planes [n][6][1024])
 cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
-                            const hb_chunk_pt* d_pts, size_t n, const uint16_t* d_ids, const int32_t* d_nbr,
-                            const uint32_t* d_bitmaps, const uint32_t* d_summary, uint32_t* d_counts,
-                            const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity, uint64_t* d_total);
+                            const hb_chunk_pt* d_pts, size_t n, const void* d_blocks, const int32_t* d_nbr,
+                            const uint32_t* d_bitmaps, const uint32_t* d_summary, const uint32_t* d_planes,
+                            uint32_t* d_counts, const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
+                            uint64_t* d_total);
 cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
                                const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
                                const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,

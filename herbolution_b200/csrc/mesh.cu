@@ -160,19 +160,34 @@ __device__ __forceinline__ void column_masks(const u64* __restrict__ occ, int x,
     }
 }
 
+// Where a column's six visible-face masks come from: recomputed from the occupancy tile (the state the
+// reference's flags converge to), or read from face planes extracted from cube.flags (literal generate_mesh).
+struct FacesFromOcc {
+    const u64* occ;
+    __device__ __forceinline__ void operator()(int x, int z, uint32_t m[6]) const { column_masks(occ, x, z, m); }
+};
+struct FacesFromPlanes {
+    const uint32_t* planes;  // this chunk: [6][1024], word = column x*32+z, bit y
+    __device__ __forceinline__ void operator()(int x, int z, uint32_t m[6]) const {
+        const uint32_t* p = planes + x * 32 + z;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) m[f] = __ldg(p + f * HB_CHUNK_AREA);
+    }
+};
+
 // Meshes the occupancy tile in sm.occ (already built and synchronised).  Column mapping: thread t
 // owns columns (x = k*8 + t/32, z = t%32), k = 0..3, so a warp reads 32 consecutive tile words.
 // Returns the chunk's quad count (all threads).  EMIT additionally writes the instances at `out`
 // (16-byte aligned), zero-filling up to the next multiple of 4 instances.
-template <bool EMIT, class MatFn>
-__device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, int bx, int by, int bz,
+template <bool EMIT, class MatFn, class FacesFn>
+__device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, const FacesFn& faces, int bx, int by, int bz,
                                               const MaterialsDev* __restrict__ mats, float* __restrict__ out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t cnt[4], incl[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         uint32_t m[6];
-        column_masks(sm.occ, k * 8 + warp, lane, m);
+        faces(k * 8 + warp, lane, m);
         const uint32_t c = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]) + __popc(m[5]);
         cnt[k] = c;
         incl[k] = warp_incl_scan(c, lane);
@@ -202,7 +217,7 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, in
             if (cnt[k] == 0 || o >= d0 + kDescCap || o + cnt[k] <= d0) continue;
             const uint32_t Lc = (uint32_t)(((k * 8 + warp) << 10) | (lane << 5));
             uint32_t m[6];
-            column_masks(sm.occ, k * 8 + warp, lane, m);  // cheap to recompute; keeps registers free
+            faces(k * 8 + warp, lane, m);  // cheap to re-evaluate; keeps registers free
             uint32_t any = m[0] | m[1] | m[2] | m[3] | m[4] | m[5];
             while (any) {
                 const int y = __ffs(any) - 1;
@@ -357,9 +372,66 @@ __global__ void __launch_bounds__(kT) k_pack(const uint16_t* __restrict__ ids, s
     }
 }
 
+// K3a for PaletteCube input (literal generate_mesh): occupancy bitmap (material.is_some()) + summary as k_pack,
+// plus six face planes from cube.flags: CubeFlags::faces() = (value & 1) ? (value >> 1) & 63 : none
+// (server/src/chunk/cube.rs:35-41), kept only where the voxel has a material (chunk.rs:187 gates on it).
+__global__ void __launch_bounds__(kT) k_pack_cubes(const hb_palette_cube* __restrict__ cubes, size_t n, int n_materials,
+                                                   uint32_t* __restrict__ bitmaps, uint32_t* __restrict__ summary,
+                                                   uint32_t* __restrict__ planes, u64* __restrict__ total) {
+    __shared__ uint32_t s_red[8][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(cubes + chunk * HB_CHUNK_VOLUME);
+        uint32_t any = 0, bad = 0;
+        for (int it = 0; it < 16; ++it) {
+            const int u = it * kT + tid;  // 8-voxel unit (64 bytes): column u>>2, y0 = (u&3)*8
+            uint32_t m8 = 0, f8[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 v = __ldg(src + u * 4 + j);  // two cubes: {material|pad, flags, material|pad, flags}
+                const uint32_t mat0 = v.x & 0xFFFFu, mat1 = v.z & 0xFFFFu;
+                const uint32_t fa0 = (mat0 && (v.y & 1u)) ? (v.y >> 1) & 63u : 0u;
+                const uint32_t fa1 = (mat1 && (v.w & 1u)) ? (v.w >> 1) & 63u : 0u;
+                bad |= (mat0 > (uint32_t)n_materials) | (mat1 > (uint32_t)n_materials);
+                m8 |= ((mat0 ? 1u : 0u) | (mat1 ? 2u : 0u)) << (2 * j);
+#pragma unroll
+                for (int f = 0; f < 6; ++f) f8[f] |= (((fa0 >> f) & 1u) | (((fa1 >> f) & 1u) << 1)) << (2 * j);
+            }
+            const int sh = (u & 3) * 8, c = u >> 2;
+            uint32_t w = m8 << sh;
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            if ((lane & 3) == 0) bitmaps[chunk * HB_CHUNK_AREA + c] = w;
+            any |= w;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+                uint32_t pw = f8[f] << sh;
+                pw |= __shfl_xor_sync(0xffffffffu, pw, 1);
+                pw |= __shfl_xor_sync(0xffffffffu, pw, 2);
+                if ((lane & 3) == 0) planes[(chunk * 6 + f) * HB_CHUNK_AREA + c] = pw;
+            }
+        }
+        any = __reduce_or_sync(0xffffffffu, any);
+        bad = __reduce_or_sync(0xffffffffu, bad);
+        if (lane == 0) { s_red[warp][0] = any; s_red[warp][1] = bad; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t a = 0, b = 0;
+            for (int i = 0; i < 8; ++i) { a |= s_red[i][0]; b |= s_red[i][1]; }
+            summary[chunk] = a ? 1u : 0u;  // only "any solid" is used in flags mode
+            if (b) atomicOr(total + 2, 2ULL);  // error path only: unknown material id
+        }
+        __syncthreads();
+    }
+}
+
 struct MatIds {
     const uint16_t* ids;  // centre chunk
     __device__ __forceinline__ uint32_t operator()(uint32_t L, int, int, int) const { return __ldg(ids + L); }
+};
+struct MatCubes {
+    const hb_palette_cube* cubes;  // centre chunk, reference PaletteCube layout
+    __device__ __forceinline__ uint32_t operator()(uint32_t L, int, int, int) const { return __ldg(&cubes[L].material); }
 };
 
 // shell index (dx+1)*9 + (dy+1)*3 + (dz+1) of the face neighbour (client/src/world/chunk.rs:158-174)
@@ -369,20 +441,22 @@ __device__ __forceinline__ int face_shell_index(int f) {
 }
 
 // K3b/K3c: count (EMIT=false) or emit (EMIT=true) for arbitrary block arrays, persistent CTAs.
-template <bool EMIT>
+// FLAGS: `blocks` are hb_palette_cube arrays and the visible faces are taken from `planes` (cube.flags) instead of
+// being recomputed from occupancy.
+template <bool EMIT, bool FLAGS>
 __global__ void __launch_bounds__(kT, kCtasPerSm)
 k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_chunk_pt* __restrict__ pts, size_t n,
-           const uint16_t* __restrict__ ids, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
-           const uint32_t* __restrict__ summary, uint32_t* __restrict__ counts, const u64* __restrict__ offsets,
-           float* __restrict__ out, u64 capacity, u64* __restrict__ total) {
+           const void* __restrict__ blocks, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
+           const uint32_t* __restrict__ summary, const uint32_t* __restrict__ planes, uint32_t* __restrict__ counts,
+           const u64* __restrict__ offsets, float* __restrict__ out, u64 capacity, u64* __restrict__ total) {
     __shared__ MeshSmem sm;
     const int tid = threadIdx.x;
     if (EMIT) load_tables(sm, tb);
     for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         // block-uniform early outs from the summaries
         const uint32_t s = summary[chunk];
-        bool trivial = !(s & 1u);
-        if (!trivial && (s & 2u)) {
+        bool trivial = !(s & 1u);  // no solid voxel: nothing to draw in either mode
+        if (!FLAGS && !trivial && (s & 2u)) {
             trivial = true;
 #pragma unroll
             for (int f = 0; f < 6; ++f) {
@@ -424,9 +498,16 @@ k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
             sm.occ[i] = v;
         }
         __syncthreads();
-        const MatIds mat{ids + chunk * HB_CHUNK_VOLUME};
-        const uint32_t q = mesh_tile<EMIT>(sm, mat, pt.x * 32, pt.y * 32, pt.z * 32, mats,
-                                           EMIT ? out + off * 25ULL : nullptr);
+        uint32_t q;
+        if (FLAGS) {
+            const MatCubes mat{static_cast<const hb_palette_cube*>(blocks) + chunk * HB_CHUNK_VOLUME};
+            q = mesh_tile<EMIT>(sm, mat, FacesFromPlanes{planes + chunk * 6 * HB_CHUNK_AREA}, pt.x * 32, pt.y * 32, pt.z * 32,
+                                mats, EMIT ? out + off * 25ULL : nullptr);
+        } else {
+            const MatIds mat{static_cast<const uint16_t*>(blocks) + chunk * HB_CHUNK_VOLUME};
+            q = mesh_tile<EMIT>(sm, mat, FacesFromOcc{sm.occ}, pt.x * 32, pt.y * 32, pt.z * 32, mats,
+                                EMIT ? out + off * 25ULL : nullptr);
+        }
         if (!EMIT && tid == 0) counts[chunk] = q;
     }
     if (EMIT) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
@@ -618,8 +699,8 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
             if (EMIT && tid == 32) sm.rng_seed = siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
             __syncthreads();
             const MatHeights mat{sm.hts, a};
-            const uint32_t q = mesh_tile<EMIT>(sm, mat, (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32, mats,
-                                               EMIT ? out + off * 25ULL : nullptr);
+            const uint32_t q = mesh_tile<EMIT>(sm, mat, FacesFromOcc{sm.occ}, (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32,
+                                               mats, EMIT ? out + off * 25ULL : nullptr);
             if (!EMIT && tid == 0) counts[chunk] = q;
         }
     }
@@ -746,19 +827,29 @@ cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_m
     return cudaGetLastError();
 }
 
+cudaError_t launch_pack_cubes(cudaStream_t s, const hb_palette_cube* d_cubes, size_t n, int n_materials,
+                              uint32_t* d_bitmaps, uint32_t* d_summary, uint32_t* d_planes, uint64_t* d_total) {
+    if (n == 0) return cudaSuccess;
+    size_t grid = (size_t)num_sms() * 8;
+    if (grid > n) grid = n;
+    k_pack_cubes<<<(unsigned)grid, kT, 0, s>>>(d_cubes, n, n_materials, d_bitmaps, d_summary, d_planes, (u64*)d_total);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
-                            const hb_chunk_pt* d_pts, size_t n, const uint16_t* d_ids, const int32_t* d_nbr,
-                            const uint32_t* d_bitmaps, const uint32_t* d_summary, uint32_t* d_counts,
-                            const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity, uint64_t* d_total) {
+                            const hb_chunk_pt* d_pts, size_t n, const void* d_blocks, const int32_t* d_nbr,
+                            const uint32_t* d_bitmaps, const uint32_t* d_summary, const uint32_t* d_planes,
+                            uint32_t* d_counts, const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
+                            uint64_t* d_total) {
     if (n == 0) return cudaSuccess;
     size_t grid = (size_t)num_sms() * kCtasPerSm;
     if (grid > n) grid = n;
-    if (emit)
-        k_mesh_ids<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, d_pts, n, d_ids, d_nbr, d_bitmaps, d_summary, d_counts,
-                                                       (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total);
-    else
-        k_mesh_ids<false><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, d_pts, n, d_ids, d_nbr, d_bitmaps, d_summary, d_counts,
-                                                        (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total);
+#define HB_LAUNCH(E, F)                                                                                              \
+    k_mesh_ids<E, F><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, d_pts, n, d_blocks, d_nbr, d_bitmaps, d_summary, d_planes, \
+                                                   d_counts, (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total)
+    if (d_planes) { if (emit) HB_LAUNCH(true, true); else HB_LAUNCH(false, true); }
+    else { if (emit) HB_LAUNCH(true, false); else HB_LAUNCH(false, false); }
+#undef HB_LAUNCH
     return cudaGetLastError();
 }
 

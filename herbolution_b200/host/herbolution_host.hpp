@@ -168,10 +168,13 @@ class ChunkGenerator {
     std::vector<ChunkPt> pending_;
 };
 
-// client/src/world/chunk.rs:97-102 (cubes reduced to their material ids)
+// client/src/world/chunk.rs:97-102.  `cubes` = material ids (faces recomputed on the GPU); if `data` is non-empty
+// it holds the PaletteCubes as received from the server and the faces are read from cube.flags (literal
+// generate_mesh: hb_mesh_cubes), which is what the incremental dig/place path needs.
 struct ChunkData {
     ChunkPt position;
-    std::vector<uint16_t> cubes;  // CHUNK_VOLUME entries, index linearize(x, y, z)
+    std::vector<uint16_t> cubes;    // CHUNK_VOLUME entries, index linearize(x, y, z)
+    std::vector<PaletteCube> data;  // optional, CHUNK_VOLUME entries
 };
 using ChunkShell = std::array<std::shared_ptr<const ChunkData>, 27>;
 using ChunkTable = std::unordered_map<ChunkPt, std::shared_ptr<ChunkData>, ChunkPtHash>;
@@ -202,21 +205,32 @@ inline MeshBatch mesh_chunks(Context& ctx, const std::vector<const ChunkData*>& 
     out.counts.assign(n, 0);
     if (!n) return out;
     std::vector<hb_chunk_pt> pts(n);
-    std::vector<uint16_t> ids(n * CHUNK_VOLUME);
+    const bool flags = !chunks[0]->data.empty();
+    std::vector<uint16_t> ids(flags ? 0 : n * CHUNK_VOLUME);
+    std::vector<PaletteCube> cubes(flags ? n * CHUNK_VOLUME : 0);
     for (size_t i = 0; i < n; ++i) {
         pts[i] = {chunks[i]->position.x, chunks[i]->position.y, chunks[i]->position.z};
-        if (chunks[i]->cubes.size() != (size_t)CHUNK_VOLUME) throw Error(HB_ERR_INVALID, "ChunkData::cubes must hold 32768 ids");
-        std::copy(chunks[i]->cubes.begin(), chunks[i]->cubes.end(), ids.begin() + (ptrdiff_t)(i * CHUNK_VOLUME));
+        if (flags) {
+            if (chunks[i]->data.size() != (size_t)CHUNK_VOLUME) throw Error(HB_ERR_INVALID, "ChunkData::data must hold 32768 cubes");
+            std::copy(chunks[i]->data.begin(), chunks[i]->data.end(), cubes.begin() + (ptrdiff_t)(i * CHUNK_VOLUME));
+        } else {
+            if (chunks[i]->cubes.size() != (size_t)CHUNK_VOLUME) throw Error(HB_ERR_INVALID, "ChunkData::cubes must hold 32768 ids");
+            std::copy(chunks[i]->cubes.begin(), chunks[i]->cubes.end(), ids.begin() + (ptrdiff_t)(i * CHUNK_VOLUME));
+        }
     }
     std::vector<int32_t> nbr(n * 27);
     check(hb_build_neighbor_index(pts.data(), n, nbr.data()));
     uint64_t total = 0;
-    int rc = hb_mesh(ctx.raw(), pts.data(), n, ids.data(), nbr.data(), nullptr, 0, out.offsets.data(), out.counts.data(), &total);
+    auto run = [&](Instance3d* dst, uint64_t cap) {
+        return flags ? hb_mesh_cubes(ctx.raw(), pts.data(), n, cubes.data(), nbr.data(), dst, cap, out.offsets.data(),
+                                     out.counts.data(), &total)
+                     : hb_mesh(ctx.raw(), pts.data(), n, ids.data(), nbr.data(), dst, cap, out.offsets.data(),
+                               out.counts.data(), &total);
+    };
+    int rc = run(nullptr, 0);
     if (rc != HB_OK && rc != HB_ERR_CAPACITY) check(rc);
     out.instances.resize(total);
-    if (total)
-        check(hb_mesh(ctx.raw(), pts.data(), n, ids.data(), nbr.data(), out.instances.data(), total, out.offsets.data(),
-                      out.counts.data(), &total));
+    if (total) check(run(out.instances.data(), total));
     return out;
 }
 

@@ -14,16 +14,22 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from ._lib import CHUNK_VOLUME, INSTANCE_DTYPE
+from ._lib import CHUNK_VOLUME, CUBE_DTYPE, INSTANCE_DTYPE
 from .context import Context
 from .generator import ChunkPt
 
 
 @dataclass
 class ChunkData:
-    """client/src/world/chunk.rs:97-102 (cubes reduced to their material ids)."""
+    """client/src/world/chunk.rs:97-102.  `cubes` is either u16[32768] material ids (faces are recomputed) or
+    CUBE_DTYPE[32768] PaletteCubes as received from the server (faces are read from cube.flags: the literal
+    generate_mesh, needed on the incremental dig/place path)."""
     position: ChunkPt
-    cubes: np.ndarray  # u16[32768], index L = x*1024 + z*32 + y
+    cubes: np.ndarray  # index L = x*1024 + z*32 + y
+
+    @property
+    def has_flags(self) -> bool:
+        return self.cubes.dtype == CUBE_DTYPE
 
 
 def create_chunk_shell(chunks: Dict[ChunkPt, ChunkData], position: ChunkPt) -> List[Optional[ChunkData]]:
@@ -44,8 +50,13 @@ def generate_mesh(ctx: Context, shell: Sequence[Optional[ChunkData]], instances:
         raise ValueError("shell[13] (the centre chunk) must be present")  # the reference unwrap()s
     present = [(i, c) for i, c in enumerate(shell) if c is not None]
     pts = np.array([c.position for _, c in present], dtype=np.int64)
-    ids = np.stack([np.asarray(c.cubes, dtype=np.uint16).reshape(CHUNK_VOLUME) for _, c in present])
-    out = ctx.mesh(pts, ids)
+    if center.has_flags:
+        if not all(c.has_flags for _, c in present):
+            raise ValueError("either every chunk of the shell carries PaletteCubes or none does")
+        out = ctx.mesh_cubes(pts, np.stack([c.cubes.reshape(CHUNK_VOLUME) for _, c in present]))
+    else:
+        ids = np.stack([np.asarray(c.cubes, dtype=np.uint16).reshape(CHUNK_VOLUME) for _, c in present])
+        out = ctx.mesh(pts, ids)
     k = [i for i, _ in present].index(13)
     o, n = int(out["offsets"][k]), int(out["counts"][k])
     instances.append(out["instances"][o:o + n].copy())
@@ -62,7 +73,10 @@ class ChunkMap:
 
     def insert(self, position, cubes: np.ndarray) -> None:
         p = ChunkPt(*map(int, position))
-        self.map[p] = ChunkData(p, np.asarray(cubes, dtype=np.uint16).reshape(CHUNK_VOLUME))
+        cubes = np.asarray(cubes)
+        if cubes.dtype != CUBE_DTYPE:
+            cubes = cubes.astype(np.uint16)
+        self.map[p] = ChunkData(p, cubes.reshape(CHUNK_VOLUME))
         self._dirty.add(p)
 
     def update(self) -> int:
@@ -72,8 +86,8 @@ class ChunkMap:
             return 0
         pts_list = list(self.map.keys())
         pts = np.array(pts_list, dtype=np.int64)
-        ids = np.stack([self.map[p].cubes for p in pts_list])
-        out = self.ctx.mesh(pts, ids)
+        blocks = np.stack([self.map[p].cubes for p in pts_list])
+        out = self.ctx.mesh_cubes(pts, blocks) if blocks.dtype == CUBE_DTYPE else self.ctx.mesh(pts, blocks)
         for i, p in enumerate(pts_list):
             if p in self._dirty:
                 o, n = int(out["offsets"][i]), int(out["counts"][i])

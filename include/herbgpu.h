@@ -141,6 +141,16 @@ HB_API int hb_mesh(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, const uint16_t
             const int32_t *neighbor_index, hb_instance3d *out, uint64_t out_capacity,
             uint64_t *out_offsets, uint32_t *out_counts, uint64_t *out_total);
 
+/* Literal drop-in of client generate_mesh (client/src/world/chunk.rs:176-223): the visible faces are READ from
+ * cube.flags -- CubeFlags::faces(), server/src/chunk/cube.rs:35-41 -- exactly as the server left them (CubeMesh::set,
+ * cull_shared_faces, ChunkMap::set_cube incl. its border quirks, server/src/chunk/map.rs:81-151), instead of being
+ * recomputed from the materials; AO probes read material.is_some() of the 27-shell.  Use this for the incremental
+ * dig/place path, where the reference's flags are not the closed-form visibility.
+ * cubes: n x 32768 hb_palette_cube.  Everything else as hb_mesh. */
+HB_API int hb_mesh_cubes(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, const hb_palette_cube *cubes,
+                         const int32_t *neighbor_index, hb_instance3d *out, uint64_t out_capacity,
+                         uint64_t *out_offsets, uint32_t *out_counts, uint64_t *out_total);
+
 /* ---- fused generate + mesh of a region ---- */
 
 /* Sink for hb_generate_mesh_region: called once per slab (a contiguous range of region chunk

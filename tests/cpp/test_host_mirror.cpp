@@ -123,6 +123,29 @@ int main(int argc, char** argv) {
                !std::memcmp(inst.data(), cm.meshes[pts[4]].data(), inst.size() * sizeof(Instance3d)),
            "generate_mesh(shell) == batched mesh");
 
+    // flags-driven (literal) mesher: PaletteCubes as generate() leaves them, before any cull_shared_faces
+    {
+        ChunkTable table;
+        for (const CubeMesh& m : meshes) {
+            auto d = std::make_shared<ChunkData>();
+            d->position = m.position;
+            d->data = m.data;
+            table[m.position] = d;
+        }
+        const ChunkPt centre = pts[7];
+        ChunkShell shell = create_chunk_shell(table, centre);
+        std::vector<Instance3d> got;
+        generate_mesh(*ctx, shell, got);
+        const hbo_cube* oshell[27];
+        for (int i = 0; i < 27; ++i) oshell[i] = shell[(size_t)i] ? reinterpret_cast<const hbo_cube*>(shell[(size_t)i]->data.data()) : nullptr;
+        const int32_t cpos[3] = {centre.x, centre.y, centre.z};
+        const size_t nref = hbo_generate_mesh(oshell, cpos, &pal, nullptr, 0);
+        std::vector<hbo_instance> ref(nref);
+        hbo_generate_mesh(oshell, cpos, &pal, ref.data(), nref);
+        EXPECT(got.size() == nref, "flags mode: %zu quads, oracle %zu", got.size(), nref);
+        if (got.size() == nref) EXPECT(!std::memcmp(got.data(), ref.data(), nref * sizeof(Instance3d)), "flags mode: quads differ");
+    }
+
     // get_noise and error behaviour
     auto tile = params->get_noise(3, -4);
     float ref_tile[CHUNK_AREA];

@@ -380,3 +380,78 @@ def test_region_c4_properties(ctx):
         k = sel.index(c)
         g = out["instances"][int(out["offsets"][k]):int(out["offsets"][k]) + int(out["counts"][k])]
         assert_instances_equal(keep[c], g, f"chunk {c}")
+
+
+# ---------------------------------------------------------------- literal, flags-driven mesher (hb_mesh_cubes)
+def oracle_mesh_cubes_all(pts, cubes, nbr, pal=None):
+    res = []
+    for i in range(len(pts)):
+        shell = [cubes[j] if j >= 0 else None for j in nbr[i]]
+        res.append(O.mesh_cubes_literal(shell, (pts["x"][i], pts["y"][i], pts["z"][i]), pal))
+    return res
+
+
+def test_mesh_cubes_after_set_and_cull(ctx):
+    """PaletteCube arrays exactly as the server leaves them: CubeMesh::set per voxel, then cull_shared_faces
+    for every adjacent pair (load_provided), then one dig + one place through set() in a border voxel."""
+    import ctypes as C
+    w = O.world(0)
+    reg = (-1, 2, 3, 2, -2, 3)
+    pts = region_points(reg)
+    meshes = [O.generate_literal(w, (p["x"], p["y"], p["z"])) for p in pts]
+    nbr = ctx.build_neighbor_index(pts)
+    for i in range(len(pts)):
+        for f_shell in (22, 16, 14):  # +x, +y, +z neighbours: each adjacent pair once
+            j = nbr[i][f_shell]
+            if j >= 0:
+                O.lib().hbo_cull_shared_faces(C.byref(meshes[i]), C.byref(meshes[j]))
+    # incremental edits through the literal set() path (dig the top voxel of a column, place one in the air)
+    for m in meshes[:4]:
+        cubes = O.mesh_cubes(m)
+        solid = np.flatnonzero(cubes["material"] != 0)
+        if len(solid):
+            L = int(solid[-1])
+            O.lib().hbo_mesh_set(C.byref(m), L >> 10, L & 31, (L >> 5) & 31, 0)
+        O.lib().hbo_mesh_set(C.byref(m), 31, 31, 31, 2)
+    cubes = np.stack([O.mesh_cubes(m) for m in meshes])
+    out = ctx.mesh_cubes(pts, cubes, nbr)
+    ref = oracle_mesh_cubes_all(pts, cubes, nbr)
+    assert out["counts"].sum() > 0
+    for i, (g, r) in enumerate(zip(split_chunks(out), ref)):
+        assert_instances_equal(g, r, f"chunk {i}")
+
+
+def test_mesh_cubes_arbitrary_flags(ctx):
+    """The faces drawn are whatever cube.flags says (even inconsistent with the materials, as
+    ChunkMap::set_cube's unconditional insert_faces on border neighbours can leave them)."""
+    rng = np.random.default_rng(21)
+    pts = region_points((0, 0, 2, 1, 0, 2))
+    n = len(pts)
+    cubes = np.zeros((n, 32768), dtype=hb.CUBE_DTYPE)
+    cubes["material"] = (rng.random((n, 32768)) < 0.35) * rng.integers(1, 4, size=(n, 32768))
+    cubes["flags"] = rng.integers(0, 128, size=(n, 32768)) * (rng.random((n, 32768)) < 0.2)
+    nbr = ctx.build_neighbor_index(pts)
+    out = ctx.mesh_cubes(pts, cubes, nbr)
+    ref = oracle_mesh_cubes_all(pts, cubes, nbr)
+    for i, (g, r) in enumerate(zip(split_chunks(out), ref)):
+        assert_instances_equal(g, r, f"chunk {i}")
+    # flags on air voxels and flags without the opaque tag draw nothing
+    cubes2 = np.zeros((1, 32768), dtype=hb.CUBE_DTYPE)
+    cubes2["flags"] = 0x7F
+    assert ctx.mesh_cubes([(0, 0, 0)], cubes2)["counts"][0] == 0
+    cubes2["material"] = 1
+    cubes2["flags"] = 0x7E
+    assert ctx.mesh_cubes([(0, 0, 0)], cubes2)["counts"][0] == 0
+    cubes2["flags"] = 0x7F
+    assert ctx.mesh_cubes([(0, 0, 0)], cubes2)["counts"][0] == 6 * 32768
+
+
+def test_mesh_cubes_equals_mesh_on_settled_world(ctx):
+    """On a settled world (generate + cull of all pairs) flags-driven and recomputed visibility agree."""
+    ctx.set_world(5)
+    reg = (4, 4, 2, 2, -1, 2)
+    pts = region_points(reg)
+    ref = O.region_pipeline(O.world(5), reg, literal=True, threads=4, want_ids=True)
+    a = ctx.mesh(pts, ref["ids"])
+    assert (a["counts"] == ref["counts"]).all()
+    ctx.set_world(0)
