@@ -49,7 +49,7 @@ struct MeshSmem {
     uint32_t warp_tot[32];
     u64 rng_seed;
     int nbr[27];
-    int red[2][8];
+    int red[3][8];
 };
 
 // ---- SipHash-1-3 with zero keys over the 12 bytes of ChunkPt: std DefaultHasher as used at
@@ -175,6 +175,56 @@ struct FacesFromPlanes {
     }
 };
 
+// One window of up to 32 quads, one lane per quad (L = voxel index, f = face, ao = four 2-bit vertex_ao values):
+// material, colour draw, 25 words into the warp-private staging buffer `ws` (stride 25: bank-conflict free), then
+// one TMA bulk shared->global copy (UBLKCP) of the whole window by lane 0 instead of 200 LDS.128 + STG.128 through
+// the LSU.  The window is zero-padded to a multiple of 4 quads.  The wait for the engine to release the buffer from
+// this warp's previous window sits after the register work so the two overlap.
+template <class MatFn>
+__device__ __forceinline__ void emit_window(MeshSmem& sm, const MatFn& mat, const MaterialsDev* __restrict__ mats,
+                                            float* __restrict__ ws, uint32_t ws_shared, char* __restrict__ gdst, uint32_t nw,
+                                            uint32_t L, uint32_t f, uint32_t ao, int bx, int by, int bz) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nw4 = (nw + 3u) & ~3u;
+    float* sq = ws + lane * 25;
+    const bool active = (uint32_t)lane < nw;
+    const int x = L >> 10, z = (L >> 5) & 31, y = L & 31;
+    float4 rgba = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        const uint32_t id = mat(L, x, y, z);
+        // Material::get_color(perms[face]) (server/src/chunk/material.rs:67-71)
+        const float p = wyrand_f32_at(sm.rng_seed, 6u * L + f);
+        const int nc = __ldg(&mats->n_colors[id - 1]);
+        const int ci = __float2int_rz(__fmul_rn(__int2float_rn(nc > 0 ? nc - 1 : 0), p));
+        rgba = __ldg(reinterpret_cast<const float4*>(mats->rgba[id - 1][ci]));
+    }
+    if (lane == 0) bulk_wait_read();  // previous window of this warp has left the staging buffer
+    __syncwarp();
+    if (active) {
+        const float4* fm = reinterpret_cast<const float4*>(sm.face_mat[f]);
+        const float4 m0 = fm[0], m1 = fm[1], m2 = fm[2];
+        sq[0] = m0.x; sq[1] = m0.y; sq[2] = m0.z; sq[3] = m0.w;
+        sq[4] = m1.x; sq[5] = m1.y; sq[6] = m1.z; sq[7] = m1.w;
+        sq[8] = m2.x; sq[9] = m2.y; sq[10] = m2.z; sq[11] = m2.w;
+        sq[12] = __int2float_rn(bx + x);  // (chunk_position + position).cast::<f32>()
+        sq[13] = __int2float_rn(by + y);
+        sq[14] = __int2float_rn(bz + z);
+        sq[15] = 1.0f;
+        sq[16] = rgba.x; sq[17] = rgba.y; sq[18] = rgba.z; sq[19] = rgba.w;
+        sq[20] = __uint_as_float(0u);  // light = 0 (chunk.rs:207)
+        sq[21] = sm.ao_lut[ao & 3u];
+        sq[22] = sm.ao_lut[(ao >> 2) & 3u];
+        sq[23] = sm.ao_lut[(ao >> 4) & 3u];
+        sq[24] = sm.ao_lut[(ao >> 6) & 3u];
+    } else if ((uint32_t)lane < nw4) {
+#pragma unroll
+        for (int i = 0; i < 25; ++i) sq[i] = 0.0f;
+    }
+    fence_proxy_async_smem();  // generic-proxy writes must be fenced for the async proxy
+    __syncwarp();
+    if (lane == 0) bulk_store(gdst, ws_shared, nw4 * 100u);
+}
+
 // Meshes the occupancy tile in sm.occ (already built and synchronised).  Column mapping: thread t
 // owns columns (x = k*8 + t/32, z = t%32), k = 0..3, so a warp reads 32 consecutive tile words.
 // Returns the chunk's quad count (all threads).  EMIT additionally writes the instances at `out`
@@ -235,57 +285,19 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, co
         }
         __syncthreads();
         const uint32_t nd = min((uint32_t)kDescCap, total - d0);
-        // (b) each warp expands windows of 32 descriptors (one quad per lane: AO, colour, matrix) into its
-        //     private staging buffer and streams them out; no block-level barrier inside this loop
+        // (b) each warp expands windows of 32 descriptors (one quad per lane) and streams them out; no block-level
+        //     barrier inside this loop
         for (uint32_t q0 = warp * 32u; q0 < nd; q0 += (kT / 32) * 32u) {
             const uint32_t nw = min(32u, nd - q0);
-            const uint32_t nw4 = (nw + 3u) & ~3u;
-            float* sq = ws + lane * 25;
-            const bool active = (uint32_t)lane < nw;
             // register phase first: it overlaps the TMA engine still reading this warp's previous window
-            uint32_t f = 0, ao = 0;
-            int x = 0, y = 0, z = 0;
-            float4 rgba = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) {
+            uint32_t L = 0, f = 0, ao = 0;
+            if ((uint32_t)lane < nw) {
                 const uint32_t d = sm.desc[q0 + lane];
-                const uint32_t L = d & 0x7FFFu;
+                L = d & 0x7FFFu;
                 f = d >> 15;
-                x = L >> 10; z = (L >> 5) & 31; y = L & 31;
-                ao = ao_bits(sm.occ, sm.ao_tab[f], x, y, z);
-                const uint32_t id = mat(L, x, y, z);
-                // Material::get_color(perms[face]) (server/src/chunk/material.rs:67-71)
-                const float p = wyrand_f32_at(sm.rng_seed, 6u * L + f);
-                const int nc = __ldg(&mats->n_colors[id - 1]);
-                const int ci = __float2int_rz(__fmul_rn(__int2float_rn(nc > 0 ? nc - 1 : 0), p));
-                rgba = __ldg(reinterpret_cast<const float4*>(mats->rgba[id - 1][ci]));
+                ao = ao_bits(sm.occ, sm.ao_tab[f], L >> 10, L & 31, (L >> 5) & 31);
             }
-            if (lane == 0) bulk_wait_read();  // previous window of this warp has left the staging buffer
-            __syncwarp();
-            if (active) {
-                const float4* fm = reinterpret_cast<const float4*>(sm.face_mat[f]);
-                const float4 m0 = fm[0], m1 = fm[1], m2 = fm[2];
-                sq[0] = m0.x; sq[1] = m0.y; sq[2] = m0.z; sq[3] = m0.w;
-                sq[4] = m1.x; sq[5] = m1.y; sq[6] = m1.z; sq[7] = m1.w;
-                sq[8] = m2.x; sq[9] = m2.y; sq[10] = m2.z; sq[11] = m2.w;
-                sq[12] = __int2float_rn(bx + x);  // (chunk_position + position).cast::<f32>()
-                sq[13] = __int2float_rn(by + y);
-                sq[14] = __int2float_rn(bz + z);
-                sq[15] = 1.0f;
-                sq[16] = rgba.x; sq[17] = rgba.y; sq[18] = rgba.z; sq[19] = rgba.w;
-                sq[20] = __uint_as_float(0u);  // light = 0 (chunk.rs:207)
-                sq[21] = sm.ao_lut[ao & 3u];
-                sq[22] = sm.ao_lut[(ao >> 2) & 3u];
-                sq[23] = sm.ao_lut[(ao >> 4) & 3u];
-                sq[24] = sm.ao_lut[(ao >> 6) & 3u];
-            } else if ((uint32_t)lane < nw4) {
-#pragma unroll
-                for (int i = 0; i < 25; ++i) sq[i] = 0.0f;
-            }
-            // hand the window to the TMA engine: one bulk shared->global copy (UBLKCP) per warp instead of
-            // 200 LDS.128 + STG.128 through the LSU.  Generic-proxy writes must be fenced for the async proxy.
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) bulk_store(out_bytes + (d0 + q0) * 100u, ws_shared, nw4 * 100u);  // < 2^24 bytes per chunk
+            emit_window(sm, mat, mats, ws, ws_shared, out_bytes + (d0 + q0) * 100u, nw, L, f, ao, bx, by, bz);  // < 2^24 B / chunk
         }
         if (d0 + kDescCap < total) __syncthreads();  // descriptors are rewritten in the next round
     }
@@ -529,7 +541,8 @@ struct MatHeights {
 // Stages the 34x34 heights halo tile of region column (ix, iz): the column's own 32x32 tile (one
 // 128-bit load per thread) plus one row/column from each of the 4 edge neighbours and one value from
 // each of the 4 corner neighbours; columns outside the region are ABSENT.  Also returns this
-// thread's partial max over the centre and min over the whole tile.  Needs kT == 256.
+// thread's partial max over the centre, min over the whole tile (hmin) and min over centre + edges
+// (emin).  Needs kT == 256.
 // Heights relative to the region's lowest voxel (world y = cy0*32), clamped to [-1, 32*ncy + 8] so that all
 // per-layer arithmetic stays in 32 bits (the +8 keeps `h - y > 6`, the stone test, exact up to the region's
 // top voxel); absent columns (INT_MIN) become -1: never solid.
@@ -543,7 +556,7 @@ struct RelHeight {
 };
 template <class Conv>
 __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int32_t* __restrict__ heights, int ix, int iz,
-                                                  int* __restrict__ hts, int& cmax, int& hmin, const Conv& conv) {
+                                                  int* __restrict__ hts, int& cmax, int& hmin, int& emin, const Conv& conv) {
     const int tid = threadIdx.x;
     auto tile_of = [&](int cix, int ciz) -> const int32_t* {
         if (cix < 0 || cix >= r.ncx || ciz < 0 || ciz >= r.ncz) return nullptr;
@@ -558,6 +571,7 @@ __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int3
         const int mx = max(max(v.x, v.y), max(v.z, v.w)), mn = min(min(v.x, v.y), min(v.z, v.w));
         cmax = max(cmax, mx);
         hmin = min(hmin, mn);
+        emin = min(emin, mn);
     }
     if (tid < 128) {  // edges: west (x = -1), east (x = 32), south (z = -1), north (z = 32); 32 values each
         const int side = tid >> 5, j = tid & 31;
@@ -568,6 +582,7 @@ __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int3
         const int h = conv(t ? __ldg(t + src) : kHeightAbsent);
         hts[dst] = h;
         hmin = min(hmin, h);
+        emin = min(emin, h);  // centre + the four edges (everything the six face masks look at)
     } else if (tid < 132) {  // corners
         const int c = tid - 128, dx = (c & 1) ? 1 : -1, dz = (c & 2) ? 1 : -1;
         const int32_t* t = tile_of(ix + dx, iz + dz);
@@ -595,9 +610,9 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
     const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
     for (int colw = blockIdx.x; colw < ncols; colw += gridDim.x) {
     const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
-    int cmax = INT32_MIN, hmin = INT32_MAX;
+    int cmax = INT32_MIN, hmin = INT32_MAX, emin = INT32_MAX;
     __syncthreads();  // previous column's readers of s_h are done
-    load_heights_tile(r, heights, ix, iz, s_h, cmax, hmin, rel);
+    load_heights_tile(r, heights, ix, iz, s_h, cmax, hmin, emin, rel);
     __syncthreads();
     for (int iy0 = 0; iy0 < r.ncy; iy0 += 32) {
         const int nl = min(32, r.ncy - iy0);
@@ -659,15 +674,18 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
     for (int colw = blockIdx.x; colw < ncols; colw += gridDim.x) {
         const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
         __syncthreads();  // previous column's readers of sm.hts / sm.red are done
-        int cmax = INT32_MIN, hmin = INT32_MAX;
-        load_heights_tile(r, heights, ix, iz, sm.hts, cmax, hmin, rel);
+        int cmax = INT32_MIN, hmin = INT32_MAX, emin = INT32_MAX;
+        load_heights_tile(r, heights, ix, iz, sm.hts, cmax, hmin, emin, rel);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
         hmin = __reduce_min_sync(0xffffffffu, hmin);
-        if (lane == 0) { sm.red[0][warp] = cmax; sm.red[1][warp] = hmin; }
+        emin = __reduce_min_sync(0xffffffffu, emin);
+        if (lane == 0) { sm.red[0][warp] = cmax; sm.red[1][warp] = hmin; sm.red[2][warp] = emin; }
         __syncthreads();
-        cmax = sm.red[0][0]; hmin = sm.red[1][0];
+        cmax = sm.red[0][0]; hmin = sm.red[1][0]; emin = sm.red[2][0];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) { cmax = max(cmax, sm.red[0][i]); hmin = min(hmin, sm.red[1][i]); }
+        for (int i = 1; i < 8; ++i) {
+            cmax = max(cmax, sm.red[0][i]); hmin = min(hmin, sm.red[1][i]); emin = min(emin, sm.red[2][i]);
+        }
 
         for (int iy = 0; iy < r.ncy; ++iy) {
             const size_t chunk = (size_t)colw * r.ncy + iy;  // slab-relative chunk index
@@ -688,6 +706,21 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
                     if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
                     continue;
                 }
+            }
+            if (EMIT && iy == 0 && r.ncy > 1 && emin >= a + 33) {
+                // Region-bottom slab: the chunk, its four lateral neighbours and the layer above are solid, the chunk
+                // below is absent -> exactly one Down face per column, in column order, and every AO probe (all at
+                // y-1) reads "empty".  No tile, masks, scan or descriptors are needed (k_count_region counted 1024).
+                if (tid == 32) sm.rng_seed = siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
+                __syncthreads();
+                const MatHeights mat{sm.hts, a};
+                float* const ws = sm.stage + warp * (32 * 25);
+                const uint32_t ws_shared = (uint32_t)__cvta_generic_to_shared(ws);
+                char* const out_bytes = reinterpret_cast<char*>(out + off * 25ULL);
+                for (uint32_t q0 = warp * 32u; q0 < (uint32_t)HB_CHUNK_AREA; q0 += (kT / 32) * 32u)
+                    emit_window(sm, mat, mats, ws, ws_shared, out_bytes + q0 * 100u, 32u, (q0 + lane) << 5, 3u, 0u,
+                                (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32);
+                continue;
             }
             __syncthreads();  // previous chunk's readers of sm.occ are done
             const u64 ymask = 0x3FFFFFFFFULL & ~(iy == 0 ? 1ULL : 0ULL)         // chunk below outside the region: absent
