@@ -330,10 +330,10 @@ __global__ void __launch_bounds__(kT) k_pack(const uint16_t* __restrict__ ids, s
         const uint4* src = reinterpret_cast<const uint4*>(ids + chunk * HB_CHUNK_VOLUME);
         uint32_t any = 0, all = ~0u, fE = ~0u, fW = ~0u, fN = ~0u, fS = ~0u, bad = 0;
         const uint32_t nm2 = (uint32_t)n_materials * 0x10001u;  // palette size in both halfwords
-#pragma unroll 4
+#pragma unroll
         for (int it = 0; it < 16; ++it) {
             const int u = it * kT + tid;
-            const uint4 v = __ldcs(src + u);
+            const uint4 v = __ldg(src + u);
             // per-halfword SIMD compares: 0xFFFF where the id is non-zero / above the palette size
             const uint32_t z0 = __vcmpne2(v.x, 0u), z1 = __vcmpne2(v.y, 0u), z2 = __vcmpne2(v.z, 0u), z3 = __vcmpne2(v.w, 0u);
             bad |= __vcmpgtu2(v.x, nm2) | __vcmpgtu2(v.y, nm2) | __vcmpgtu2(v.z, nm2) | __vcmpgtu2(v.w, nm2);
@@ -854,7 +854,7 @@ int num_sms() {
 cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_materials, uint32_t* d_bitmaps,
                         uint32_t* d_summary, uint64_t* d_total) {
     if (n == 0) return cudaSuccess;
-    size_t grid = (size_t)num_sms() * 8;
+    size_t grid = (size_t)num_sms() * 32;
     if (grid > n) grid = n;
     k_pack<<<(unsigned)grid, kT, 0, s>>>(d_ids, n, n_materials, d_bitmaps, d_summary, (u64*)d_total);
     return cudaGetLastError();
