@@ -681,11 +681,10 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
         emin = __reduce_min_sync(0xffffffffu, emin);
         if (lane == 0) { sm.red[0][warp] = cmax; sm.red[1][warp] = hmin; sm.red[2][warp] = emin; }
         __syncthreads();
-        cmax = sm.red[0][0]; hmin = sm.red[1][0]; emin = sm.red[2][0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) {
-            cmax = max(cmax, sm.red[0][i]); hmin = min(hmin, sm.red[1][i]); emin = min(emin, sm.red[2][i]);
-        }
+        // every warp folds the 8 per-warp partials with one more warp reduction (lanes 0..7 hold them)
+        cmax = __reduce_max_sync(0xffffffffu, lane < 8 ? sm.red[0][lane] : INT32_MIN);
+        hmin = __reduce_min_sync(0xffffffffu, lane < 8 ? sm.red[1][lane] : INT32_MAX);
+        emin = __reduce_min_sync(0xffffffffu, lane < 8 ? sm.red[2][lane] : INT32_MAX);
 
         for (int iy = 0; iy < r.ncy; ++iy) {
             const size_t chunk = (size_t)colw * r.ncy + iy;  // slab-relative chunk index
