@@ -88,6 +88,8 @@ PROTOTYPES = {
                                 C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "hb_generate_mesh_region": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int, REGION_SINK, C.c_void_p,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "hb_generate_mesh_region_slab": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_int, REGION_SINK,
+                                               C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_region_plan_create": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_uint64, C.c_int,
                                         C.POINTER(C.c_void_p)]),
     "hb_region_plan_destroy": (None, [C.c_void_p]),

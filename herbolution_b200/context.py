@@ -155,7 +155,8 @@ class Context:
 
     # -- fused region ----------------------------------------------------------------------
     def generate_mesh_region(self, region: Region, want_ids: bool = False,
-                             sink: Optional[Callable[..., None]] = None) -> dict:
+                             sink: Optional[Callable[..., None]] = None, ix_begin: int = 0,
+                             ix_end: Optional[int] = None) -> dict:
         """sink(first_chunk, offsets u64[n], counts u32[n], instances INSTANCE_DTYPE[span], ids or None);
         the arrays are views of pinned library buffers, valid only during the call."""
 
@@ -174,8 +175,9 @@ class Context:
 
         cb = _lib.REGION_SINK(_cb)
         tc, tq = C.c_uint64(0), C.c_uint64(0)
-        check(self._lib.hb_generate_mesh_region(self._h, C.byref(region), int(want_ids), cb, None, C.byref(tc),
-                                                C.byref(tq)))
+        ix_end = region.ncx if ix_end is None else ix_end
+        check(self._lib.hb_generate_mesh_region_slab(self._h, C.byref(region), ix_begin, ix_end, int(want_ids), cb, None,
+                                                     C.byref(tc), C.byref(tq)))
         return {"chunks": tc.value, "quads": tq.value}
 
     def download(self, dev_ptr: int, dtype, count: int) -> np.ndarray:

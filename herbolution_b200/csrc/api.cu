@@ -799,9 +799,19 @@ int hb_dev_download(hb_ctx* c, void* host_dst, const void* dev_src, size_t bytes
 
 int hb_generate_mesh_region(hb_ctx* c, const hb_region* region, int want_ids, hb_region_sink sink, void* user,
                             uint64_t* total_chunks, uint64_t* total_quads) {
+    if (!region) return fail(HB_ERR_INVALID, "region is null");
+    return hb_generate_mesh_region_slab(c, region, 0, region->ncx, want_ids, sink, user, total_chunks, total_quads);
+}
+
+int hb_generate_mesh_region_slab(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t ix_end, int want_ids,
+                                 hb_region_sink sink, void* user, uint64_t* total_chunks, uint64_t* total_quads) {
     if (!c) return fail(HB_ERR_INVALID, "ctx is null");
     int rc = region_check(region);
     if (rc != HB_OK) return rc;
+    if (ix_begin < 0 || ix_end > region->ncx || ix_begin > ix_end) return fail(HB_ERR_INVALID, "bad slab [%d,%d)", ix_begin, ix_end);
+    if (total_chunks) *total_chunks = 0;
+    if (total_quads) *total_quads = 0;
+    if (ix_begin == ix_end) return HB_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     HB_CUDA(cudaSetDevice(c->device));
     // slab width: aim at ~384 MiB of instances per slab (about 300 KB per column on this terrain),
@@ -812,12 +822,12 @@ int hb_generate_mesh_region(hb_ctx* c, const hb_region* region, int want_ids, hb
         const size_t ids_per_ix = (size_t)region->ncz * region->ncy * HB_CHUNK_VOLUME * sizeof(uint16_t);
         width = (int32_t)std::max<size_t>(1, std::min<size_t>(width, ((size_t)1 << 30) / ids_per_ix));
     }
-    width = std::min(width, region->ncx);
+    width = std::min(width, ix_end - ix_begin);
 
     hb_region_plan plan[2];
     for (int b = 0; b < 2; ++b) {
         plan[b].ctx = c; plan[b].region = *region; plan[b].want_ids = want_ids;
-        plan_target(&plan[b], 0, width);
+        plan_target(&plan[b], ix_begin, ix_begin + width);
         rc = plan_alloc(&plan[b], width);
         if (rc != HB_OK) goto done;
     }
@@ -839,12 +849,12 @@ int hb_generate_mesh_region(hb_ctx* c, const hb_region* region, int want_ids, hb
             return HB_OK;
         };
         int slab = 0;
-        for (int32_t ix0 = 0; ix0 < region->ncx && rc == HB_OK; ix0 += width, ++slab) {
+        for (int32_t ix0 = ix_begin; ix0 < ix_end && rc == HB_OK; ix0 += width, ++slab) {
             const int b = slab & 1;
             hb_region_plan* p = &plan[b];
             rc = drain(b);  // buffers of parity b are free again (device out + pinned)
             if (rc != HB_OK) break;
-            plan_target(p, ix0, std::min(region->ncx, ix0 + width));
+            plan_target(p, ix0, std::min(ix_end, ix0 + width));
             const size_t nch = p->n_chunks();
             rc = plan_enqueue(p, HB_STAGE_HEIGHTS | HB_STAGE_COUNT | HB_STAGE_SCAN, c->stream);
             if (rc != HB_OK) break;

@@ -169,6 +169,14 @@ HB_API int hb_generate_mesh_region(hb_ctx *ctx, const hb_region *region, int wan
                             hb_region_sink sink, void *user,
                             uint64_t *total_chunks, uint64_t *total_quads);
 
+/* Same for the x-slab ix in [ix_begin, ix_end) of `region` only: how a region is sharded across GPUs (one ctx per
+ * GPU, herbolution_b200/sharding.py).  The slab's border columns see their neighbours inside the region (the
+ * one-column apron of heights is recomputed from the noise function, no exchange); first_chunk passed to the sink
+ * is still the index within the whole region. */
+HB_API int hb_generate_mesh_region_slab(hb_ctx *ctx, const hb_region *region, int32_t ix_begin, int32_t ix_end,
+                                        int want_ids, hb_region_sink sink, void *user,
+                                        uint64_t *total_chunks, uint64_t *total_quads);
+
 /* ---- device-resident pipeline (kernel-only measurement, chaining with other CUDA work) ----
  * A plan owns the device buffers for region chunks with ix in [ix_begin, ix_end).  Stages only
  * ENQUEUE kernels on `stream` (a cudaStream_t passed as void*; NULL = the ctx stream). */

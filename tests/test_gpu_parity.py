@@ -338,6 +338,31 @@ def test_region_plan_slabs_equal_whole(ctx):
         plan.close()
 
 
+def test_region_slabs_through_host_api_equal_whole(ctx):
+    """BASELINE config 5 in miniature: the region is cut into x-slabs as herbolution_b200.sharding does per
+    GPU; every slab is generated + meshed on its own (apron recomputed, no exchange) and streams back through the
+    pinned sink.  The union equals the unsharded region chunk for chunk."""
+    from herbolution_b200 import sharding
+    ctx.set_world(5)
+    region = hb.Region(-5, 2, 9, 3, -3, 6)
+    _, whole = collect_region(ctx, region, want_ids=True)
+    for world in (2, 4):
+        got = {}
+
+        def sink(first, off, cnt, inst, ids):
+            for k in range(len(cnt)):
+                assert first + k not in got
+                got[first + k] = (inst[int(off[k]):int(off[k]) + int(cnt[k])].copy(), ids[k].copy())
+
+        totals = [ctx.generate_mesh_region(region, want_ids=True, sink=sink, ix_begin=a, ix_end=b)
+                  for a, b in (sharding.slab_bounds(region.ncx, world, r) for r in range(world))]
+        assert sum(t["chunks"] for t in totals) == region.n_chunks == len(got)
+        for i in range(region.n_chunks):
+            assert_instances_equal(got[i][0], whole[i][0], f"world {world} chunk {i}")
+            assert (got[i][1] == whole[i][1]).all()
+    ctx.set_world(0)
+
+
 def test_region_c4_properties(ctx):
     """BASELINE config 4 at a reduced but still multi-slab size (64x64 columns x 6): size-independent
     properties -- quad total equals the sum over independently meshed sub-blocks' interior-consistent
