@@ -180,10 +180,9 @@ struct FacesFromPlanes {
 // one TMA bulk shared->global copy (UBLKCP) of the whole window by lane 0 instead of 200 LDS.128 + STG.128 through
 // the LSU.  The window is zero-padded to a multiple of 4 quads.  The wait for the engine to release the buffer from
 // this warp's previous window sits after the register work so the two overlap.
-template <class MatFn>
-__device__ __forceinline__ void emit_window(MeshSmem& sm, const MatFn& mat, const MaterialsDev* __restrict__ mats,
-                                            float* __restrict__ ws, uint32_t ws_shared, char* __restrict__ gdst, uint32_t nw,
-                                            uint32_t L, uint32_t f, uint32_t ao, int bx, int by, int bz) {
+__device__ __forceinline__ void emit_window(MeshSmem& sm, const MaterialsDev* __restrict__ mats, float* __restrict__ ws,
+                                            uint32_t ws_shared, char* __restrict__ gdst, uint32_t nw, uint32_t L, uint32_t f,
+                                            uint32_t ao, uint32_t id, int bx, int by, int bz) {
     const int lane = threadIdx.x & 31;
     const uint32_t nw4 = (nw + 3u) & ~3u;
     float* sq = ws + lane * 25;
@@ -191,7 +190,6 @@ __device__ __forceinline__ void emit_window(MeshSmem& sm, const MatFn& mat, cons
     const int x = L >> 10, z = (L >> 5) & 31, y = L & 31;
     float4 rgba = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
-        const uint32_t id = mat(L, x, y, z);
         // Material::get_color(perms[face]) (server/src/chunk/material.rs:67-71)
         const float p = wyrand_f32_at(sm.rng_seed, 6u * L + f);
         const int nc = __ldg(&mats->n_colors[id - 1]);
@@ -287,17 +285,27 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, co
         const uint32_t nd = min((uint32_t)kDescCap, total - d0);
         // (b) each warp expands windows of 32 descriptors (one quad per lane) and streams them out; no block-level
         //     barrier inside this loop
+        // The descriptor and the material of the NEXT window are fetched before the current one is expanded, so a
+        // block-array material read (a scattered 2-byte global load in the general mesher) overlaps a whole window.
+        uint32_t d_next = 0, id_next = 0;
+        if (warp * 32u + lane < nd) {
+            d_next = sm.desc[warp * 32u + lane];
+            const uint32_t Ln = d_next & 0x7FFFu;
+            id_next = mat(Ln, Ln >> 10, Ln & 31, (Ln >> 5) & 31);
+        }
         for (uint32_t q0 = warp * 32u; q0 < nd; q0 += (kT / 32) * 32u) {
             const uint32_t nw = min(32u, nd - q0);
-            // register phase first: it overlaps the TMA engine still reading this warp's previous window
-            uint32_t L = 0, f = 0, ao = 0;
-            if ((uint32_t)lane < nw) {
-                const uint32_t d = sm.desc[q0 + lane];
-                L = d & 0x7FFFu;
-                f = d >> 15;
-                ao = ao_bits(sm.occ, sm.ao_tab[f], L >> 10, L & 31, (L >> 5) & 31);
+            const uint32_t d = d_next, id = id_next;
+            const uint32_t qn = q0 + (kT / 32) * 32u + lane;
+            if (qn < nd) {
+                d_next = sm.desc[qn];
+                const uint32_t Ln = d_next & 0x7FFFu;
+                id_next = mat(Ln, Ln >> 10, Ln & 31, (Ln >> 5) & 31);
             }
-            emit_window(sm, mat, mats, ws, ws_shared, out_bytes + (d0 + q0) * 100u, nw, L, f, ao, bx, by, bz);  // < 2^24 B / chunk
+            const uint32_t L = d & 0x7FFFu, f = d >> 15;
+            uint32_t ao = 0;
+            if ((uint32_t)lane < nw) ao = ao_bits(sm.occ, sm.ao_tab[f], L >> 10, L & 31, (L >> 5) & 31);
+            emit_window(sm, mats, ws, ws_shared, out_bytes + (d0 + q0) * 100u, nw, L, f, ao, id, bx, by, bz);  // < 2^24 B / chunk
         }
         if (d0 + kDescCap < total) __syncthreads();  // descriptors are rewritten in the next round
     }
@@ -446,16 +454,77 @@ struct MatCubes {
     __device__ __forceinline__ uint32_t operator()(uint32_t L, int, int, int) const { return __ldg(&cubes[L].material); }
 };
 
-// shell index (dx+1)*9 + (dy+1)*3 + (dz+1) of the face neighbour (client/src/world/chunk.rs:158-174)
-__device__ __forceinline__ int face_shell_index(int f) {
-    const int t[6] = {22, 4, 16, 10, 14, 12};
-    return t[f];
+// K3b (COUNT) for the general mesher: no occupancy tile.  Every thread takes four columns and builds their six
+// face masks straight from the L2-resident bitmaps (own word, four lateral words -- from the neighbour chunk at the
+// chunk border -- and one bit each from the chunks above and below), or reads the face planes in FLAGS mode.
+// One barrier per chunk; equals what mesh_tile<EMIT> emits (same masks), which the parity tests pin down.
+template <bool FLAGS>
+__global__ void __launch_bounds__(kT) k_count_ids(size_t n, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
+                                                   const uint32_t* __restrict__ summary, const uint32_t* __restrict__ planes,
+                                                   uint32_t* __restrict__ counts) {
+    __shared__ uint32_t s_part[kT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const uint32_t s = summary[chunk];
+        if (!(s & 1u)) {  // no solid voxel
+            if (tid == 0) counts[chunk] = 0;
+            continue;
+        }
+        uint32_t c = 0;
+        if (FLAGS) {
+            const uint32_t* p = planes + chunk * 6 * HB_CHUNK_AREA;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int f = 0; f < 6; ++f) c += __popc(__ldg(p + f * HB_CHUNK_AREA + (k * 8 + warp) * 32 + lane));
+        } else {
+            const int32_t* nb = nbr + chunk * 27;
+            // shell index (dx+1)*9 + (dy+1)*3 + (dz+1) of the six face neighbours (client/src/world/chunk.rs:158-174)
+            const int nE = nb[22], nW = nb[4], nU = nb[16], nD = nb[10], nN = nb[14], nS = nb[12];
+            if (s & 2u) {  // completely solid: nothing to count if the six facing slabs are solid too
+                bool buried = true;
+                const int nf[6] = {nE, nW, nU, nD, nN, nS};
+#pragma unroll
+                for (int f = 0; f < 6; ++f)
+                    if (nf[f] < 0 || !((summary[nf[f]] >> (2 + (f ^ 1))) & 1u)) buried = false;
+                if (buried) {
+                    if (tid == 0) counts[chunk] = 0;
+                    continue;
+                }
+            }
+            const uint32_t* bm = bitmaps + chunk * HB_CHUNK_AREA;
+            auto word = [&](int nbc, int col) -> uint32_t { return nbc >= 0 ? __ldg(bitmaps + (size_t)nbc * HB_CHUNK_AREA + col) : 0u; };
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int x = k * 8 + warp, z = lane, col = x * 32 + z;
+                const uint32_t cen = __ldg(bm + col);
+                if (!cen) continue;
+                const uint32_t e = x < 31 ? __ldg(bm + col + 32) : word(nE, z);
+                const uint32_t w = x > 0 ? __ldg(bm + col - 32) : word(nW, 31 * 32 + z);
+                const uint32_t nn = z < 31 ? __ldg(bm + col + 1) : word(nN, x * 32);
+                const uint32_t ss = z > 0 ? __ldg(bm + col - 1) : word(nS, x * 32 + 31);
+                const uint32_t up = (cen >> 1) | ((word(nU, col) & 1u) << 31);   // voxel above: y+1, or y = 0 of the chunk above
+                const uint32_t dn = (cen << 1) | (word(nD, col) >> 31);          // voxel below
+                c += __popc(cen & ~e) + __popc(cen & ~w) + __popc(cen & ~up) + __popc(cen & ~dn) + __popc(cen & ~nn) +
+                     __popc(cen & ~ss);
+            }
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) s_part[warp] = c;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int i = 0; i < kT / 32; ++i) t += s_part[i];
+            counts[chunk] = t;
+        }
+        __syncthreads();
+    }
 }
 
-// K3b/K3c: count (EMIT=false) or emit (EMIT=true) for arbitrary block arrays, persistent CTAs.
 // FLAGS: `blocks` are hb_palette_cube arrays and the visible faces are taken from `planes` (cube.flags) instead of
 // being recomputed from occupancy.
-template <bool EMIT, bool FLAGS>
+template <bool EMIT, bool FLAGS>  // EMIT is always true since COUNT moved to k_count_ids; kept for mesh_tile's signature
 __global__ void __launch_bounds__(kT, kCtasPerSm)
 k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_chunk_pt* __restrict__ pts, size_t n,
            const void* __restrict__ blocks, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
@@ -465,49 +534,46 @@ k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
     const int tid = threadIdx.x;
     if (EMIT) load_tables(sm, tb);
     for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
-        // block-uniform early outs from the summaries
-        const uint32_t s = summary[chunk];
-        bool trivial = !(s & 1u);  // no solid voxel: nothing to draw in either mode
-        if (!FLAGS && !trivial && (s & 2u)) {
-            trivial = true;
-#pragma unroll
-            for (int f = 0; f < 6; ++f) {
-                const int nb = nbr[chunk * 27 + face_shell_index(f)];
-                if (nb < 0 || !((summary[nb] >> (2 + (f ^ 1))) & 1u)) trivial = false;
-            }
-        }
-        if (trivial) {
-            if (!EMIT && tid == 0) counts[chunk] = 0;
+        // block-uniform early out: the COUNT stage already knows which chunks have no visible face at all
+        // (all air, or buried: k_count_ids), so EMIT needs one load per chunk to skip them
+        const uint32_t my_count = counts[chunk];
+        if (my_count == 0) continue;
+        const u64 off = offsets[chunk];
+        if (off + (((u64)my_count + 3ULL) & ~3ULL) > capacity) {
+            if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
             continue;
-        }
-        u64 off = 0;
-        if (EMIT) {
-            off = offsets[chunk];
-            const u64 span = ((u64)counts[chunk] + 3ULL) & ~3ULL;
-            if (off + span > capacity) {
-                if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
-                continue;
-            }
         }
         __syncthreads();  // previous chunk's readers of sm.nbr / sm.occ are done
         if (tid < 27) sm.nbr[tid] = nbr[chunk * 27 + tid];
         const hb_chunk_pt pt = pts[chunk];
         if (EMIT && tid == 32) sm.rng_seed = siphash13_chunk(pt.x, pt.y, pt.z);
         __syncthreads();
-        for (int i = tid; i < kTileN; i += kT) {
-            const int xi = i / kTile, zi = i - xi * kTile;
-            const int dx = (xi == 0) ? -1 : (xi == kTile - 1 ? 1 : 0);
-            const int dz = (zi == 0) ? -1 : (zi == kTile - 1 ? 1 : 0);
-            const int c = ((xi - 1) & 31) * 32 + ((zi - 1) & 31);
-            const int sb = (dx + 1) * 9 + (dz + 1);
-            u64 v = 0;
-            const int n0 = sm.nbr[sb + 3];  // dy = 0
-            if (n0 >= 0) v |= (u64)__ldg(bitmaps + (size_t)n0 * HB_CHUNK_AREA + c) << 1;
-            const int nd = sm.nbr[sb];      // dy = -1: its y = 31
-            if (nd >= 0) v |= (u64)(__ldg(bitmaps + (size_t)nd * HB_CHUNK_AREA + c) >> 31);
-            const int nu = sm.nbr[sb + 6];  // dy = +1: its y = 0
-            if (nu >= 0) v |= (u64)(__ldg(bitmaps + (size_t)nu * HB_CHUNK_AREA + c) & 1u) << 33;
-            sm.occ[i] = v;
+        // all (up to 15) bitmap words of this thread's tile elements are requested before any is used, so the
+        // L2/HBM latency is paid once per chunk instead of once per element
+        constexpr int kIter = (kTileN + kT - 1) / kT;
+        uint32_t w0[kIter], wd[kIter], wu[kIter];
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+            const int i = tid + it * kT;
+            w0[it] = wd[it] = wu[it] = 0u;
+            if (i < kTileN) {
+                const int xi = i / kTile, zi = i - xi * kTile;
+                const int dx = (xi == 0) ? -1 : (xi == kTile - 1 ? 1 : 0);
+                const int dz = (zi == 0) ? -1 : (zi == kTile - 1 ? 1 : 0);
+                const int c = ((xi - 1) & 31) * 32 + ((zi - 1) & 31);
+                const int sb = (dx + 1) * 9 + (dz + 1);
+                const int n0 = sm.nbr[sb + 3];  // dy = 0
+                const int nd = sm.nbr[sb];      // dy = -1: its y = 31
+                const int nu = sm.nbr[sb + 6];  // dy = +1: its y = 0
+                if (n0 >= 0) w0[it] = __ldg(bitmaps + (size_t)n0 * HB_CHUNK_AREA + c);
+                if (nd >= 0) wd[it] = __ldg(bitmaps + (size_t)nd * HB_CHUNK_AREA + c);
+                if (nu >= 0) wu[it] = __ldg(bitmaps + (size_t)nu * HB_CHUNK_AREA + c);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+            const int i = tid + it * kT;
+            if (i < kTileN) sm.occ[i] = ((u64)w0[it] << 1) | (u64)(wd[it] >> 31) | ((u64)(wu[it] & 1u) << 33);
         }
         __syncthreads();
         uint32_t q;
@@ -716,9 +782,11 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
                 float* const ws = sm.stage + warp * (32 * 25);
                 const uint32_t ws_shared = (uint32_t)__cvta_generic_to_shared(ws);
                 char* const out_bytes = reinterpret_cast<char*>(out + off * 25ULL);
-                for (uint32_t q0 = warp * 32u; q0 < (uint32_t)HB_CHUNK_AREA; q0 += (kT / 32) * 32u)
-                    emit_window(sm, mat, mats, ws, ws_shared, out_bytes + q0 * 100u, 32u, (q0 + lane) << 5, 3u, 0u,
+                for (uint32_t q0 = warp * 32u; q0 < (uint32_t)HB_CHUNK_AREA; q0 += (kT / 32) * 32u) {
+                    const uint32_t L = (q0 + lane) << 5;  // voxel (x, 0, z) of column q0 + lane
+                    emit_window(sm, mats, ws, ws_shared, out_bytes + q0 * 100u, 32u, L, 3u, 0u, mat(L, L >> 10, 0, (L >> 5) & 31),
                                 (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32);
+                }
                 continue;
             }
             __syncthreads();  // previous chunk's readers of sm.occ are done
@@ -874,13 +942,24 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
                             uint32_t* d_counts, const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
                             uint64_t* d_total) {
     if (n == 0) return cudaSuccess;
-    size_t grid = (size_t)num_sms() * kCtasPerSm;
+    // Persistent CTAs stride through the chunk list.  Batches are usually ordered (ix, iz, iy) with a small number
+    // of layers, so an even stride would hand every CTA the same layer (all surface or all buried) for the whole
+    // launch; an odd stride rotates through the layers and balances the load.
+    size_t grid = ((size_t)num_sms() * kCtasPerSm) - 1;
     if (grid > n) grid = n;
 #define HB_LAUNCH(E, F)                                                                                              \
     k_mesh_ids<E, F><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, d_pts, n, d_blocks, d_nbr, d_bitmaps, d_summary, d_planes, \
                                                    d_counts, (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total)
-    if (d_planes) { if (emit) HB_LAUNCH(true, true); else HB_LAUNCH(false, true); }
-    else { if (emit) HB_LAUNCH(true, false); else HB_LAUNCH(false, false); }
+    if (!emit) {
+        size_t cgrid = (size_t)num_sms() * 8 - 1;  // odd, see above
+        if (cgrid > n) cgrid = n;
+        if (d_planes) k_count_ids<true><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts);
+        else k_count_ids<false><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts);
+    } else if (d_planes) {
+        HB_LAUNCH(true, true);
+    } else {
+        HB_LAUNCH(true, false);
+    }
 #undef HB_LAUNCH
     return cudaGetLastError();
 }
