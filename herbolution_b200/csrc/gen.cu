@@ -1,7 +1,8 @@
 // gen.cu -- terrain generation kernels (sm_100a).
 //
-//   k_heights : batched 2-D simplex FBM, one CTA per chunk column, permutation table in shared
-//               memory, 4 independent samples per thread.  FP32/ALU-issue bound.
+//   k_heights : batched 2-D simplex FBM, one CTA per chunk column, permutation + gradient tables in shared
+//               memory, 4 samples per thread evaluated two at a time with Blackwell's packed f32x2
+//               arithmetic (FFMA2 / FADD2 / FMUL2).  FP32/ALU-issue bound.
 //               Replaces get_2d_noise_helper_f32 + fbm_2d + simplex_2d (crates/simd-noise) and the
 //               height computation of GenerationParams::generate (server/src/generator/mod.rs:74-79).
 //   k_fill    : heights -> u16 block ids, one 128-bit streaming store per thread per 8 voxels,
@@ -57,11 +58,13 @@ __global__ void __launch_bounds__(kThreads) k_heights(WorldDev w, Cols cols, int
 
     float v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = threadIdx.x + k * kThreads;
-        const float x = __fadd_rn(start_x, __int2float_rn(i & 31));
-        const float z = __fadd_rn(start_z, __int2float_rn(i >> 5));
-        v[k] = fbm2(s_tab, __fmul_rn(x, w.freq), __fmul_rn(z, w.freq), w);
+    for (int k = 0; k < 4; k += 2) {  // two samples per packed evaluation (FFMA2 / FADD2 / FMUL2)
+        const int i0 = threadIdx.x + k * kThreads, i1 = i0 + kThreads;
+        const float2 x = pk(__fadd_rn(start_x, __int2float_rn(i0 & 31)), __fadd_rn(start_x, __int2float_rn(i1 & 31)));
+        const float2 z = pk(__fadd_rn(start_z, __int2float_rn(i0 >> 5)), __fadd_rn(start_z, __int2float_rn(i1 >> 5)));
+        const float2 r = fbm2_pair(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
+        v[k] = r.x;
+        v[k + 1] = r.y;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

@@ -47,78 +47,108 @@ __device__ __forceinline__ float2 grad2_of(int seed_lo, int hash) {
 }
 
 // Shared-memory tables for the 2-D path: the permutation (256 B) and, per permutation slot, the
-// gradient it selects for this seed (G[i] = grad2(P[i]), 2 KB).  A corner's gradient is then two
-// dependent shared loads instead of a load plus ~12 select/logic instructions.
+// gradient it selects for this seed (gx[i], gy[i] = grad2(P[i]), 2 KB).  A corner's gradient is then two
+// dependent shared loads instead of a load plus ~12 select/logic instructions.  gx and gy are separate
+// arrays so that the values of two samples land in adjacent registers (operands of the packed f32x2 ops).
 struct NoiseTables {
     __align__(16) uint8_t perm[256];
-    __align__(16) float2 grad[256];
+    __align__(16) float gx[256];
+    __align__(16) float gy[256];
 };
 
 // Cooperative table setup (call from all threads, then __syncthreads()).
 __device__ __forceinline__ void load_noise_tables(NoiseTables& t, int seed_lo) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const int p = kPerm[i];
+        const float2 g = grad2_of(seed_lo, p);
         t.perm[i] = (uint8_t)p;
-        t.grad[i] = grad2_of(seed_lo, p);
+        t.gx[i] = g.x;
+        t.gy[i] = g.y;
     }
 }
 
-// functions/simplex_32.rs:103-170 (value half of simplex_2d_deriv)
-__device__ __forceinline__ float simplex2(const NoiseTables& T, float x, float y) {
-    const float s = __fmul_rn(HB_F2, __fadd_rn(x, y));
-    const float ips = floorf(__fadd_rn(x, s));
-    const float jps = floorf(__fadd_rn(y, s));
-    const int i = __float2int_rz(ips);  // exact: ips is integral (cast_i32, simd/ops/f32.rs:716-739)
-    const int j = __float2int_rz(jps);
-    const float t = __fmul_rn(__int2float_rn(i + j), HB_G2);
-    const float x0 = __fsub_rn(x, __fsub_rn(ips, t));
-    const float y0 = __fsub_rn(y, __fsub_rn(jps, t));
+// Packed helpers: Blackwell's FADD2 / FMUL2 / FFMA2 (add/mul/fma.rn.f32x2) process two f32 per instruction with the
+// same per-component IEEE round-to-nearest results as the scalar ops, and fold operand negation and broadcast
+// immediates, so a - b is written as a + (-b) (exactly the same value).
+//
+// CAUTION (measured with CUDA 12.9): ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 even with
+// --fmad=false, which would break bit-exactness against the reference (its operator overloads never fuse).  It does
+// not contract across a packed/scalar boundary.  So every product that feeds an add is either computed with scalar
+// FMULs (smul2) or consumed by scalar FADDs (sadd2); the SASS must contain exactly six FFMA2 per simplex pair (the
+// neg_mul_add sites), which tests/test_abi.py checks, and the GPU parity tests compare the noise bit for bit.
+__device__ __forceinline__ float2 pk(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fnma2(float2 a, float2 b, float2 c) { return __ffma2_rn(neg2(a), b, c); }  // c - a*b, fused
+__device__ __forceinline__ float2 smul2(float2 a, float2 b) { return pk(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 sadd2(float2 a, float2 b) { return pk(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 
-    const bool xge = x0 >= y0;  // i1 = all-ones mask (-1) when x0 >= y0
-    const bool ygt = y0 > x0;   // j1
-    const float x1 = __fadd_rn(__fadd_rn(x0, xge ? -1.0f : 0.0f), HB_G2);
-    const float y1 = __fadd_rn(__fadd_rn(y0, ygt ? -1.0f : 0.0f), HB_G2);
-    const float x2 = __fadd_rn(__fadd_rn(x0, -1.0f), HB_G22);
-    const float y2 = __fadd_rn(__fadd_rn(y0, -1.0f), HB_G22);
+// functions/simplex_32.rs:103-170 (value half of simplex_2d_deriv) for TWO samples at once: every variable is a
+// float2 (.x = sample A, .y = sample B).  The arithmetic per sample is op for op the reference's: separate
+// round-to-nearest add/mul everywhere, true FMA only at the six neg_mul_add sites
+// (_mm256_fnmadd_ps, simd/ops/f32.rs:141-145).  x and y must not be the direct result of a packed multiply.
+__device__ __forceinline__ float2 simplex2_pair(const NoiseTables& T, float2 x, float2 y) {
+    const float2 s = smul2(bc(HB_F2), add2(x, y));  // feeds x + s, y + s
+    const float2 xs = add2(x, s), ys = add2(y, s);
+    const float2 ips = pk(floorf(xs.x), floorf(xs.y)), jps = pk(floorf(ys.x), floorf(ys.y));
+    const int iA = __float2int_rz(ips.x), iB = __float2int_rz(ips.y);  // exact: integral (cast_i32, simd/ops/f32.rs:716-739)
+    const int jA = __float2int_rz(jps.x), jB = __float2int_rz(jps.y);
+    const float2 t = smul2(pk(__int2float_rn(iA + jA), __int2float_rn(iB + jB)), bc(HB_G2));  // feeds ips - t, jps - t
+    const float2 x0 = sub2(x, sub2(ips, t));
+    const float2 y0 = sub2(y, sub2(jps, t));
+
+    const bool xgeA = x0.x >= y0.x, xgeB = x0.y >= y0.y;  // i1 = all-ones mask (-1) when x0 >= y0
+    const bool ygtA = y0.x > x0.x, ygtB = y0.y > x0.y;    // j1
+    const float2 x1 = add2(add2(x0, pk(xgeA ? -1.0f : 0.0f, xgeB ? -1.0f : 0.0f)), bc(HB_G2));
+    const float2 y1 = add2(add2(y0, pk(ygtA ? -1.0f : 0.0f, ygtB ? -1.0f : 0.0f)), bc(HB_G2));
+    const float2 x2 = add2(add2(x0, bc(-1.0f)), bc(HB_G22));
+    const float2 y2 = add2(add2(y0, bc(-1.0f)), bc(HB_G22));
 
     // gi_k = P[(ii + di) + P[jj + dj]] (simplex_32.rs:137-141); indices are taken mod 256 because the
     // reference's 512-entry table is the permutation twice
-    const int pj0 = T.perm[j & 255];
-    const int pj1 = T.perm[(j + 1) & 255];
-    const float2 g0 = T.grad[(i + pj0) & 255];
-    const float2 g1 = T.grad[(i + (xge ? 1 : 0) + (ygt ? pj1 : pj0)) & 255];
-    const float2 g2 = T.grad[(i + 1 + pj1) & 255];
+    const int pj0A = T.perm[jA & 255], pj1A = T.perm[(jA + 1) & 255];
+    const int pj0B = T.perm[jB & 255], pj1B = T.perm[(jB + 1) & 255];
+    const int k0A = (iA + pj0A) & 255, k0B = (iB + pj0B) & 255;
+    const int k1A = (iA + (xgeA ? 1 : 0) + (ygtA ? pj1A : pj0A)) & 255;
+    const int k1B = (iB + (xgeB ? 1 : 0) + (ygtB ? pj1B : pj0B)) & 255;
+    const int k2A = (iA + 1 + pj1A) & 255, k2B = (iB + 1 + pj1B) & 255;
+    const float2 g0x = pk(T.gx[k0A], T.gx[k0B]), g0y = pk(T.gy[k0A], T.gy[k0B]);
+    const float2 g1x = pk(T.gx[k1A], T.gx[k1B]), g1y = pk(T.gy[k1A], T.gy[k1B]);
+    const float2 g2x = pk(T.gx[k2A], T.gx[k2B]), g2y = pk(T.gy[k2A], T.gy[k2B]);
 
-    // neg_mul_add(a, b, c) = fma(-a, b, c): _mm256_fnmadd_ps (simd/ops/f32.rs:141-145)
-    float t0 = __fmaf_rn(-y0, y0, __fmaf_rn(-x0, x0, 0.5f));
-    float t1 = __fmaf_rn(-y1, y1, __fmaf_rn(-x1, x1, 0.5f));
-    float t2 = __fmaf_rn(-y2, y2, __fmaf_rn(-x2, x2, 0.5f));
+    float2 t0 = fnma2(y0, y0, fnma2(x0, x0, bc(0.5f)));
+    float2 t1 = fnma2(y1, y1, fnma2(x1, x1, bc(0.5f)));
+    float2 t2 = fnma2(y2, y2, fnma2(x2, x2, bc(0.5f)));
     // t &= t.cmp_gte(0): negative -> +0.  fmaxf(t, 0) differs only for t = -0 (keeps/loses the sign
     // of zero), and t is squared next, so the result is identical.
-    t0 = fmaxf(t0, 0.0f);
-    t1 = fmaxf(t1, 0.0f);
-    t2 = fmaxf(t2, 0.0f);
+    t0 = pk(fmaxf(t0.x, 0.0f), fmaxf(t0.y, 0.0f));
+    t1 = pk(fmaxf(t1.x, 0.0f), fmaxf(t1.y, 0.0f));
+    t2 = pk(fmaxf(t2.x, 0.0f), fmaxf(t2.y, 0.0f));
+    const float2 t20 = mul2(t0, t0), t40 = mul2(t20, t20);
+    const float2 t21 = mul2(t1, t1), t41 = mul2(t21, t21);
+    const float2 t22 = mul2(t2, t2), t42 = mul2(t22, t22);
 
-    const float t20 = __fmul_rn(t0, t0), t40 = __fmul_rn(t20, t20);
-    const float t21 = __fmul_rn(t1, t1), t41 = __fmul_rn(t21, t21);
-    const float t22 = __fmul_rn(t2, t2), t42 = __fmul_rn(t22, t22);
-
-    // g = gx*x + gy*y: two multiplies and one add, as the operator overloads do (never fused)
-    const float n0 = __fmul_rn(t40, __fadd_rn(__fmul_rn(g0.x, x0), __fmul_rn(g0.y, y0)));
-    const float n1 = __fmul_rn(t41, __fadd_rn(__fmul_rn(g1.x, x1), __fmul_rn(g1.y, y1)));
-    const float n2 = __fmul_rn(t42, __fadd_rn(__fmul_rn(g2.x, x2), __fmul_rn(g2.y, y2)));
-    return __fmul_rn(__fadd_rn(n0, __fadd_rn(n1, n2)), 45.26450774985561631259f);
+    // g = gx*x + gy*y: two multiplies and one add, as the operator overloads do (never fused):
+    // packed products, scalar sums
+    const float2 n0 = mul2(t40, sadd2(mul2(g0x, x0), mul2(g0y, y0)));
+    const float2 n1 = mul2(t41, sadd2(mul2(g1x, x1), mul2(g1y, y1)));
+    const float2 n2 = mul2(t42, sadd2(mul2(g2x, x2), mul2(g2y, y2)));
+    return mul2(sadd2(n0, sadd2(n1, n2)), bc(45.26450774985561631259f));
 }
 
-// functions/fbm_32.rs:18-31
-__device__ __forceinline__ float fbm2(const NoiseTables& T, float x, float y, const WorldDev& w) {
-    float result = simplex2(T, x, y);
+// functions/fbm_32.rs:18-31, two samples at once
+__device__ __forceinline__ float2 fbm2_pair(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
+    float2 result = simplex2_pair(T, x, y);
     float amp = 1.0f;
+    const float2 lac = bc(w.lacunarity);
     for (int o = 1; o < w.octaves; ++o) {
-        x = __fmul_rn(x, w.lacunarity);
-        y = __fmul_rn(y, w.lacunarity);
+        x = smul2(x, lac);  // scalar: x and y feed adds inside simplex2_pair
+        y = smul2(y, lac);
         amp = __fmul_rn(amp, w.gain);
-        result = __fadd_rn(__fmul_rn(simplex2(T, x, y), amp), result);
+        result = sadd2(mul2(simplex2_pair(T, x, y), bc(amp)), result);
     }
     return result;
 }

@@ -130,3 +130,26 @@ def test_host_mirror_api_surface():
     shell = hb.create_chunk_shell({hb.ChunkPt(0, 0, 0): hb.ChunkData(hb.ChunkPt(0, 0, 0), np.zeros(32768, np.uint16))},
                                   hb.ChunkPt(0, 0, 0))
     assert len(shell) == 27 and shell[13] is not None and sum(s is not None for s in shell) == 1
+
+
+def test_noise_kernel_has_no_unintended_fma_contraction():
+    """ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false; the reference's
+    operator overloads never fuse (only the six neg_mul_add sites of simplex_2d do).  csrc/noise.cuh routes every
+    product that feeds an add across a packed/scalar boundary; this pins the result in the shipped SASS:
+    k_heights evaluates 4 simplex pairs in its instruction stream (2 pairs x {first octave, octave loop}), so it
+    must contain exactly 4 x 6 FFMA2 and no scalar FFMA at all."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
+    funcs = re.split(r"\n\s*Function : ", sass)
+    heights = [f for f in funcs if "k_heights" in f.split("\n", 1)[0]]
+    assert len(heights) == 2  # ColList and ColRegion instantiations
+    for f in heights:
+        ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", f)
+        assert sum(o.startswith("FFMA2") for o in ops) == 24, "packed FMA count changed: check for contraction"
+        assert not [o for o in ops if o.startswith("FFMA") and not o.startswith("FFMA2")]
+        assert sum(o.startswith("FMUL2") for o in ops) > 0 and sum(o.startswith("FADD2") for o in ops) > 0  # Blackwell packed f32x2
+    # the whole library is compiled without FMA contraction in the 3-D noise path too (reference: no FMAs there)
+    n3 = [f for f in funcs if "k_noise3d" in f.split("\n", 1)[0]]
+    assert n3 and not re.findall(r"\bFFMA\b", n3[0])
