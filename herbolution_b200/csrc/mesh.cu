@@ -620,17 +620,43 @@ struct RelHeight {
         return (int)(d < -1 ? -1 : (d > top ? top : d));
     }
 };
-template <class Conv>
-__device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int32_t* __restrict__ heights, int ix, int iz,
-                                                  int* __restrict__ hts, int& cmax, int& hmin, int& emin, const Conv& conv) {
+struct TileRegs {
+    int4 centre;  // 4 consecutive z of row tid / 8
+    int edge;     // this thread's edge or corner value (threads 0..131)
+};
+
+// global -> registers half of the tile staging (raw heights; ABSENT for columns outside the region)
+__device__ __forceinline__ TileRegs fetch_heights_tile(const RegionDev& r, const int32_t* __restrict__ heights, int ix, int iz) {
     const int tid = threadIdx.x;
     auto tile_of = [&](int cix, int ciz) -> const int32_t* {
         if (cix < 0 || cix >= r.ncx || ciz < 0 || ciz >= r.ncz) return nullptr;
         return heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA;
     };
-    {   // centre: element e = x*32 + z, 4 consecutive z per thread
-        int4 v = __ldg(reinterpret_cast<const int4*>(tile_of(ix, iz)) + tid);
-        v.x = conv(v.x); v.y = conv(v.y); v.z = conv(v.z); v.w = conv(v.w);
+    TileRegs t;
+    t.centre = __ldg(reinterpret_cast<const int4*>(tile_of(ix, iz)) + tid);  // element e = x*32 + z
+    t.edge = kHeightAbsent;
+    if (tid < 128) {  // edges: west (x = -1), east (x = 32), south (z = -1), north (z = 32); 32 values each
+        const int side = tid >> 5, j = tid & 31;
+        const int32_t* p = side == 0 ? tile_of(ix - 1, iz) : side == 1 ? tile_of(ix + 1, iz)
+                         : side == 2 ? tile_of(ix, iz - 1) : tile_of(ix, iz + 1);
+        const int src = side == 0 ? 31 * 32 + j : side == 1 ? j : side == 2 ? j * 32 + 31 : j * 32;
+        if (p) t.edge = __ldg(p + src);
+    } else if (tid < 132) {  // corners
+        const int c = tid - 128, dx = (c & 1) ? 1 : -1, dz = (c & 2) ? 1 : -1;
+        const int32_t* p = tile_of(ix + dx, iz + dz);
+        if (p) t.edge = __ldg(p + (dx < 0 ? 31 : 0) * 32 + (dz < 0 ? 31 : 0));
+    }
+    return t;
+}
+
+// registers -> shared half; also this thread's partial max over the centre, min over the whole tile (hmin) and
+// min over centre + edges (emin: everything the six face masks look at)
+template <class Conv>
+__device__ __forceinline__ void store_heights_tile(const TileRegs& t, int* __restrict__ hts, int& cmax, int& hmin, int& emin,
+                                                   const Conv& conv) {
+    const int tid = threadIdx.x;
+    {
+        const int4 v = make_int4(conv(t.centre.x), conv(t.centre.y), conv(t.centre.z), conv(t.centre.w));
         const int x = tid >> 3, z = (tid & 7) * 4;
         int* o = hts + (x + 1) * kTile + (z + 1);
         o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
@@ -639,23 +665,25 @@ __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int3
         hmin = min(hmin, mn);
         emin = min(emin, mn);
     }
-    if (tid < 128) {  // edges: west (x = -1), east (x = 32), south (z = -1), north (z = 32); 32 values each
+    if (tid < 128) {
         const int side = tid >> 5, j = tid & 31;
-        const int32_t* t = side == 0 ? tile_of(ix - 1, iz) : side == 1 ? tile_of(ix + 1, iz)
-                         : side == 2 ? tile_of(ix, iz - 1) : tile_of(ix, iz + 1);
-        const int src = side == 0 ? 31 * 32 + j : side == 1 ? j : side == 2 ? j * 32 + 31 : j * 32;
         const int dst = side == 0 ? (j + 1) : side == 1 ? 33 * kTile + (j + 1) : side == 2 ? (j + 1) * kTile : (j + 1) * kTile + 33;
-        const int h = conv(t ? __ldg(t + src) : kHeightAbsent);
+        const int h = conv(t.edge);
         hts[dst] = h;
         hmin = min(hmin, h);
-        emin = min(emin, h);  // centre + the four edges (everything the six face masks look at)
-    } else if (tid < 132) {  // corners
-        const int c = tid - 128, dx = (c & 1) ? 1 : -1, dz = (c & 2) ? 1 : -1;
-        const int32_t* t = tile_of(ix + dx, iz + dz);
-        const int h = conv(t ? __ldg(t + (dx < 0 ? 31 : 0) * 32 + (dz < 0 ? 31 : 0)) : kHeightAbsent);
-        hts[(dx < 0 ? 0 : 33) * kTile + (dz < 0 ? 0 : 33)] = h;
+        emin = min(emin, h);
+    } else if (tid < 132) {
+        const int c = tid - 128;
+        const int h = conv(t.edge);
+        hts[((c & 1) ? 33 : 0) * kTile + ((c & 2) ? 33 : 0)] = h;
         hmin = min(hmin, h);
     }
+}
+
+template <class Conv>
+__device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int32_t* __restrict__ heights, int ix, int iz,
+                                                  int* __restrict__ hts, int& cmax, int& hmin, int& emin, const Conv& conv) {
+    store_heights_tile(fetch_heights_tile(r, heights, ix, iz), hts, cmax, hmin, emin, conv);
 }
 
 // Heightmap terrain, closed-form face count (the fused path's COUNT stage).  With solid(y) = y < h the
@@ -674,11 +702,15 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
     const RelHeight rel{(long long)r.cy0 * 32, 32 * r.ncy + 8};  // converted once while the tile is staged
     const int last = r.ncy - 1;
     const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
+    // the next column's tile is fetched into registers while the current one is counted
+    TileRegs next{};
+    if ((int)blockIdx.x < ncols) next = fetch_heights_tile(r, heights, r.ix_begin + (int)blockIdx.x / r.ncz, (int)blockIdx.x % r.ncz);
     for (int colw = blockIdx.x; colw < ncols; colw += gridDim.x) {
-    const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
     int cmax = INT32_MIN, hmin = INT32_MAX, emin = INT32_MAX;
     __syncthreads();  // previous column's readers of s_h are done
-    load_heights_tile(r, heights, ix, iz, s_h, cmax, hmin, emin, rel);
+    store_heights_tile(next, s_h, cmax, hmin, emin, rel);
+    const int coln = colw + (int)gridDim.x;
+    if (coln < ncols) next = fetch_heights_tile(r, heights, r.ix_begin + coln / r.ncz, coln % r.ncz);
     __syncthreads();
     for (int iy0 = 0; iy0 < r.ncy; iy0 += 32) {
         const int nl = min(32, r.ncy - iy0);
