@@ -143,50 +143,64 @@ __global__ void __launch_bounds__(kThreads) k_fill(Chunks chunks, const int32_t*
 // PaletteCube image after generate(): for a solid voxel, face f is kept iff the in-chunk neighbour
 // in direction f is air or f leaves the chunk; an air voxel has flags = 1 iff some in-chunk neighbour
 // is solid (CubeMesh::set touches it through remove_neighboring_faces, mesh.rs:209-232), else 0.
+//
+// Phase 1: one thread per column turns heights into eight 32-bit masks over y (six "face kept" masks, the
+// solid mask, "some in-chunk neighbour is solid").  Phase 2: one thread per voxel pair reads its column's masks
+// (two 128-bit shared loads, broadcast across the 16 lanes of a column) and writes 16 bytes; a warp instruction
+// stores 512 contiguous bytes.
 template <class Chunks>
 __global__ void __launch_bounds__(kThreads) k_fill_cubes(Chunks chunks, const int32_t* __restrict__ heights,
                                                           hb_palette_cube* __restrict__ cubes) {
-    __shared__ int s_h[HB_CHUNK_AREA];
+    __shared__ int s_d[HB_CHUNK_AREA];                   // clamp(h - wy0, 0, 40): solid voxels in the column, + margin
+    __shared__ __align__(16) uint32_t s_m[HB_CHUNK_AREA][8];  // E W U D N S kept-face masks, solid, neighbour-solid
     const size_t chunk = blockIdx.x;
     int col, cy;
     chunks.get(chunk, col, cy);
-    const int4* src = reinterpret_cast<const int4*>(heights + (size_t)col * HB_CHUNK_AREA);
-    reinterpret_cast<int4*>(s_h)[threadIdx.x] = __ldg(src + threadIdx.x);
-    __syncthreads();
     const long long wy0 = (long long)cy * 32;
+    {
+        const int4 h4 = __ldg(reinterpret_cast<const int4*>(heights + (size_t)col * HB_CHUNK_AREA) + threadIdx.x);
+        auto rel = [&](int h) -> int {
+            const long long d = (long long)h - wy0;
+            return (int)(d < 0 ? 0 : (d > 40 ? 40 : d));
+        };
+        reinterpret_cast<int4*>(s_d)[threadIdx.x] = make_int4(rel(h4.x), rel(h4.y), rel(h4.z), rel(h4.w));
+    }
+    __syncthreads();
+    auto solid_mask = [&](int c) -> uint32_t {
+        const int d = s_d[c];
+        return d >= 32 ? 0xFFFFFFFFu : ((1u << d) - 1u);
+    };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = k * kThreads + threadIdx.x, x = c >> 5, z = c & 31;
+        const uint32_t so = solid_mask(c);
+        const uint32_t nE = x < 31 ? solid_mask(c + 32) : 0u, nW = x > 0 ? solid_mask(c - 32) : 0u;
+        const uint32_t nN = z < 31 ? solid_mask(c + 1) : 0u, nS = z > 0 ? solid_mask(c - 1) : 0u;
+        const uint32_t nU = so >> 1, nD = so << 1;  // in-chunk voxel above / below
+        uint4 lo, hi;
+        lo.x = so & ~nE; lo.y = so & ~nW; lo.z = so & ~nU; lo.w = so & ~nD;
+        hi.x = so & ~nN; hi.y = so & ~nS; hi.z = so; hi.w = nE | nW | nU | nD | nN | nS;
+        *reinterpret_cast<uint4*>(&s_m[c][0]) = lo;
+        *reinterpret_cast<uint4*>(&s_m[c][4]) = hi;
+    }
+    __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(cubes + chunk * HB_CHUNK_VOLUME);
+#pragma unroll 4
     for (int it = 0; it < 64; ++it) {
-        const int p = it * kThreads + threadIdx.x;  // voxel pair
+        const int p = it * kThreads + threadIdx.x;  // voxel pair: L = 2p, 2p+1 (same column, y even / odd)
+        const int c = p >> 4, y = (p & 15) * 2;
+        const uint4 lo = *reinterpret_cast<const uint4*>(&s_m[c][0]);
+        const uint4 hi = *reinterpret_cast<const uint4*>(&s_m[c][4]);
+        const int d = s_d[c] - y;  // h - wy of the even voxel
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int L = 2 * p + e;
-            const int y = L & 31, z = (L >> 5) & 31, x = L >> 10;
-            const long long wy = wy0 + y;
-            const int c = x * 32 + z;
-            auto dcl = [&](int hh) -> int {
-                long long dl = (long long)hh - wy;
-                return (int)(dl < -8 ? -8 : (dl > 16 ? 16 : dl));
-            };
-            const int d = dcl(s_h[c]);
-            const uint32_t id = block_id(d);
-            // neighbour solidity: same column y+-1 -> d-1 / d+1; lateral columns at the same y
-            const bool sU = (y < 31) && (d - 1 > 0);
-            const bool sD = (y > 0) && (d + 1 > 0);
-            const bool sE = (x < 31) && (dcl(s_h[c + 32]) > 0);
-            const bool sW = (x > 0) && (dcl(s_h[c - 32]) > 0);
-            const bool sN = (z < 31) && (dcl(s_h[c + 1]) > 0);
-            const bool sS = (z > 0) && (dcl(s_h[c - 1]) > 0);
-            uint32_t flags;
-            if (id) {
-                const uint32_t faces = (sE ? 0u : 1u) | (sW ? 0u : 2u) | (sU ? 0u : 4u) | (sD ? 0u : 8u) |
-                                       (sN ? 0u : 16u) | (sS ? 0u : 32u);
-                flags = (faces << 1) | 1u;
-            } else {
-                flags = (sE | sW | sU | sD | sN | sS) ? 1u : 0u;
-            }
-            w[2 * e] = id;  // material u16 + zero pad
-            w[2 * e + 1] = flags;
+            const int yy = y + e;
+            const uint32_t faces = ((lo.x >> yy) & 1u) | (((lo.y >> yy) & 1u) << 1) | (((lo.z >> yy) & 1u) << 2) |
+                                   (((lo.w >> yy) & 1u) << 3) | (((hi.x >> yy) & 1u) << 4) | (((hi.y >> yy) & 1u) << 5);
+            const bool solid = (hi.z >> yy) & 1u;
+            w[2 * e] = block_id(d - e);                                       // material u16 + zero pad
+            w[2 * e + 1] = solid ? ((faces << 1) | 1u) : ((hi.w >> yy) & 1u);  // CubeFlags (cube.rs:69-72)
         }
         __stcs(dst + p, make_uint4(w[0], w[1], w[2], w[3]));
     }
