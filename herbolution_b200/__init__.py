@@ -5,15 +5,16 @@ This package is the thin host-side mirror of the reference's generator / mesher 
 ABI.  Importing it never touches the CPU oracle under oracle/; using it without the built CUDA
 library, or without a GPU, raises.
 """
-from ._lib import (CHUNK_AREA, CHUNK_LENGTH, CHUNK_PT_DTYPE, CHUNK_VOLUME, CUBE_DTYPE, INSTANCE_DTYPE, HerbGpuError,
+from ._lib import (CHUNK_AREA, CHUNK_CUBE_DTYPE, CHUNK_LENGTH, CHUNK_PT_DTYPE, CHUNK_VOLUME, CUBE_DTYPE, INSTANCE_DTYPE, HerbGpuError,
                    Region, STAGE_ALL_MESH, STAGE_COUNT, STAGE_EMIT, STAGE_FILL, STAGE_HEIGHTS, STAGE_SCAN)
 from .context import Context, RegionPlan
 from .generator import ChunkGenerator, ChunkPt, CubeMesh, GenerationParams
 from .mesher import ChunkData, ChunkMap, create_chunk_shell, generate_mesh
+from .world import World
 
 __all__ = [
-    "CHUNK_AREA", "CHUNK_LENGTH", "CHUNK_PT_DTYPE", "CHUNK_VOLUME", "CUBE_DTYPE", "INSTANCE_DTYPE", "HerbGpuError",
+    "CHUNK_AREA", "CHUNK_CUBE_DTYPE", "CHUNK_LENGTH", "CHUNK_PT_DTYPE", "CHUNK_VOLUME", "CUBE_DTYPE", "INSTANCE_DTYPE", "HerbGpuError",
     "Region", "STAGE_ALL_MESH", "STAGE_COUNT", "STAGE_EMIT", "STAGE_FILL", "STAGE_HEIGHTS", "STAGE_SCAN",
     "Context", "RegionPlan", "ChunkGenerator", "ChunkPt", "CubeMesh", "GenerationParams",
-    "ChunkData", "ChunkMap", "create_chunk_shell", "generate_mesh",
+    "ChunkData", "ChunkMap", "create_chunk_shell", "generate_mesh", "World",
 ]

@@ -35,7 +35,17 @@ CHUNK_PT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4")])
 INSTANCE_DTYPE = np.dtype([("model", "<f4", (16,)), ("rgba", "<f4", (4,)), ("light", "<u4"), ("ao", "<f4", (4,))])
 # == hb_palette_cube / PaletteCube (8 bytes, server/src/chunk/cube.rs:5-10)
 CUBE_DTYPE = np.dtype([("material", "<u2"), ("pad", "<u2"), ("flags", "<u4")])
+# == hb_chunk_cube / ChunkCube (12 bytes: vec3u5 position + PaletteCube, server/src/chunk/handle.rs:28-32)
+CHUNK_CUBE_DTYPE = np.dtype([("pos", "<u2"), ("pad0", "<u2"), ("material", "<u2"), ("pad", "<u2"), ("flags", "<u4")])
 assert INSTANCE_DTYPE.itemsize == 100 and CUBE_DTYPE.itemsize == 8 and CHUNK_PT_DTYPE.itemsize == 12
+assert CHUNK_CUBE_DTYPE.itemsize == 12
+
+
+class ChunkPtC(C.Structure):
+    """hb_chunk_pt passed by value."""
+
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("z", C.c_int32)]
+
 
 
 class Region(C.Structure):
@@ -102,6 +112,21 @@ PROTOTYPES = {
     "hb_dev_mesh_workspace_bytes": (C.c_size_t, [C.c_size_t]),
     "hb_dev_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    # device-resident world (server ChunkMap + CubeUpdate wire format + client remesh)
+    "hb_world_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "hb_world_destroy": (None, [C.c_void_p]),
+    "hb_world_len": (C.c_size_t, [C.c_void_p]),
+    "hb_world_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hb_world_unload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hb_world_set_cubes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hb_world_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
+    "hb_world_fetch_updates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_uint64]),
+    "hb_world_remesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
+    "hb_world_remesh_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]),
+    "hb_world_read_chunk": (C.c_int, [C.c_void_p, ChunkPtC, C.c_void_p]),
 }
 
 _lib = None

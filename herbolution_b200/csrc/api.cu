@@ -13,7 +13,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "common.cuh"
+#include "host_common.cuh"
 
 using namespace hb;
 
@@ -21,6 +21,9 @@ namespace {
 
 thread_local char g_err[512] = "";
 
+}  // namespace
+
+namespace hb {
 int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -28,34 +31,9 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+}  // namespace hb
 
-#define HB_CUDA(expr)                                                                                 \
-    do {                                                                                              \
-        cudaError_t e__ = (expr);                                                                     \
-        if (e__ != cudaSuccess)                                                                       \
-            return fail(HB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-
-// Growable device / pinned-host scratch buffer.
-struct Buf {
-    void* p = nullptr;
-    size_t cap = 0;
-    bool pinned = false;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        release();
-        const size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
-        if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
-        cap = want;
-        return cudaSuccess;
-    }
-    void release() {
-        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
-        p = nullptr; cap = 0;
-    }
-    template <class T> T* as() const { return static_cast<T*>(p); }
-};
+namespace {
 
 // Instance3d model_0..2 per face: CubeFace::rotation (lib/src/spatial/face.rs:60-69) ->
 // Quat::from_euler (lib/src/rotation.rs:77-88) -> to_axes (:109-116) -> * Mat3::from(Vec3::ONE)
@@ -120,54 +98,7 @@ void default_materials(MaterialsDev* m) {
     }
 }
 
-struct KeyXZ {
-    int32_t x, z;
-    bool operator==(const KeyXZ& o) const { return x == o.x && z == o.z; }
-};
-struct KeyXZHash {
-    size_t operator()(const KeyXZ& k) const {
-        return (size_t)(((uint64_t)(uint32_t)k.x << 32) | (uint32_t)k.z) * 0x9E3779B97F4A7C15ULL >> 7;
-    }
-};
-struct KeyXYZ {
-    int32_t x, y, z;
-    bool operator==(const KeyXYZ& o) const { return x == o.x && y == o.y && z == o.z; }
-};
-struct KeyXYZHash {
-    size_t operator()(const KeyXYZ& k) const {
-        uint64_t h = (uint64_t)(uint32_t)k.x * 0x9E3779B97F4A7C15ULL;
-        h ^= ((uint64_t)(uint32_t)k.y + 0x7F4A7C15ULL) * 0xC2B2AE3D27D4EB4FULL;
-        h = (h << 31) | (h >> 33);
-        h ^= (uint64_t)(uint32_t)k.z * 0x165667B19E3779F9ULL;
-        return (size_t)(h ^ (h >> 29));
-    }
-};
-
-bool coord_ok(int32_t c) { return c >= -HB_MAX_CHUNK_COORD && c <= HB_MAX_CHUNK_COORD; }
-
 }  // namespace
-
-struct hb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;  // compute
-    cudaStream_t copy = nullptr;    // D2H of finished slabs
-    std::mutex mu;
-    WorldDev world{};
-    int64_t seed = 0;
-    MeshTables tables{};
-    MaterialsDev mats{};
-    MaterialsDev* d_mats = nullptr;
-    // scratch for the host-pointer entry points
-    Buf d_pts, d_cols, d_colidx, d_heights, d_noise, d_ids, d_cubes, d_nbr, d_bitmaps, d_summary, d_counts,
-        d_offsets, d_scan, d_total, d_out;
-    Buf h_total;
-    // region streaming
-    Buf h_inst[2], h_off[2], h_cnt[2], h_ids[2];
-    hb_ctx() {
-        h_total.pinned = true;
-        for (int i = 0; i < 2; ++i) h_inst[i].pinned = h_off[i].pinned = h_cnt[i].pinned = h_ids[i].pinned = true;
-    }
-};
 
 struct hb_region_plan {
     hb_ctx* ctx = nullptr;

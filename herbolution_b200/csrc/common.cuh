@@ -49,6 +49,10 @@ cudaError_t launch_heights_region(cudaStream_t s, const WorldDev& w, const Regio
                                   size_t col_begin, size_t col_end);
 cudaError_t launch_fill(cudaStream_t s, const hb_chunk_pt* d_pts, const int32_t* d_col_of_chunk, size_t n,
                         const int32_t* d_heights, uint16_t* d_ids, hb_palette_cube* d_cubes);
+// PaletteCube images of n chunks written to slots d_slots[i] of a chunk store + their updated_positions sets
+cudaError_t launch_fill_world(cudaStream_t s, const hb_chunk_pt* d_pts, const int32_t* d_col_of_chunk, size_t n,
+                              const int32_t* d_heights, hb_palette_cube* d_store, const int32_t* d_slots,
+                              uint32_t* d_touched);
 cudaError_t launch_fill_region(cudaStream_t s, const RegionDev& r, const int32_t* d_heights, uint16_t* d_ids);
 cudaError_t launch_noise3d(cudaStream_t s, const WorldDev& w, float sx, float sy, float sz, int nx, int ny, int nz,
                            float fx, float fy, float fz, float* d_out);
@@ -56,13 +60,16 @@ cudaError_t launch_noise3d(cudaStream_t s, const WorldDev& w, float sx, float sy
 cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_materials, uint32_t* d_bitmaps,
                         uint32_t* d_summary, uint64_t* d_total);
 cudaError_t launch_pack_cubes(cudaStream_t s, const hb_palette_cube* d_cubes, size_t n, int n_materials,
-                              uint32_t* d_bitmaps, uint32_t* d_summary, uint32_t* d_planes, uint64_t* d_total);
+                              uint32_t* d_bitmaps, uint32_t* d_summary, uint32_t* d_planes, uint64_t* d_total,
+                              const int32_t* d_list = nullptr);
+// d_list (optional, both calls): work item j handles chunk d_list[j]; counts/offsets stay indexed by j while
+// cubes, bitmaps, summary, planes, pts and nbr are indexed by chunk (device-resident world slots).
 // d_blocks: u16 ids (d_planes == nullptr: faces recomputed) or hb_palette_cube (faces from d_planes [n][6][1024])
 cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
                             const hb_chunk_pt* d_pts, size_t n, const void* d_blocks, const int32_t* d_nbr,
                             const uint32_t* d_bitmaps, const uint32_t* d_summary, const uint32_t* d_planes,
                             uint32_t* d_counts, const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
-                            uint64_t* d_total);
+                            uint64_t* d_total, const int32_t* d_list = nullptr);
 cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
                                const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
                                const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,

@@ -148,12 +148,18 @@ __global__ void __launch_bounds__(kThreads) k_fill(Chunks chunks, const int32_t*
 // solid mask, "some in-chunk neighbour is solid").  Phase 2: one thread per voxel pair reads its column's masks
 // (two 128-bit shared loads, broadcast across the 16 lanes of a column) and writes 16 bytes; a warp instruction
 // stores 512 contiguous bytes.
+//
+// World mode (slots != nullptr): chunk i is written to slot slots[i] of the device-resident store, and the set of
+// positions CubeMesh::set pushed to updated_positions -- every solid voxel and every in-chunk neighbour of one --
+// goes to touched[slot][column] (bit y).
 template <class Chunks>
 __global__ void __launch_bounds__(kThreads) k_fill_cubes(Chunks chunks, const int32_t* __restrict__ heights,
-                                                          hb_palette_cube* __restrict__ cubes) {
+                                                          hb_palette_cube* __restrict__ cubes,
+                                                          const int32_t* __restrict__ slots, uint32_t* __restrict__ touched) {
     __shared__ int s_d[HB_CHUNK_AREA];                   // clamp(h - wy0, 0, 40): solid voxels in the column, + margin
     __shared__ __align__(16) uint32_t s_m[HB_CHUNK_AREA][8];  // E W U D N S kept-face masks, solid, neighbour-solid
     const size_t chunk = blockIdx.x;
+    const size_t slot = slots ? (size_t)slots[chunk] : chunk;
     int col, cy;
     chunks.get(chunk, col, cy);
     const long long wy0 = (long long)cy * 32;
@@ -182,9 +188,10 @@ __global__ void __launch_bounds__(kThreads) k_fill_cubes(Chunks chunks, const in
         hi.x = so & ~nN; hi.y = so & ~nS; hi.z = so; hi.w = nE | nW | nU | nD | nN | nS;
         *reinterpret_cast<uint4*>(&s_m[c][0]) = lo;
         *reinterpret_cast<uint4*>(&s_m[c][4]) = hi;
+        if (touched) touched[slot * HB_CHUNK_AREA + c] = hi.z | hi.w;
     }
     __syncthreads();
-    uint4* dst = reinterpret_cast<uint4*>(cubes + chunk * HB_CHUNK_VOLUME);
+    uint4* dst = reinterpret_cast<uint4*>(cubes + slot * HB_CHUNK_VOLUME);
 #pragma unroll 4
     for (int it = 0; it < 64; ++it) {
         const int p = it * kThreads + threadIdx.x;  // voxel pair: L = 2p, 2p+1 (same column, y even / odd)
@@ -243,7 +250,16 @@ cudaError_t launch_fill(cudaStream_t s, const hb_chunk_pt* d_pts, const int32_t*
     if (n == 0) return cudaSuccess;
     ChunkList cl{d_pts, d_col_of_chunk};
     if (d_ids) k_fill<ChunkList><<<(unsigned)n, kThreads, 0, s>>>(cl, d_heights, d_ids);
-    if (d_cubes) k_fill_cubes<ChunkList><<<(unsigned)n, kThreads, 0, s>>>(cl, d_heights, d_cubes);
+    if (d_cubes) k_fill_cubes<ChunkList><<<(unsigned)n, kThreads, 0, s>>>(cl, d_heights, d_cubes, nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_world(cudaStream_t s, const hb_chunk_pt* d_pts, const int32_t* d_col_of_chunk, size_t n,
+                              const int32_t* d_heights, hb_palette_cube* d_store, const int32_t* d_slots,
+                              uint32_t* d_touched) {
+    if (n == 0) return cudaSuccess;
+    k_fill_cubes<ChunkList><<<(unsigned)n, kThreads, 0, s>>>(ChunkList{d_pts, d_col_of_chunk}, d_heights, d_store, d_slots,
+                                                             d_touched);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,93 @@
+// host_common.cuh -- host-side definitions shared by api.cu and world.cu: error plumbing, scratch buffers,
+// chunk-coordinate hash keys and the context object behind the opaque hb_ctx handle.
+#pragma once
+#include <stdarg.h>
+#include <stdint.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace hb {
+
+// records the thread-local message hb_last_error() returns, and hands back `code` (api.cu)
+int fail(int code, const char* fmt, ...);
+
+#define HB_CUDA(expr)                                                                                 \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(HB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// Growable device / pinned-host scratch buffer.
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+        p = nullptr; cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+
+struct KeyXZ {
+    int32_t x, z;
+    bool operator==(const KeyXZ& o) const { return x == o.x && z == o.z; }
+};
+struct KeyXZHash {
+    size_t operator()(const KeyXZ& k) const {
+        return (size_t)(((uint64_t)(uint32_t)k.x << 32) | (uint32_t)k.z) * 0x9E3779B97F4A7C15ULL >> 7;
+    }
+};
+struct KeyXYZ {
+    int32_t x, y, z;
+    bool operator==(const KeyXYZ& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct KeyXYZHash {
+    size_t operator()(const KeyXYZ& k) const {
+        uint64_t h = (uint64_t)(uint32_t)k.x * 0x9E3779B97F4A7C15ULL;
+        h ^= ((uint64_t)(uint32_t)k.y + 0x7F4A7C15ULL) * 0xC2B2AE3D27D4EB4FULL;
+        h = (h << 31) | (h >> 33);
+        h ^= (uint64_t)(uint32_t)k.z * 0x165667B19E3779F9ULL;
+        return (size_t)(h ^ (h >> 29));
+    }
+};
+
+inline bool coord_ok(int32_t c) { return c >= -HB_MAX_CHUNK_COORD && c <= HB_MAX_CHUNK_COORD; }
+
+}  // namespace hb
+
+struct hb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;  // compute
+    cudaStream_t copy = nullptr;    // D2H of finished slabs
+    std::mutex mu;
+    hb::WorldDev world{};
+    int64_t seed = 0;
+    hb::MeshTables tables{};
+    hb::MaterialsDev mats{};
+    hb::MaterialsDev* d_mats = nullptr;
+    // scratch for the host-pointer entry points
+    hb::Buf d_pts, d_cols, d_colidx, d_heights, d_noise, d_ids, d_cubes, d_nbr, d_bitmaps, d_summary, d_counts,
+        d_offsets, d_scan, d_total, d_out;
+    hb::Buf h_total;
+    // region streaming
+    hb::Buf h_inst[2], h_off[2], h_cnt[2], h_ids[2];
+    hb_ctx() {
+        h_total.pinned = true;
+        for (int i = 0; i < 2; ++i) h_inst[i].pinned = h_off[i].pinned = h_cnt[i].pinned = h_ids[i].pinned = true;
+    }
+};
+

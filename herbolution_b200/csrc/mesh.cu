@@ -395,12 +395,16 @@ __global__ void __launch_bounds__(kT) k_pack(const uint16_t* __restrict__ ids, s
 // K3a for PaletteCube input (literal generate_mesh): occupancy bitmap (material.is_some()) + summary as k_pack,
 // plus six face planes from cube.flags: CubeFlags::faces() = (value & 1) ? (value >> 1) & 63 : none
 // (server/src/chunk/cube.rs:35-41), kept only where the voxel has a material (chunk.rs:187 gates on it).
+// `list` (optional): work item j processes chunk list[j] instead of chunk j (device-resident world: only the
+// slots whose cubes changed are re-packed).
 __global__ void __launch_bounds__(kT) k_pack_cubes(const hb_palette_cube* __restrict__ cubes, size_t n, int n_materials,
                                                    uint32_t* __restrict__ bitmaps, uint32_t* __restrict__ summary,
-                                                   uint32_t* __restrict__ planes, u64* __restrict__ total) {
+                                                   uint32_t* __restrict__ planes, u64* __restrict__ total,
+                                                   const int32_t* __restrict__ list) {
     __shared__ uint32_t s_red[8][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+    for (size_t item = blockIdx.x; item < n; item += gridDim.x) {
+        const size_t chunk = list ? (size_t)list[item] : item;
         const uint4* src = reinterpret_cast<const uint4*>(cubes + chunk * HB_CHUNK_VOLUME);
         uint32_t any = 0, bad = 0;
         for (int it = 0; it < 16; ++it) {
@@ -461,13 +465,14 @@ struct MatCubes {
 template <bool FLAGS>
 __global__ void __launch_bounds__(kT) k_count_ids(size_t n, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
                                                    const uint32_t* __restrict__ summary, const uint32_t* __restrict__ planes,
-                                                   uint32_t* __restrict__ counts) {
+                                                   uint32_t* __restrict__ counts, const int32_t* __restrict__ list) {
     __shared__ uint32_t s_part[kT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+    for (size_t item = blockIdx.x; item < n; item += gridDim.x) {
+        const size_t chunk = list ? (size_t)list[item] : item;  // counts[] is indexed by work item
         const uint32_t s = summary[chunk];
         if (!(s & 1u)) {  // no solid voxel
-            if (tid == 0) counts[chunk] = 0;
+            if (tid == 0) counts[item] = 0;
             continue;
         }
         uint32_t c = 0;
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(kT) k_count_ids(size_t n, const int32_t* __res
                 for (int f = 0; f < 6; ++f)
                     if (nf[f] < 0 || !((summary[nf[f]] >> (2 + (f ^ 1))) & 1u)) buried = false;
                 if (buried) {
-                    if (tid == 0) counts[chunk] = 0;
+                    if (tid == 0) counts[item] = 0;
                     continue;
                 }
             }
@@ -516,7 +521,7 @@ __global__ void __launch_bounds__(kT) k_count_ids(size_t n, const int32_t* __res
             uint32_t t = 0;
 #pragma unroll
             for (int i = 0; i < kT / 32; ++i) t += s_part[i];
-            counts[chunk] = t;
+            counts[item] = t;
         }
         __syncthreads();
     }
@@ -529,16 +534,18 @@ __global__ void __launch_bounds__(kT, kCtasPerSm)
 k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_chunk_pt* __restrict__ pts, size_t n,
            const void* __restrict__ blocks, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
            const uint32_t* __restrict__ summary, const uint32_t* __restrict__ planes, uint32_t* __restrict__ counts,
-           const u64* __restrict__ offsets, float* __restrict__ out, u64 capacity, u64* __restrict__ total) {
+           const u64* __restrict__ offsets, float* __restrict__ out, u64 capacity, u64* __restrict__ total,
+           const int32_t* __restrict__ list) {
     __shared__ MeshSmem sm;
     const int tid = threadIdx.x;
     if (EMIT) load_tables(sm, tb);
-    for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+    for (size_t item = blockIdx.x; item < n; item += gridDim.x) {
         // block-uniform early out: the COUNT stage already knows which chunks have no visible face at all
         // (all air, or buried: k_count_ids), so EMIT needs one load per chunk to skip them
-        const uint32_t my_count = counts[chunk];
+        const uint32_t my_count = counts[item];
         if (my_count == 0) continue;
-        const u64 off = offsets[chunk];
+        const u64 off = offsets[item];
+        const size_t chunk = list ? (size_t)list[item] : item;  // counts[] / offsets[] are indexed by work item
         if (off + (((u64)my_count + 3ULL) & ~3ULL) > capacity) {
             if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
             continue;
@@ -586,7 +593,7 @@ k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
             q = mesh_tile<EMIT>(sm, mat, FacesFromOcc{sm.occ}, pt.x * 32, pt.y * 32, pt.z * 32, mats,
                                 EMIT ? out + off * 25ULL : nullptr);
         }
-        if (!EMIT && tid == 0) counts[chunk] = q;
+        if (!EMIT && tid == 0) counts[item] = q;
     }
     if (EMIT) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
 }
@@ -960,11 +967,12 @@ cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_m
 }
 
 cudaError_t launch_pack_cubes(cudaStream_t s, const hb_palette_cube* d_cubes, size_t n, int n_materials,
-                              uint32_t* d_bitmaps, uint32_t* d_summary, uint32_t* d_planes, uint64_t* d_total) {
+                              uint32_t* d_bitmaps, uint32_t* d_summary, uint32_t* d_planes, uint64_t* d_total,
+                              const int32_t* d_list) {
     if (n == 0) return cudaSuccess;
     size_t grid = (size_t)num_sms() * 8;
     if (grid > n) grid = n;
-    k_pack_cubes<<<(unsigned)grid, kT, 0, s>>>(d_cubes, n, n_materials, d_bitmaps, d_summary, d_planes, (u64*)d_total);
+    k_pack_cubes<<<(unsigned)grid, kT, 0, s>>>(d_cubes, n, n_materials, d_bitmaps, d_summary, d_planes, (u64*)d_total, d_list);
     return cudaGetLastError();
 }
 
@@ -972,7 +980,7 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
                             const hb_chunk_pt* d_pts, size_t n, const void* d_blocks, const int32_t* d_nbr,
                             const uint32_t* d_bitmaps, const uint32_t* d_summary, const uint32_t* d_planes,
                             uint32_t* d_counts, const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
-                            uint64_t* d_total) {
+                            uint64_t* d_total, const int32_t* d_list) {
     if (n == 0) return cudaSuccess;
     // Persistent CTAs stride through the chunk list.  Batches are usually ordered (ix, iz, iy) with a small number
     // of layers, so an even stride would hand every CTA the same layer (all surface or all buried) for the whole
@@ -981,12 +989,12 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
     if (grid > n) grid = n;
 #define HB_LAUNCH(E, F)                                                                                              \
     k_mesh_ids<E, F><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, d_pts, n, d_blocks, d_nbr, d_bitmaps, d_summary, d_planes, \
-                                                   d_counts, (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total)
+                                                   d_counts, (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total, d_list)
     if (!emit) {
         size_t cgrid = (size_t)num_sms() * 8 - 1;  // odd, see above
         if (cgrid > n) cgrid = n;
-        if (d_planes) k_count_ids<true><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts);
-        else k_count_ids<false><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts);
+        if (d_planes) k_count_ids<true><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts, d_list);
+        else k_count_ids<false><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts, d_list);
     } else if (d_planes) {
         HB_LAUNCH(true, true);
     } else {

@@ -1,0 +1,123 @@
+"""World: the device-resident ChunkMap (hb_world_*), numpy-typed 1:1 wrappers.
+
+Mirrors the reference's runtime loop on both sides of the wire:
+
+    server  ChunkMap::queue_load / load_provided   -> World.load          (server/src/chunk/map.rs:69-75,203-228)
+            ChunkMap::set_cube                     -> World.set_cubes     (map.rs:81-151)
+            Chunk::sync_with_client                -> World.sync / fetch_updates   (server/src/chunk/mod.rs:35-67)
+    client  ChunkMap::update (remesh what changed) -> World.remesh        (client/src/world/chunk.rs:47-76)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import CHUNK_CUBE_DTYPE, CHUNK_PT_DTYPE, CHUNK_VOLUME, CUBE_DTYPE, INSTANCE_DTYPE, ChunkPtC, check, ptr
+from .context import Context, as_chunk_pts
+
+
+def vec3u5_unpack(pos: np.ndarray):
+    """vec3u5 bits -> (x, y, z) (lib/src/vector.rs:1181-1193)."""
+    p = np.asarray(pos, dtype=np.uint16).astype(np.int64)
+    return (p >> 11) & 31, (p >> 6) & 31, (p >> 1) & 31
+
+
+class World:
+    def __init__(self, ctx: Context, capacity: int):
+        self._lib = _lib.load()
+        self.ctx = ctx
+        self.capacity = int(capacity)
+        self._h = C.c_void_p()
+        check(self._lib.hb_world_create(ctx._h, self.capacity, C.byref(self._h)))
+
+    def __len__(self) -> int:
+        return int(self._lib.hb_world_len(self._h))
+
+    def load(self, positions) -> None:
+        pts = as_chunk_pts(positions)
+        check(self._lib.hb_world_load(self._h, ptr(pts), pts.shape[0]))
+
+    def unload(self, positions) -> None:
+        pts = as_chunk_pts(positions)
+        check(self._lib.hb_world_unload(self._h, ptr(pts), pts.shape[0]))
+
+    def set_cubes(self, cubes_xyz, materials) -> None:
+        """Edits applied in order; cubes_xyz (n, 3) world cube coordinates, materials 0 = dig."""
+        xyz = np.ascontiguousarray(cubes_xyz, dtype=np.int32).reshape(-1, 3)
+        mats = np.ascontiguousarray(materials, dtype=np.uint16).reshape(-1)
+        if mats.shape[0] != xyz.shape[0]:
+            raise ValueError("one material per edit")
+        check(self._lib.hb_world_set_cubes(self._h, ptr(xyz), ptr(mats), xyz.shape[0]))
+
+    def set_cube(self, position, material: int) -> None:
+        self.set_cubes([position], [material])
+
+    def sync(self) -> tuple:
+        """Returns (dirty chunks, CubeUpdate entries) drained by this sync."""
+        n, e = C.c_size_t(0), C.c_uint64(0)
+        check(self._lib.hb_world_sync(self._h, C.byref(n), C.byref(e)))
+        self._last = (n.value, e.value)
+        return self._last
+
+    def fetch_updates(self) -> dict:
+        """{"pts", "offsets", "counts", "entries" (CHUNK_CUBE_DTYPE)} of the last sync()."""
+        n, e = getattr(self, "_last", (0, 0))
+        pts = np.zeros(n, dtype=CHUNK_PT_DTYPE)
+        offsets = np.zeros(n, dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.uint32)
+        entries = np.zeros(e, dtype=CHUNK_CUBE_DTYPE)
+        check(self._lib.hb_world_fetch_updates(self._h, ptr(pts), n, ptr(offsets), ptr(counts), ptr(entries), e))
+        return {"pts": pts, "offsets": offsets, "counts": counts, "entries": entries}
+
+    def remesh(self) -> dict:
+        """{"pts", "offsets", "counts", "instances"} for every chunk that received a CubeUpdate since the last remesh."""
+        n, total = C.c_size_t(0), C.c_uint64(0)
+        rc = self._lib.hb_world_remesh(self._h, None, 0, None, 0, None, None, C.byref(n), C.byref(total))
+        if rc not in (_lib.HB_OK, _lib.HB_ERR_CAPACITY):
+            check(rc)
+        pts = np.zeros(n.value, dtype=CHUNK_PT_DTYPE)
+        offsets = np.zeros(n.value, dtype=np.uint64)
+        counts = np.zeros(n.value, dtype=np.uint32)
+        inst = np.zeros(total.value, dtype=INSTANCE_DTYPE)
+        if rc == _lib.HB_ERR_CAPACITY:
+            check(self._lib.hb_world_remesh(self._h, ptr(pts), n.value, ptr(inst), total.value, ptr(offsets), ptr(counts),
+                                            C.byref(n), C.byref(total)))
+        return {"pts": pts, "offsets": offsets, "counts": counts, "instances": inst}
+
+    def remesh_dev(self) -> dict:
+        """Like remesh() but the instances stay in HBM: adds "d_instances" (raw device pointer) and "span"."""
+        n, total = C.c_size_t(0), C.c_uint64(0)
+        d = C.c_void_p()
+        cap = self.capacity
+        pts = np.zeros(cap, dtype=CHUNK_PT_DTYPE)
+        offsets = np.zeros(cap, dtype=np.uint64)
+        counts = np.zeros(cap, dtype=np.uint32)
+        check(self._lib.hb_world_remesh_dev(self._h, ptr(pts), cap, ptr(offsets), ptr(counts), C.byref(n), C.byref(total),
+                                            C.byref(d)))
+        k = n.value
+        return {"pts": pts[:k], "offsets": offsets[:k], "counts": counts[:k], "span": total.value, "d_instances": d.value}
+
+    def read_chunk(self, position) -> np.ndarray:
+        x, y, z = (int(v) for v in position)
+        out = np.zeros(CHUNK_VOLUME, dtype=CUBE_DTYPE)
+        check(self._lib.hb_world_read_chunk(self._h, ChunkPtC(x, y, z), ptr(out)))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.hb_world_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -217,6 +217,73 @@ HB_API int hb_dev_mesh(hb_ctx *ctx, void *stream, const hb_chunk_pt *d_pts, size
                 const int32_t *d_neighbor_index, void *d_workspace, hb_instance3d *d_out,
                 uint64_t out_capacity, uint64_t *d_offsets, uint32_t *d_counts, uint64_t *d_total);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident world: the server's ChunkMap (server/src/chunk/map.rs) with its PaletteCube arrays kept
+ * in HBM, the incremental dig/place path, the server->client CubeUpdate wire format and the client's
+ * remesh-what-changed loop.  One hb_world serves both sides: the client's
+ * ChunkData is a copy of the server's cubes kept current by CubeUpdates (client/src/world/chunk.rs:132-149),
+ * so meshing from the resident cubes after a sync equals meshing the client's copy.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hb_world hb_world;
+
+/* == ChunkCube (server/src/chunk/handle.rs:28-32): vec3u5 position + PaletteCube.  The Rust struct is
+ * repr(Rust) and never leaves the process, so this 12-byte C layout is the binding's own. */
+typedef struct hb_chunk_cube {
+    uint16_t pos;   /* vec3u5 bits: 1 | x<<11 | y<<6 | z<<1 (lib/src/vector.rs:1181-1193) */
+    uint16_t _pad;
+    hb_palette_cube cube;
+} hb_chunk_cube;
+
+/* A store of `capacity` chunk slots (292 KiB of HBM each: cubes, update sets, mesher bitmaps). */
+HB_API int hb_world_create(hb_ctx *ctx, size_t capacity, hb_world **out);
+HB_API void hb_world_destroy(hb_world *world);
+HB_API size_t hb_world_len(const hb_world *world);          /* chunks currently loaded */
+
+/* ChunkMap::queue_load + ChunkGenerator + ChunkMap::load_provided (server/src/chunk/map.rs:69-75,203-228,
+ * server/src/generator/mod.rs:32-95): generates every not-yet-loaded chunk of pts[0..n) straight into its slot
+ * (PaletteCube image as CubeMesh::set leaves it), then runs cull_shared_faces (server/src/chunk/mesh.rs:76-123)
+ * for every (new chunk, loaded face neighbour) pair.  Already-loaded and repeated positions are ignored, as
+ * queue_load does.  HB_ERR_CAPACITY (nothing changed) if the free slots do not suffice. */
+HB_API int hb_world_load(hb_world *world, const hb_chunk_pt *pts, size_t n);
+/* ChunkMap::unload_requested (map.rs:230-235): the slot is freed; neighbours keep whatever faces the earlier
+ * cull removed, exactly as the reference leaves them. */
+HB_API int hb_world_unload(hb_world *world, const hb_chunk_pt *pts, size_t n);
+
+/* ChunkMap::set_cube (map.rs:81-151) applied to n edits IN ORDER: cubes_xyz = n x 3 world cube coordinates
+ * (chunk = c >> 5, local = c & 31, lib/src/point.rs:25-32), materials[i] = 0 (None: dig) or a palette id.
+ * Includes the reference's border behaviour: the face of the adjacent chunk's border voxel is inserted
+ * unconditionally, and edits to a position whose own chunk is not loaded still touch loaded neighbours. */
+HB_API int hb_world_set_cubes(hb_world *world, const int32_t *cubes_xyz, const uint16_t *materials, size_t n);
+
+/* Chunk::sync_with_client (server/src/chunk/mod.rs:35-67) for every chunk: drains each chunk's
+ * updated_positions.  Chunks with a non-empty set join the remesh set (they are the chunks whose client copy
+ * receives a CubeUpdate, client/src/world/chunk.rs:52-63).  Reports how many chunks were dirty and how many
+ * hb_chunk_cube entries hb_world_fetch_updates would deliver.  The reference keeps updated_positions as a Vec with
+ * duplicates; here it is a set (one bit per voxel), which the client cannot tell apart: apply_updates_from_server
+ * overwrites cubes[pos] with the same final cube for every duplicate. */
+HB_API int hb_world_sync(hb_world *world, size_t *n_dirty, uint64_t *n_entries);
+/* The CubeUpdates of the last hb_world_sync, one run per dirty chunk: out_pts[i] = chunk, its entries are
+ * out_entries[out_offsets[i] .. +out_counts[i]) in ascending voxel index, each carrying the cube as it is now.
+ * Optional (a fused server+client can skip the wire format and go straight to hb_world_remesh).
+ * HB_ERR_CAPACITY if pts_capacity / entries_capacity are too small. */
+HB_API int hb_world_fetch_updates(hb_world *world, hb_chunk_pt *out_pts, size_t pts_capacity, uint64_t *out_offsets,
+                           uint32_t *out_counts, hb_chunk_cube *out_entries, uint64_t entries_capacity);
+
+/* Client ChunkMap::update (client/src/world/chunk.rs:47-76): generate_mesh (faces read from cube.flags, AO and
+ * occupancy through the 27-chunk shell of loaded chunks) for every chunk of the remesh set that is still loaded.
+ * Two-call pattern like hb_mesh: with too small a pts_capacity / out_capacity the call reports *n_chunks and
+ * *out_total, returns HB_ERR_CAPACITY and keeps the remesh set; on HB_OK the set is cleared.  Chunk i's
+ * instances are out[out_offsets[i] .. +out_counts[i]) (offsets are multiples of 4, gaps zero-filled). */
+HB_API int hb_world_remesh(hb_world *world, hb_chunk_pt *out_pts, size_t pts_capacity, hb_instance3d *out,
+                    uint64_t out_capacity, uint64_t *out_offsets, uint32_t *out_counts, size_t *n_chunks,
+                    uint64_t *out_total);
+/* Same, leaving the instances in device memory (valid until the next hb_world_* call on this world). */
+HB_API int hb_world_remesh_dev(hb_world *world, hb_chunk_pt *out_pts, size_t pts_capacity, uint64_t *out_offsets,
+                        uint32_t *out_counts, size_t *n_chunks, uint64_t *out_total,
+                        const hb_instance3d **d_instances);
+/* Copy one loaded chunk's PaletteCube array (32768 x 8 B) to the host; HB_ERR_INVALID if it is not loaded. */
+HB_API int hb_world_read_chunk(hb_world *world, hb_chunk_pt pt, hb_palette_cube *out_cubes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -358,6 +358,13 @@ static inline int cullable_nonempty(uint16_t material) { return material != 0; }
 static const int NORMAL[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 static inline int inverse_face(int f) { return f ^ 1; } /* face.rs:71-81 */
 
+/* updated_positions.push(vec3u5::new(x, y, z)) */
+static inline void push_updated(hbo_cube_mesh *m, int x, int y, int z) {
+    if (m->upd && m->n_updated < m->upd_cap)
+        m->upd[m->n_updated] = (uint16_t)(1u | ((unsigned)x << 11) | ((unsigned)y << 6) | ((unsigned)z << 1));
+    m->n_updated++;
+}
+
 /* mesh.rs:209-232 */
 static void remove_neighboring_faces(hbo_cube_mesh *m, uint32_t faces, int x, int y, int z) {
     for (int f = 0; f < 6; ++f) { /* FaceIter order, face.rs:313-329 */
@@ -366,7 +373,7 @@ static void remove_neighboring_faces(hbo_cube_mesh *m, uint32_t faces, int x, in
         if (nx < 0 || ny < 0 || nz < 0) continue;       /* try_cast::<u8>() fails */
         if (nx >= 32 || ny >= 32 || nz >= 32) continue; /* vec3u5::try_from fails */
         int index = lin(nx, ny, nz);
-        m->n_updated++;
+        push_updated(m, nx, ny, nz);
         if (cullable_nonempty(m->data[index].material)) cube_remove_face(&m->data[lin(x, y, z)], f);
         cube_remove_face(&m->data[index], inverse_face(f));
     }
@@ -379,7 +386,7 @@ static void add_neighboring_faces(hbo_cube_mesh *m, uint32_t faces, int x, int y
         if (!(it & (1u << f))) continue;
         int nx = x + NORMAL[f][0], ny = y + NORMAL[f][1], nz = z + NORMAL[f][2];
         if (nx < 0 || ny < 0 || nz < 0 || nx >= 32 || ny >= 32 || nz >= 32) continue;
-        m->n_updated++;
+        push_updated(m, nx, ny, nz);
         cube_insert_face(&m->data[lin(nx, ny, nz)], inverse_face(f));
     }
 }
@@ -403,7 +410,7 @@ void hbo_mesh_set(hbo_cube_mesh *m, int x, int y, int z, uint16_t new_material) 
         m->data[i].flags = flags_set_opaque(0u);
         add_neighboring_faces(m, present, x, y, z);
     }
-    m->n_updated++;
+    push_updated(m, x, y, z);
 }
 
 /* generator/mod.rs:63-95 through CubeMesh::set */
@@ -493,8 +500,8 @@ void hbo_cull_shared_faces(hbo_cube_mesh *a, hbo_cube_mesh *b) {
             if (cullable_nonempty(ca->material) && cullable_nonempty(cb->material)) {
                 cube_remove_face(ca, shared);
                 cube_remove_face(cb, other_shared);
-                a->n_updated++;
-                b->n_updated++;
+                push_updated(a, pa[0], pa[1], pa[2]);
+                push_updated(b, pb[0], pb[1], pb[2]);
             }
         }
 }
@@ -879,4 +886,148 @@ uint64_t hbo_region_pipeline(const hbo_world *w, const hbo_palette *pal,
     free(offsets);
     free(own_counts);
     return total;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Server ChunkMap, CubeUpdate wire format, client apply  */
+/* ------------------------------------------------------------------------- */
+
+struct hbo_map {
+    hbo_world world;
+    hbo_cube_mesh **chunks; /* by handle; NULL after unload */
+    int n, cap;
+};
+
+hbo_map *hbo_map_create(const hbo_world *w) {
+    hbo_map *m = (hbo_map *)calloc(1, sizeof(*m));
+    if (m) m->world = *w;
+    return m;
+}
+
+static void map_free_chunk(hbo_cube_mesh *c) {
+    if (!c) return;
+    free(c->upd);
+    free(c);
+}
+
+void hbo_map_destroy(hbo_map *m) {
+    if (!m) return;
+    for (int i = 0; i < m->n; ++i) map_free_chunk(m->chunks[i]);
+    free(m->chunks);
+    free(m);
+}
+
+int hbo_map_find(const hbo_map *m, int32_t cx, int32_t cy, int32_t cz) {
+    for (int i = 0; i < m->n; ++i) {
+        const hbo_cube_mesh *c = m->chunks[i];
+        if (c && c->pos[0] == cx && c->pos[1] == cy && c->pos[2] == cz) return i;
+    }
+    return -1;
+}
+
+int hbo_map_len(const hbo_map *m) { return m->n; }
+
+/* the log must hold every push a chunk can see between two drains: generation pushes at most
+ * 7 per voxel, six culls 1024 each; edits add a handful.  Grown on demand at drain time is not
+ * possible (pushes happen inside set()), so it is sized generously and pushes past it are an error
+ * the tests check for via hbo_map_pending() > stored. */
+#define HBO_UPD_CAP ((uint64_t)HBO_CHUNK_VOLUME * 8u)
+
+int hbo_map_load(hbo_map *m, int32_t cx, int32_t cy, int32_t cz) {
+    int h = hbo_map_find(m, cx, cy, cz);
+    if (h >= 0) return h; /* map.rs:69-75 */
+    hbo_cube_mesh *c = (hbo_cube_mesh *)malloc(sizeof(*c));
+    if (!c) return -1;
+    hbo_mesh_init(c, cx, cy, cz);
+    c->upd = (uint16_t *)malloc(sizeof(uint16_t) * HBO_UPD_CAP);
+    c->upd_cap = c->upd ? HBO_UPD_CAP : 0;
+    hbo_generate_literal(&m->world, c);
+    /* map.rs:203-228: for face in CubeFace::values(): neighbour loaded -> mesh.cull_shared_faces(adj) */
+    for (int f = 0; f < 6; ++f) {
+        int o = hbo_map_find(m, cx + NORMAL[f][0], cy + NORMAL[f][1], cz + NORMAL[f][2]);
+        if (o >= 0) hbo_cull_shared_faces(c, m->chunks[o]);
+    }
+    if (m->n == m->cap) {
+        int ncap = m->cap ? m->cap * 2 : 64;
+        hbo_cube_mesh **nc = (hbo_cube_mesh **)realloc(m->chunks, sizeof(*nc) * (size_t)ncap);
+        if (!nc) { map_free_chunk(c); return -1; }
+        m->chunks = nc;
+        m->cap = ncap;
+    }
+    m->chunks[m->n] = c;
+    return m->n++;
+}
+
+void hbo_map_unload(hbo_map *m, int32_t cx, int32_t cy, int32_t cz) {
+    int h = hbo_map_find(m, cx, cy, cz);
+    if (h < 0) return;
+    map_free_chunk(m->chunks[h]);
+    m->chunks[h] = NULL;
+}
+
+/* map.rs:81-151 */
+void hbo_map_set_cube(hbo_map *m, int32_t wx, int32_t wy, int32_t wz, uint16_t material) {
+    /* lib/src/point.rs:25-32: chunk = p >> 5 (arithmetic), local = p & 31 */
+    const int32_t c[3] = {wx >> 5, wy >> 5, wz >> 5};
+    const int l[3] = {wx & 31, wy & 31, wz & 31};
+    /* edges, in the reference's order: (-x, EAST), (+x, WEST), (-y, UP), (+y, DOWN), (-z, NORTH), (+z, SOUTH) */
+    static const int off[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+    static const int face_of[6] = {0, 1, 2, 3, 4, 5};
+    for (int e = 0; e < 6; ++e) {
+        const int axis = e >> 1, neg = (e & 1) == 0;
+        if (!(neg ? l[axis] == 0 : l[axis] == 31)) continue;
+        int o = hbo_map_find(m, c[0] + off[e][0], c[1] + off[e][1], c[2] + off[e][2]);
+        if (o < 0) continue;
+        int nl[3] = {l[0], l[1], l[2]};
+        nl[axis] = neg ? 31 : 0;
+        hbo_cube_mesh *nm = m->chunks[o];
+        cube_insert_face(&nm->data[lin(nl[0], nl[1], nl[2])], face_of[e]); /* unconditional, map.rs:113 */
+        push_updated(nm, nl[0], nl[1], nl[2]);
+    }
+    int h = hbo_map_find(m, c[0], c[1], c[2]);
+    if (h < 0) return;
+    /* palette.get_id_by_key: stone/dirt/grass are in every generated chunk's palette (ids 1..3) */
+    hbo_mesh_set(m->chunks[h], l[0], l[1], l[2], material);
+}
+
+const hbo_cube *hbo_map_cubes(const hbo_map *m, int handle) {
+    if (handle < 0 || handle >= m->n || !m->chunks[handle]) return NULL;
+    return m->chunks[handle]->data;
+}
+
+void hbo_map_position(const hbo_map *m, int handle, int32_t pos[3]) {
+    pos[0] = pos[1] = pos[2] = 0;
+    if (handle < 0 || handle >= m->n || !m->chunks[handle]) return;
+    memcpy(pos, m->chunks[handle]->pos, sizeof(int32_t) * 3);
+}
+
+uint64_t hbo_map_pending(const hbo_map *m, int handle) {
+    if (handle < 0 || handle >= m->n || !m->chunks[handle]) return 0;
+    return m->chunks[handle]->n_updated;
+}
+
+/* server/src/chunk/mod.rs:35-67 */
+uint64_t hbo_map_drain(hbo_map *m, int handle, hbo_chunk_cube *out, uint64_t cap) {
+    if (handle < 0 || handle >= m->n || !m->chunks[handle]) return 0;
+    hbo_cube_mesh *c = m->chunks[handle];
+    const uint64_t n = c->n_updated < c->upd_cap ? c->n_updated : c->upd_cap;
+    for (uint64_t i = 0; i < n && i < cap; ++i) {
+        const unsigned p = c->upd[i];
+        const int x = (p >> 11) & 31, y = (p >> 6) & 31, z = (p >> 1) & 31;
+        out[i].pos = (uint16_t)p;
+        out[i].pad = 0;
+        out[i].cube = c->data[lin(x, y, z)];
+    }
+    const uint64_t total = c->n_updated;
+    c->n_updated = 0;
+    return total;
+}
+
+/* client/src/world/chunk.rs:132-149 */
+void hbo_apply_updates(hbo_cube *client_cubes, const hbo_chunk_cube *entries, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const unsigned p = entries[i].pos;
+        const int x = (p >> 11) & 31, y = (p >> 6) & 31, z = (p >> 1) & 31;
+        client_cubes[lin(x, y, z)] = entries[i].cube;
+    }
 }

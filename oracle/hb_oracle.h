@@ -83,6 +83,8 @@ typedef struct hbo_cube_mesh {
     int32_t pos[3];
     hbo_cube data[HBO_CHUNK_VOLUME];
     uint64_t n_updated;            /* updated_positions.len() */
+    uint16_t *upd;                 /* optional log of updated_positions (vec3u5 bits); NULL = count only */
+    uint64_t upd_cap;              /* entries `upd` can hold; pushes beyond it are counted, not stored */
 } hbo_cube_mesh;
 
 /* ---- noise (crates/simd-noise) ---- */
@@ -130,6 +132,39 @@ uint64_t hbo_region_pipeline(const hbo_world *w, const hbo_palette *pal,
                              int32_t cy0, int32_t ncy, int literal, int threads,
                              uint32_t *counts, hbo_instance *out, size_t cap,
                              uint16_t *ids_out, double secs[3]);
+
+/* ---- server ChunkMap + wire format + client remesh ----
+ * hbo_map is the server's ChunkMap (server/src/chunk/map.rs) holding CubeMeshes with their
+ * updated_positions logs.  Chunk handles are dense indices in load order. */
+typedef struct hbo_map hbo_map;
+/* == ChunkCube (server/src/chunk/handle.rs:28-32): vec3u5 position + PaletteCube.  The Rust struct
+ * is repr(Rust); this 12-byte C layout is ours. */
+typedef struct hbo_chunk_cube {
+    uint16_t pos;                  /* vec3u5 bits: 1 | x<<11 | y<<6 | z<<1 (lib/src/vector.rs:1181-1193) */
+    uint16_t pad;
+    hbo_cube cube;
+} hbo_chunk_cube;
+
+hbo_map *hbo_map_create(const hbo_world *w);
+void hbo_map_destroy(hbo_map *m);
+/* generator (literal set() path) + ChunkMap::load_provided (map.rs:203-228): cull_shared_faces
+ * against every already-loaded face neighbour, then insert.  Returns the chunk's handle, or the
+ * existing one if it is already loaded (queue_load ignores those, map.rs:69-75). */
+int hbo_map_load(hbo_map *m, int32_t cx, int32_t cy, int32_t cz);
+int hbo_map_find(const hbo_map *m, int32_t cx, int32_t cy, int32_t cz); /* -1 = not loaded */
+void hbo_map_unload(hbo_map *m, int32_t cx, int32_t cy, int32_t cz);   /* map.rs:230-235 */
+int hbo_map_len(const hbo_map *m);                                     /* handles issued so far */
+/* ChunkMap::set_cube (map.rs:81-151), world cube coordinates, material 0 = None */
+void hbo_map_set_cube(hbo_map *m, int32_t wx, int32_t wy, int32_t wz, uint16_t material);
+const hbo_cube *hbo_map_cubes(const hbo_map *m, int handle);           /* NULL if unloaded */
+void hbo_map_position(const hbo_map *m, int handle, int32_t pos[3]);
+uint64_t hbo_map_pending(const hbo_map *m, int handle);                /* updated_positions.len() */
+/* Chunk::sync_with_client (server/src/chunk/mod.rs:35-67): drains updated_positions (duplicates
+ * and order kept) into ChunkCube entries carrying the cube as it is now.  Returns the number of
+ * entries; writes at most cap. */
+uint64_t hbo_map_drain(hbo_map *m, int handle, hbo_chunk_cube *out, uint64_t cap);
+/* client apply_updates_from_server (client/src/world/chunk.rs:132-149) */
+void hbo_apply_updates(hbo_cube *client_cubes, const hbo_chunk_cube *entries, uint64_t n);
 
 #ifdef __cplusplus
 }

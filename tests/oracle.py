@@ -35,7 +35,8 @@ class Palette(C.Structure):
 
 
 class CubeMeshC(C.Structure):
-    _fields_ = [("pos", C.c_int32 * 3), ("data", C.c_uint8 * (8 * CHUNK_VOLUME)), ("n_updated", C.c_uint64)]
+    _fields_ = [("pos", C.c_int32 * 3), ("data", C.c_uint8 * (8 * CHUNK_VOLUME)), ("n_updated", C.c_uint64),
+                ("upd", C.c_void_p), ("upd_cap", C.c_uint64)]
 
 
 _lib = None
@@ -57,6 +58,29 @@ def lib() -> C.CDLL:
         L.hbo_noise_tile3.argtypes = [C.POINTER(World)] + [C.c_float] * 3 + [C.c_int] * 3 + [C.c_float] * 3 + [C.c_void_p]
         L.hbo_height.restype = C.c_int32
         L.hbo_height.argtypes = [C.c_float]
+        L.hbo_map_create.restype = C.c_void_p
+        L.hbo_map_create.argtypes = [C.POINTER(World)]
+        L.hbo_map_destroy.restype = None
+        L.hbo_map_destroy.argtypes = [C.c_void_p]
+        for name in ("hbo_map_load", "hbo_map_find"):
+            getattr(L, name).restype = C.c_int
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        L.hbo_map_unload.restype = None
+        L.hbo_map_unload.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        L.hbo_map_len.restype = C.c_int
+        L.hbo_map_len.argtypes = [C.c_void_p]
+        L.hbo_map_set_cube.restype = None
+        L.hbo_map_set_cube.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint16]
+        L.hbo_map_cubes.restype = C.c_void_p
+        L.hbo_map_cubes.argtypes = [C.c_void_p, C.c_int]
+        L.hbo_map_position.restype = None
+        L.hbo_map_position.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hbo_map_pending.restype = C.c_uint64
+        L.hbo_map_pending.argtypes = [C.c_void_p, C.c_int]
+        L.hbo_map_drain.restype = C.c_uint64
+        L.hbo_map_drain.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+        L.hbo_apply_updates.restype = None
+        L.hbo_apply_updates.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.hbo_default_palette.restype = None
         L.hbo_default_palette.argtypes = [C.POINTER(Palette)]
         L.hbo_mesh_init.restype = None
@@ -213,3 +237,85 @@ def region_pipeline(w: World, region, literal: bool, threads: int = 1, want_inst
                                       cap if inst is not None else 0, ids.ctypes.data if ids is not None else None, secs)
     return {"total": int(total), "counts": counts, "instances": inst[:total] if inst is not None else None,
             "ids": ids, "secs": tuple(secs)}
+
+
+# == hbo_chunk_cube (12 bytes)
+CHUNK_CUBE_DTYPE = np.dtype([("pos", "<u2"), ("pad0", "<u2"), ("material", "<u2"), ("pad", "<u2"), ("flags", "<u4")])
+
+
+class ChunkMapOracle:
+    """The reference's server ChunkMap + wire format + client copy, literal (oracle/hb_oracle.c, hbo_map_*).
+
+    server: load / unload / set_cube / drain (Chunk::sync_with_client)
+    client: `client[pos]` = the client's ChunkData.cubes, updated by apply(); remesh(pos) = generate_mesh over
+            the client's 27-shell."""
+
+    def __init__(self, w: World, pal: Palette = None):
+        self._h = lib().hbo_map_create(C.byref(w))
+        self.pal = pal or default_palette()
+        self.client = {}
+
+    def close(self):
+        if self._h:
+            lib().hbo_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def load(self, pos) -> int:
+        x, y, z = (int(v) for v in pos)
+        h = lib().hbo_map_load(self._h, x, y, z)
+        assert h >= 0
+        # client Chunk::create: all-None cubes (client/src/world/chunk.rs:105-119)
+        self.client.setdefault((x, y, z), np.zeros(CHUNK_VOLUME, dtype=CUBE_DTYPE))
+        return h
+
+    def unload(self, pos) -> None:
+        x, y, z = (int(v) for v in pos)
+        lib().hbo_map_unload(self._h, x, y, z)
+        self.client.pop((x, y, z), None)
+
+    def set_cube(self, wpos, material: int) -> None:
+        lib().hbo_map_set_cube(self._h, int(wpos[0]), int(wpos[1]), int(wpos[2]), int(material))
+
+    def loaded(self):
+        """[(handle, (x, y, z))] of the loaded chunks."""
+        out = []
+        p = (C.c_int32 * 3)()
+        for h in range(lib().hbo_map_len(self._h)):
+            if lib().hbo_map_cubes(self._h, h):
+                lib().hbo_map_position(self._h, h, p)
+                out.append((h, (p[0], p[1], p[2])))
+        return out
+
+    def cubes(self, pos) -> np.ndarray:
+        h = lib().hbo_map_find(self._h, int(pos[0]), int(pos[1]), int(pos[2]))
+        assert h >= 0
+        addr = lib().hbo_map_cubes(self._h, h)
+        return np.frombuffer((C.c_uint8 * (8 * CHUNK_VOLUME)).from_address(addr), dtype=CUBE_DTYPE).copy()
+
+    def drain(self) -> dict:
+        """sync_with_client for every chunk: {pos: CHUNK_CUBE_DTYPE entries (order and duplicates kept)}."""
+        out = {}
+        for h, pos in self.loaded():
+            n = lib().hbo_map_pending(self._h, h)
+            if n == 0:
+                continue
+            buf = np.zeros(n, dtype=CHUNK_CUBE_DTYPE)
+            got = lib().hbo_map_drain(self._h, h, buf.ctypes.data, n)
+            assert got == n, "oracle update log overflowed"
+            out[pos] = buf
+        return out
+
+    def apply(self, updates: dict) -> None:
+        """client apply_updates_from_server for every chunk that received a CubeUpdate."""
+        for pos, entries in updates.items():
+            if pos in self.client:
+                e = np.ascontiguousarray(entries)
+                lib().hbo_apply_updates(self.client[pos].ctypes.data, e.ctypes.data, e.shape[0])
+
+    def remesh(self, pos) -> np.ndarray:
+        x, y, z = pos
+        shell = [self.client.get((x + dx, y + dy, z + dz)) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)]
+        return mesh_cubes_literal(shell, pos, self.pal)
