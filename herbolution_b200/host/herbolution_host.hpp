@@ -8,6 +8,8 @@
 //   server/src/generator/mod.rs      ChunkGenerator::{new, request, dequeue}, GenerationParams::{new, generate, get_noise}
 //   server/src/chunk/mesh.rs         CubeMesh {position, data}, CubeMesh::get
 //   client/src/world/chunk.rs        ChunkData, create_chunk_shell, generate_mesh, ChunkMap::update
+//   server/src/chunk/map.rs          ChunkMap::{queue_load, queue_unload, set_cube, update} -> ServerChunkMap
+//   server/src/chunk/mod.rs          Chunk::sync_with_client -> ServerChunkMap::sync_with_client (CubeUpdate lists)
 //
 // Errors: the reference panics (unwrap) on internal failures; here every failing hb_* call throws
 // herbolution::Error carrying the hb_status and hb_last_error().  There is no CPU fallback.
@@ -289,6 +291,101 @@ class ChunkMap {
    private:
     std::shared_ptr<Context> ctx_;
     std::vector<ChunkPt> dirty_;
+};
+
+// lib::point::CubePt (lib/src/point.rs:7-12): world cube coordinates
+struct CubePt {
+    int32_t x = 0, y = 0, z = 0;
+};
+using ChunkCube = hb_chunk_cube;  // server/src/chunk/handle.rs:28-32
+// server/src/chunk/handle.rs:19-22, with the chunk it is addressed to (the reference routes it through that
+// chunk's own channel)
+struct CubeUpdate {
+    ChunkPt chunk;
+    std::vector<ChunkCube> overwrites;
+};
+
+// Server ChunkMap (server/src/chunk/map.rs) over a device-resident store, plus the two steps that follow it each
+// tick: Chunk::sync_with_client (server/src/chunk/mod.rs:35-67) and the client's remesh of every chunk that got a
+// CubeUpdate (client/src/world/chunk.rs:47-76).  queue_load / queue_unload / set_cube / update keep the
+// reference's names and meaning; update() flushes the queues like load_provided + unload_requested (map.rs:236-245).
+class ServerChunkMap {
+   public:
+    ServerChunkMap(std::shared_ptr<Context> ctx, size_t capacity) : ctx_(std::move(ctx)) {
+        check(hb_world_create(ctx_->raw(), capacity, &w_));
+    }
+    ~ServerChunkMap() { hb_world_destroy(w_); }
+    ServerChunkMap(const ServerChunkMap&) = delete;
+    ServerChunkMap& operator=(const ServerChunkMap&) = delete;
+
+    void queue_load(ChunkPt p) { load_.push_back(p); }      // map.rs:69-75
+    void queue_unload(ChunkPt p) { unload_.push_back(p); }  // map.rs:65-67
+    // map.rs:81-151; material 0 = None
+    void set_cube(CubePt p, uint16_t material) {
+        const int32_t xyz[3] = {p.x, p.y, p.z};
+        check(hb_world_set_cubes(w_, xyz, &material, 1));
+    }
+    void set_cubes(const std::vector<CubePt>& ps, const std::vector<uint16_t>& materials) {
+        if (ps.size() != materials.size()) throw Error(HB_ERR_INVALID, "one material per edit");
+        check(hb_world_set_cubes(w_, reinterpret_cast<const int32_t*>(ps.data()), materials.data(), ps.size()));
+    }
+    // map.rs:236-245: load_provided, then unload_requested
+    void update() {
+        check(hb_world_load(w_, reinterpret_cast<const hb_chunk_pt*>(load_.data()), load_.size()));
+        load_.clear();
+        check(hb_world_unload(w_, reinterpret_cast<const hb_chunk_pt*>(unload_.data()), unload_.size()));
+        unload_.clear();
+    }
+    size_t len() const { return hb_world_len(w_); }
+    // Chunk::sync_with_client for every chunk; want_wire = false skips building the CubeUpdate lists
+    std::vector<CubeUpdate> sync_with_client(bool want_wire = true) {
+        size_t n = 0;
+        uint64_t e = 0;
+        check(hb_world_sync(w_, &n, &e));
+        std::vector<CubeUpdate> out;
+        if (!want_wire || n == 0) return out;
+        std::vector<hb_chunk_pt> pts(n);
+        std::vector<uint64_t> off(n);
+        std::vector<uint32_t> cnt(n);
+        std::vector<ChunkCube> entries(e);
+        check(hb_world_fetch_updates(w_, pts.data(), n, off.data(), cnt.data(), entries.data(), e));
+        out.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            out[i].chunk = ChunkPt{pts[i].x, pts[i].y, pts[i].z};
+            out[i].overwrites.assign(entries.begin() + (ptrdiff_t)off[i], entries.begin() + (ptrdiff_t)(off[i] + cnt[i]));
+        }
+        return out;
+    }
+    // client ChunkMap::update: (position, instances) of every chunk that received a CubeUpdate since the last call
+    std::vector<std::pair<ChunkPt, std::vector<Instance3d>>> remesh() {
+        size_t n = 0;
+        uint64_t total = 0;
+        int rc = hb_world_remesh(w_, nullptr, 0, nullptr, 0, nullptr, nullptr, &n, &total);
+        if (rc != HB_OK && rc != HB_ERR_CAPACITY) check(rc);
+        std::vector<std::pair<ChunkPt, std::vector<Instance3d>>> out;
+        if (rc == HB_OK) return out;  // nothing to do
+        std::vector<hb_chunk_pt> pts(n);
+        std::vector<uint64_t> off(n);
+        std::vector<uint32_t> cnt(n);
+        std::vector<Instance3d> inst(total);
+        check(hb_world_remesh(w_, pts.data(), n, inst.data(), total, off.data(), cnt.data(), &n, &total));
+        out.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            out[i].first = ChunkPt{pts[i].x, pts[i].y, pts[i].z};
+            out[i].second.assign(inst.begin() + (ptrdiff_t)off[i], inst.begin() + (ptrdiff_t)(off[i] + cnt[i]));
+        }
+        return out;
+    }
+    std::vector<PaletteCube> read(ChunkPt p) const {
+        std::vector<PaletteCube> out((size_t)CHUNK_VOLUME);
+        check(hb_world_read_chunk(w_, hb_chunk_pt{p.x, p.y, p.z}, out.data()));
+        return out;
+    }
+
+   private:
+    std::shared_ptr<Context> ctx_;
+    hb_world* w_ = nullptr;
+    std::vector<ChunkPt> load_, unload_;
 };
 
 }  // namespace herbolution

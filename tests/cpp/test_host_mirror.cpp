@@ -146,6 +146,62 @@ int main(int argc, char** argv) {
         if (got.size() == nref) EXPECT(!std::memcmp(got.data(), ref.data(), nref * sizeof(Instance3d)), "flags mode: quads differ");
     }
 
+    // server ChunkMap on the device-resident store: load, dig/place in order, CubeUpdate wire, client remesh
+    {
+        ctx->set_world(seed);
+        ServerChunkMap server(ctx, 16);
+        hbo_map* om = hbo_map_create(&w);
+        const ChunkPt lp[4] = {{0, -1, 0}, {1, -1, 0}, {0, 0, 0}, {1, 0, 0}};
+        for (const ChunkPt& p : lp) {
+            server.queue_load(p);
+            hbo_map_load(om, p.x, p.y, p.z);
+        }
+        server.update();
+        EXPECT(server.len() == 4, "ServerChunkMap::len %zu", server.len());
+        const CubePt ed[5] = {{31, -3, 4}, {32, -3, 4}, {31, -3, 4}, {5, 40, 5}, {0, -1, 31}};
+        const uint16_t em[5] = {0, 0, 2, 3, 0};
+        for (int i = 0; i < 5; ++i) {
+            server.set_cube(ed[i], em[i]);
+            hbo_map_set_cube(om, ed[i].x, ed[i].y, ed[i].z, em[i]);
+        }
+        std::unordered_map<ChunkPt, std::vector<hbo_cube>, ChunkPtHash> client;
+        for (const CubeUpdate& u : server.sync_with_client()) {
+            std::vector<hbo_cube>& cc = client[u.chunk];
+            cc.assign((size_t)CHUNK_VOLUME, hbo_cube{0, 0, 0});
+            hbo_apply_updates(cc.data(), reinterpret_cast<const hbo_chunk_cube*>(u.overwrites.data()), u.overwrites.size());
+        }
+        EXPECT(client.size() == 4, "CubeUpdates for %zu chunks", client.size());
+        for (const ChunkPt& p : lp) {
+            const hbo_cube* ref = hbo_map_cubes(om, hbo_map_find(om, p.x, p.y, p.z));
+            const std::vector<PaletteCube> got = server.read(p);
+            EXPECT(!std::memcmp(got.data(), ref, sizeof(hbo_cube) * CHUNK_VOLUME), "server cubes (%d,%d,%d)", p.x, p.y, p.z);
+            EXPECT(client.count(p) && !std::memcmp(client[p].data(), ref, sizeof(hbo_cube) * CHUNK_VOLUME),
+                   "client copy after CubeUpdate (%d,%d,%d)", p.x, p.y, p.z);
+        }
+        auto remeshed = server.remesh();
+        EXPECT(remeshed.size() == 4, "remeshed %zu chunks", remeshed.size());
+        for (const auto& pr : remeshed) {
+            const ChunkPt c = pr.first;
+            const hbo_cube* oshell[27];
+            int k = 0;
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dz = -1; dz <= 1; ++dz, ++k) {
+                        const int h = hbo_map_find(om, c.x + dx, c.y + dy, c.z + dz);
+                        oshell[k] = h >= 0 ? hbo_map_cubes(om, h) : nullptr;
+                    }
+            const int32_t cpos[3] = {c.x, c.y, c.z};
+            const size_t nref = hbo_generate_mesh(oshell, cpos, &pal, nullptr, 0);
+            std::vector<hbo_instance> ref(nref);
+            hbo_generate_mesh(oshell, cpos, &pal, ref.data(), nref);
+            EXPECT(pr.second.size() == nref, "remesh (%d,%d,%d): %zu quads, oracle %zu", c.x, c.y, c.z, pr.second.size(), nref);
+            if (pr.second.size() == nref)
+                EXPECT(!std::memcmp(pr.second.data(), ref.data(), nref * sizeof(Instance3d)), "remesh (%d,%d,%d) differs", c.x, c.y, c.z);
+        }
+        EXPECT(server.remesh().empty(), "nothing left to remesh");
+        hbo_map_destroy(om);
+    }
+
     // get_noise and error behaviour
     auto tile = params->get_noise(3, -4);
     float ref_tile[CHUNK_AREA];
