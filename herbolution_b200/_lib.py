@@ -127,6 +127,12 @@ PROTOTYPES = {
     "hb_world_remesh_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]),
     "hb_world_read_chunk": (C.c_int, [C.c_void_p, ChunkPtC, C.c_void_p]),
+    # on-disk cube codec (server/src/chunk/codec.rs)
+    "hb_rle_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                C.POINTER(C.c_uint64)]),
+    "hb_rle_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hb_dev_rle_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -153,6 +153,33 @@ class Context:
                      C.byref(total)))
         return {"instances": inst, "offsets": offsets, "counts": counts}
 
+    # -- on-disk cube codec (server/src/chunk/codec.rs) ------------------------------------
+    def rle_encode(self, ids: np.ndarray) -> dict:
+        """encode_cubes for n chunks: {"bytes": u8[span], "offsets": u64[n], "sizes": u32[n]}."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint16).reshape(-1, CHUNK_VOLUME)
+        n = ids.shape[0]
+        offsets = np.zeros(n, dtype=np.uint64)
+        sizes = np.zeros(n, dtype=np.uint32)
+        total = C.c_uint64(0)
+        rc = self._lib.hb_rle_encode(self._h, ptr(ids), n, None, 0, ptr(offsets), ptr(sizes), C.byref(total))
+        if rc not in (_lib.HB_OK, _lib.HB_ERR_CAPACITY):
+            check(rc)
+        out = np.zeros(total.value, dtype=np.uint8)
+        if total.value:
+            check(self._lib.hb_rle_encode(self._h, ptr(ids), n, ptr(out), total.value, ptr(offsets), ptr(sizes),
+                                          C.byref(total)))
+        return {"bytes": out, "offsets": offsets, "sizes": sizes}
+
+    def rle_decode(self, data: np.ndarray, offsets, sizes) -> np.ndarray:
+        """CubeGrid::decode record loop for n streams -> u16[n][32768] raw ids."""
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64).reshape(-1)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint32).reshape(-1)
+        n = offsets.shape[0]
+        out = np.zeros((n, CHUNK_VOLUME), dtype=np.uint16)
+        check(self._lib.hb_rle_decode(self._h, ptr(data), data.shape[0], ptr(offsets), ptr(sizes), n, ptr(out)))
+        return out
+
     # -- fused region ----------------------------------------------------------------------
     def generate_mesh_region(self, region: Region, want_ids: bool = False,
                              sink: Optional[Callable[..., None]] = None, ix_begin: int = 0,

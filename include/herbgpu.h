@@ -284,6 +284,32 @@ HB_API int hb_world_remesh_dev(hb_world *world, hb_chunk_pt *out_pts, size_t pts
 /* Copy one loaded chunk's PaletteCube array (32768 x 8 B) to the host; HB_ERR_INVALID if it is not loaded. */
 HB_API int hb_world_read_chunk(hb_world *world, hb_chunk_pt pt, hb_palette_cube *out_cubes);
 
+/* ------------------------------------------------------------------------------------------------
+ * On-disk cube codec (server/src/chunk/codec.rs): the run-length records of
+ * encode_cubes (codec.rs:73-101) and the record loop of CubeGrid::decode (codec.rs:52-66), bit for bit.
+ * A record is [u8 count][u16 LE id]; a run is cut every 255 voxels; the encoder starts in state (None, 0), so a
+ * chunk whose first voxel has a material begins with an empty record.  `ids` are the raw in-memory ids used
+ * everywhere in this library (0 = None, k = palette index k-1).  The reference writes PaletteMaterialId::to_u16
+ * (the 0-based index) and 0 for None, and reads back NonZeroU16::new(v + 1): None and the first material share wire
+ * value 0 and come back as the first material -- the codec is lossy by construction (and unused: no writer is ever
+ * called, server/src/chunk/provider.rs:48-58); it is reproduced here as it is, not repaired.  The palette half of
+ * CubeGrid::encode is not produced (decode does not skip it either).
+ * ---------------------------------------------------------------------------------------------- */
+/* ids: n x 32768.  Chunk i's stream is out[out_offsets[i] .. + out_sizes[i]) (bytes; starts are multiples of 12,
+ * gaps zero-filled); *out_total = bytes spanned.  Two-call pattern: HB_ERR_CAPACITY reports offsets, sizes, total. */
+HB_API int hb_rle_encode(hb_ctx *ctx, const uint16_t *ids, size_t n, uint8_t *out, uint64_t out_capacity,
+                  uint64_t *out_offsets, uint32_t *out_sizes, uint64_t *out_total);
+/* Stream i = bytes[offsets[i] .. + sizes[i]) -> out_ids[i][32768].  A partial trailing record is ignored, voxels
+ * the stream does not reach are None, wire 65535 wraps to None (release-build arithmetic); a stream that decodes to
+ * more than 32768 voxels is HB_ERR_INVALID (the reference panics). */
+HB_API int hb_rle_decode(hb_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, const uint64_t *offsets,
+                  const uint32_t *sizes, size_t n, uint16_t *out_ids);
+/* Device-pointer form of the encoder: counts -> offsets (in records; x3 for bytes) -> records if d_out.
+ * d_scan_workspace as for hb_dev_mesh; d_total[0] = span in records, d_total[2] & 1 = capacity exceeded. */
+HB_API int hb_dev_rle_encode(hb_ctx *ctx, void *stream, const uint16_t *d_ids, size_t n, void *d_scan_workspace,
+                      uint8_t *d_out, uint64_t capacity_records, uint64_t *d_offsets, uint32_t *d_counts,
+                      uint64_t *d_total);
+
 #ifdef __cplusplus
 }
 #endif

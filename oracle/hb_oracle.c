@@ -1031,3 +1031,61 @@ void hbo_apply_updates(hbo_cube *client_cubes, const hbo_chunk_cube *entries, ui
         client_cubes[lin(x, y, z)] = entries[i].cube;
     }
 }
+
+/* ------------------------------------------------------------------------- */
+/* On-disk cube codec: server/src/chunk/codec.rs              */
+/* ------------------------------------------------------------------------- */
+
+/* PaletteMaterialId::to_u16 (material.rs:224-226) is the 0-based palette index, and None is written as 0
+ * (codec.rs:85-90,96-101): air and the first material share the wire value 0.  `raw` is the in-memory
+ * NonZeroU16 niche value (0 = None, k = index k-1). */
+static inline uint16_t wire_of_raw(uint16_t raw) { return raw ? (uint16_t)(raw - 1) : 0; }
+
+/* encode_cubes (codec.rs:73-101): [u8 count][u16 LE id] records; a record is closed when the material changes
+ * or the count reaches 255; the state starts as (None, 0), so a first voxel that is not None closes an empty
+ * record first.  Returns the number of bytes the stream has; writes at most cap. */
+size_t hbo_rle_encode(const uint16_t *raw_ids, size_t n, uint8_t *out, size_t cap) {
+    size_t w = 0;
+    uint8_t count = 0;
+    uint16_t current = 0; /* None */
+#define HBO_PUSH_REC()                                         \
+    do {                                                       \
+        const uint16_t v = wire_of_raw(current);               \
+        if (w + 0 < cap) out[w + 0] = count;                   \
+        if (w + 1 < cap) out[w + 1] = (uint8_t)(v & 0xFF);     \
+        if (w + 2 < cap) out[w + 2] = (uint8_t)(v >> 8);       \
+        w += 3;                                                \
+    } while (0)
+    for (size_t i = 0; i < n; ++i) {
+        const uint16_t m = raw_ids[i];
+        if (current != m || count == 255) {
+            HBO_PUSH_REC();
+            current = m;
+            count = 1;
+        } else {
+            count++;
+        }
+    }
+    HBO_PUSH_REC();
+#undef HBO_PUSH_REC
+    return w;
+}
+
+/* CubeGrid::decode record loop (codec.rs:52-66): whole 3-byte records only (array_chunks drops a tail);
+ * PaletteMaterialId::new(v) = NonZeroU16::new(v + 1) (material.rs:219-222), i.e. wire 0 comes back as the first
+ * material, never as None; v = 65535 wraps to None in a release build.  Voxels the stream does not reach stay
+ * None.  Returns 0, or -1 where the reference indexes past the chunk and panics. */
+int hbo_rle_decode(const uint8_t *bytes, size_t nbytes, uint16_t *raw_ids) {
+    memset(raw_ids, 0, sizeof(uint16_t) * HBO_CHUNK_VOLUME);
+    size_t i = 0;
+    for (size_t r = 0; r + 3 <= nbytes; r += 3) {
+        const uint8_t count = bytes[r];
+        const uint16_t v = (uint16_t)(bytes[r + 1] | (bytes[r + 2] << 8));
+        const uint16_t raw = (uint16_t)(v + 1u);
+        for (uint8_t k = 0; k < count; ++k) {
+            if (i >= HBO_CHUNK_VOLUME) return -1;
+            raw_ids[i++] = raw;
+        }
+    }
+    return 0;
+}

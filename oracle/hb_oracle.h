@@ -166,6 +166,11 @@ uint64_t hbo_map_drain(hbo_map *m, int handle, hbo_chunk_cube *out, uint64_t cap
 /* client apply_updates_from_server (client/src/world/chunk.rs:132-149) */
 void hbo_apply_updates(hbo_cube *client_cubes, const hbo_chunk_cube *entries, uint64_t n);
 
+/* ---- on-disk cube codec (server/src/chunk/codec.rs) ----
+ * raw ids: 0 = None, k = palette index k-1 (the NonZeroU16 niche the reference stores). */
+size_t hbo_rle_encode(const uint16_t *raw_ids, size_t n, uint8_t *out, size_t cap); /* codec.rs:73-101 */
+int hbo_rle_decode(const uint8_t *bytes, size_t nbytes, uint16_t *raw_ids);        /* codec.rs:52-66 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,10 @@ def lib() -> C.CDLL:
         L.hbo_map_drain.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
         L.hbo_apply_updates.restype = None
         L.hbo_apply_updates.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.hbo_rle_encode.restype = C.c_size_t
+        L.hbo_rle_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.hbo_rle_decode.restype = C.c_int
+        L.hbo_rle_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.hbo_default_palette.restype = None
         L.hbo_default_palette.argtypes = [C.POINTER(Palette)]
         L.hbo_mesh_init.restype = None
@@ -319,3 +323,20 @@ class ChunkMapOracle:
         x, y, z = pos
         shell = [self.client.get((x + dx, y + dy, z + dz)) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)]
         return mesh_cubes_literal(shell, pos, self.pal)
+
+
+def rle_encode(ids: np.ndarray) -> np.ndarray:
+    """encode_cubes (server/src/chunk/codec.rs:73-101) of one chunk's raw ids."""
+    ids = np.ascontiguousarray(ids, dtype=np.uint16).reshape(-1)
+    n = lib().hbo_rle_encode(ids.ctypes.data, ids.shape[0], None, 0)
+    out = np.zeros(n, dtype=np.uint8)
+    assert lib().hbo_rle_encode(ids.ctypes.data, ids.shape[0], out.ctypes.data, n) == n
+    return out
+
+
+def rle_decode(data: np.ndarray):
+    """CubeGrid::decode record loop -> (status, raw ids)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+    out = np.zeros(CHUNK_VOLUME, dtype=np.uint16)
+    rc = lib().hbo_rle_decode(data.ctypes.data if data.shape[0] else None, data.shape[0], out.ctypes.data)
+    return rc, out
