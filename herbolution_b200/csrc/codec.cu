@@ -14,6 +14,7 @@ namespace {
 using u64 = unsigned long long;
 constexpr int kCT = 256;
 constexpr int kSeg = HB_CHUNK_VOLUME / kCT;  // 128 ids per thread
+constexpr int kStageBytes = 16384;
 
 // PaletteMaterialId::to_u16 (material.rs:224-226) / None -> 0 (codec.rs:85-90)
 __device__ __forceinline__ uint32_t wire_of_raw(uint32_t raw) { return raw ? raw - 1u : 0u; }
@@ -31,6 +32,9 @@ __global__ void __launch_bounds__(kCT) k_rle_encode(const uint16_t* __restrict__
                                                     u64 capacity_records, u64* __restrict__ total) {
     __shared__ int s_wmin[kCT / 32];
     __shared__ uint32_t s_wsum[kCT / 32];
+    // EMIT: a chunk's records are assembled here and leave as coalesced 32-bit stores (terrain chunks have about
+    // 1 100 records = 3.4 KB); a chunk with more than kStageBytes of records falls back to direct byte stores
+    __shared__ uint32_t s_stage[EMIT ? kStageBytes / 4 : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         const uint16_t* src = ids + chunk * HB_CHUNK_VOLUME + tid * kSeg;
@@ -118,7 +122,12 @@ __global__ void __launch_bounds__(kCT) k_rle_encode(const uint16_t* __restrict__
             if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
             continue;
         }
-        uint8_t* dst = out + (off + before) * 3ULL;
+        const bool staged = all * 3u <= (uint32_t)kStageBytes;  // block-uniform
+        if (staged) {
+            if (tid == 0 && ((all * 3u) & 3u)) s_stage[(all * 3u) >> 2] = 0u;  // tail of the last word: the zero-filled gap
+            __syncthreads();
+        }
+        uint8_t* dst = staged ? reinterpret_cast<uint8_t*>(s_stage) + before * 3u : out + (off + before) * 3ULL;
         if (tid == 0 && id0 != 0) { put_record(dst, 0u, 0u); dst += 3; }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -140,6 +149,13 @@ __global__ void __launch_bounds__(kCT) k_rle_encode(const uint16_t* __restrict__
                 put_record(dst, (uint32_t)len, wire);
                 dst += 3;
             }
+        }
+        if (staged) {
+            __syncthreads();
+            // stream starts are multiples of 4 records = 12 bytes, so the words are aligned in the output too
+            uint32_t* outw = reinterpret_cast<uint32_t*>(out + off * 3ULL);
+            const uint32_t words = (all * 3u + 3u) >> 2;
+            for (uint32_t i = tid; i < words; i += kCT) outw[i] = s_stage[i];
         }
     }
 }

@@ -88,6 +88,21 @@ def main():
                       "chunks_per_s": n / (t_all * 1e-3), "algorithmic_bytes": algo_bytes,
                       "algorithmic_GBs": algo_bytes / (t_all * 1e-3) / 1e9,
                       "pack_read_GBs_if_all_pack": n * 65536 / (t_cnt * 1e-3) / 1e9}
+    # codec: run-length encode the same ids (server/src/chunk/codec.rs)
+    d_roff = torch.empty(n * 8, dtype=torch.uint8, device=dev)
+    d_rcnt = torch.empty(n * 4, dtype=torch.uint8, device=dev)
+    check(lib.hb_dev_rle_encode(ctx._h, s, p(d_ids), n, p(ws), None, 0, p(d_roff), p(d_rcnt), p(d_tot)))
+    st.synchronize()
+    rspan = int(d_tot[0])
+    d_rle = torch.zeros(max(rspan, 4) * 3, dtype=torch.uint8, device=dev)
+    rle_count = lambda: check(lib.hb_dev_rle_encode(ctx._h, s, p(d_ids), n, p(ws), None, 0, p(d_roff), p(d_rcnt), p(d_tot)))  # noqa: E731
+    rle_all = lambda: check(lib.hb_dev_rle_encode(ctx._h, s, p(d_ids), n, p(ws), p(d_rle), rspan, p(d_roff), p(d_rcnt), p(d_tot)))  # noqa: E731
+    t_rc, t_ra = timed(rle_count), timed(rle_all)
+    st.synchronize()
+    assert int(d_tot[2]) == 0
+    out["codec"] = {"chunks": n, "records": rspan, "encoded_MB": rspan * 3 / 1e6, "ratio": n * 65536 / (rspan * 3),
+                    "ms_count_scan": t_rc, "ms_total": t_ra, "chunks_per_s": n / (t_ra * 1e-3),
+                    "read_GBs": 2 * n * 65536 / (t_ra * 1e-3) / 1e9}
     print(json.dumps(out))
 
 
