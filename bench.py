@@ -73,7 +73,12 @@ def run_cpu(sample, threads: int, reps: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.
+
+    nvidia-smi is started before the warm-up (it needs ~100 ms to come up) and polls every 20 ms; every line is
+    time-stamped on arrival.  stop() reports the samples that arrived between begin() and end() -- the timed
+    region -- and, if that region was too short to catch one, the samples up to stop(), which the caller places
+    after the per-stage timing loops that run the same kernels back to back ("window" says which)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -82,11 +87,18 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.t = None
+        self.t_begin = self.t_end = None
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -96,20 +108,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_stop = time.perf_counter()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        t1 = self.t_end if self.t_end is not None else t_stop
+        # a line printed at time t describes the GPU a few ms earlier: accept arrivals up to 25 ms after end()
+        timed = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.025]
+        window = "timed region"
+        if not timed:
+            timed = [ln for ts, ln in self.lines if t0 <= ts <= t_stop]
+            window = "timed region + per-stage timing loops (timed region shorter than one sample period)"
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in timed:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -121,7 +141,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -220,21 +241,22 @@ def main():
     ALL = hb.STAGE_ALL_MESH
     launches_per_step = plan.launches(ALL)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(warmup, 3)):
         plan.enqueue(ALL, stream)
     res = plan.result(stream)
     n_chunks, quads, span = res["n_chunks"], res["quads"], res["span"]
 
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(tstream)
     for _ in range(steps):
         plan.enqueue(ALL, stream)
     ev1.record(tstream)
     barrier()
-    clocks = sampler.stop()
+    sampler.end()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     total_chunks = sum_over_ranks(float(n_chunks))
     value = total_chunks * steps / (ms_total * 1e-3)
@@ -249,6 +271,7 @@ def main():
             plan.enqueue(st, stream)
             evs[r][i + 1].record(tstream)
     torch.cuda.synchronize()
+    clocks = sampler.stop()
     stage_ms = {nm: statistics.mean(evs[r][i].elapsed_time(evs[r][i + 1]) for r in range(reps))
                 for i, (nm, _) in enumerate(stage_names)}
     peak, peak_src = measured_peaks()

@@ -28,6 +28,7 @@ HB_ERR_NOMEM = -5
 
 STAGE_HEIGHTS, STAGE_COUNT, STAGE_SCAN, STAGE_EMIT, STAGE_FILL = 1, 2, 4, 8, 16
 STAGE_ALL_MESH = 15
+NOISE_FBM, NOISE_RIDGE, NOISE_TURBULENCE, NOISE_GRADIENT = 0, 1, 2, 3
 
 # == hb_chunk_pt / lib::point::ChunkPt
 CHUNK_PT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4")])
@@ -81,6 +82,7 @@ REGION_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, 
 PROTOTYPES = {
     "hb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "hb_destroy": (None, [C.c_void_p]),
+    "hb_set_noise_kind": (C.c_int, [C.c_void_p, C.c_int32]),
     "hb_last_error": (C.c_char_p, []),
     "hb_version": (C.c_char_p, []),
     "hb_set_world": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_float, C.c_float]),

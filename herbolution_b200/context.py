@@ -84,6 +84,10 @@ class Context:
         check(self._lib.hb_set_world(self._h, seed, freq, octaves, lacunarity, gain))
         self.seed = seed
 
+    def set_noise_kind(self, kind: int) -> None:
+        """_lib.NOISE_FBM (the game's, default) / NOISE_RIDGE / NOISE_TURBULENCE / NOISE_GRADIENT."""
+        check(self._lib.hb_set_noise_kind(self._h, int(kind)))
+
     def set_materials(self, colors: list) -> None:
         """colors[m] = list of rgba tuples of material id m+1 (server/src/chunk/material.rs:27-61)."""
         n = len(colors)

@@ -309,7 +309,15 @@ int hb_set_world(hb_ctx* c, int64_t seed, float freq, int32_t octaves, float lac
     if (octaves < 1 || octaves > 255) return fail(HB_ERR_INVALID, "octaves must be in 1..255 (u8 in the reference)");
     std::lock_guard<std::mutex> lk(c->mu);
     c->seed = seed;
-    c->world = WorldDev{(int32_t)seed, freq, octaves, lacunarity, gain};
+    c->world = WorldDev{(int32_t)seed, freq, octaves, lacunarity, gain, c->world.kind};
+    return HB_OK;
+}
+
+int hb_set_noise_kind(hb_ctx* c, int32_t kind) {
+    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    if (kind < HB_NOISE_FBM || kind > HB_NOISE_GRADIENT) return fail(HB_ERR_INVALID, "unknown noise kind %d", kind);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->world.kind = kind;
     return HB_OK;
 }
 

@@ -16,6 +16,7 @@ struct WorldDev {
     int32_t octaves;
     float lacunarity;
     float gain;
+    int32_t kind;     // HB_NOISE_*: which of the crate's Sample32 implementations the tile walk calls
 };
 
 // Constant tables built on the host with the reference's formulas (api.cu) and passed by value.

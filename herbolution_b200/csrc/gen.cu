@@ -41,7 +41,7 @@ struct ColRegion {
 
 // One CTA = one chunk column = 32x32 samples.  Sample i: x = i & 31, z = i >> 5 (the crate's tile
 // order x + z*32, noise/f32.rs:95-113).  Heights are written in voxel-column order x*32 + z.
-template <class Cols>
+template <class Cols, int KIND>
 __global__ void __launch_bounds__(kThreads) k_heights(WorldDev w, Cols cols, int32_t* __restrict__ heights,
                                                        float* __restrict__ noise) {
     __shared__ NoiseTables s_tab;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreads) k_heights(WorldDev w, Cols cols, int
         const int i0 = threadIdx.x + k * kThreads, i1 = i0 + kThreads;
         const float2 x = pk(__fadd_rn(start_x, __int2float_rn(i0 & 31)), __fadd_rn(start_x, __int2float_rn(i1 & 31)));
         const float2 z = pk(__fadd_rn(start_z, __int2float_rn(i0 >> 5)), __fadd_rn(start_z, __int2float_rn(i1 >> 5)));
-        const float2 r = fbm2_pair(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
+        const float2 r = noise2_pair<KIND>(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
         v[k] = r.x;
         v[k + 1] = r.y;
     }
@@ -225,7 +225,17 @@ __global__ void __launch_bounds__(kThreads) k_noise3d(WorldDev w, float sx, floa
         const float x = __fadd_rn(sx, __int2float_rn(ix));
         const float y = __fadd_rn(sy, __int2float_rn(iy));
         const float z = __fadd_rn(sz, __int2float_rn(iz));
-        out[i] = fbm3(__fmul_rn(x, fx), __fmul_rn(y, fy), __fmul_rn(z, fz), w);
+        out[i] = noise3(__fmul_rn(x, fx), __fmul_rn(y, fy), __fmul_rn(z, fz), w);
+    }
+}
+
+template <class Cols>
+void launch_heights_kind(cudaStream_t s, const WorldDev& w, Cols cols, unsigned grid, int32_t* d_heights, float* d_noise) {
+    switch (w.kind) {
+        case HB_NOISE_RIDGE: k_heights<Cols, HB_NOISE_RIDGE><<<grid, kThreads, 0, s>>>(w, cols, d_heights, d_noise); break;
+        case HB_NOISE_TURBULENCE: k_heights<Cols, HB_NOISE_TURBULENCE><<<grid, kThreads, 0, s>>>(w, cols, d_heights, d_noise); break;
+        case HB_NOISE_GRADIENT: k_heights<Cols, HB_NOISE_GRADIENT><<<grid, kThreads, 0, s>>>(w, cols, d_heights, d_noise); break;
+        default: k_heights<Cols, HB_NOISE_FBM><<<grid, kThreads, 0, s>>>(w, cols, d_heights, d_noise); break;
     }
 }
 
@@ -234,14 +244,14 @@ __global__ void __launch_bounds__(kThreads) k_noise3d(WorldDev w, float sx, floa
 cudaError_t launch_heights(cudaStream_t s, const WorldDev& w, const int32_t* d_cols_xz, size_t ncol,
                            int32_t* d_heights, float* d_noise) {
     if (ncol == 0) return cudaSuccess;
-    k_heights<ColList><<<(unsigned)ncol, kThreads, 0, s>>>(w, ColList{d_cols_xz}, d_heights, d_noise);
+    launch_heights_kind(s, w, ColList{d_cols_xz}, (unsigned)ncol, d_heights, d_noise);
     return cudaGetLastError();
 }
 
 cudaError_t launch_heights_region(cudaStream_t s, const WorldDev& w, const RegionDev& r, int32_t* d_heights,
                                   size_t col_begin, size_t col_end) {
     if (col_end <= col_begin) return cudaSuccess;
-    k_heights<ColRegion><<<(unsigned)(col_end - col_begin), kThreads, 0, s>>>(w, ColRegion{r, (int)col_begin}, d_heights, nullptr);
+    launch_heights_kind(s, w, ColRegion{r, (int)col_begin}, (unsigned)(col_end - col_begin), d_heights, nullptr);
     return cudaGetLastError();
 }
 

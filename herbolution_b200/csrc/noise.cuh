@@ -153,6 +153,36 @@ __device__ __forceinline__ float2 fbm2_pair(const NoiseTables& T, float2 x, floa
     return result;
 }
 
+__device__ __forceinline__ float2 abs2(float2 a) { return pk(fabsf(a.x), fabsf(a.y)); }  // andnot(-0.0, a), simd/ops/f32.rs:307-310
+
+// The crate's other Sample32 implementations over the same simplex (noise/{ridge,turbulence,gradient}.rs):
+//   ridge_2d      (functions/ridge_32.rs:18-31):      r = 1 - |s0|;  r = r + neg_mul_add(|s|, amp, 1)   (fused on AVX2)
+//   turbulence_2d (functions/turbulence_32.rs:18-32): r = |s0|;      r = r + |s * amp|
+//   gradient      (noise/gradient.rs:77-79):          r = s0
+// KIND is a template parameter so the FBM kernel's code is untouched by the variants.
+template <int KIND>
+__device__ __forceinline__ float2 noise2_pair(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
+    if (KIND == HB_NOISE_FBM) return fbm2_pair(T, x, y, w);
+    const float2 s0 = simplex2_pair(T, x, y);
+    if (KIND == HB_NOISE_GRADIENT) return s0;
+    float2 result = KIND == HB_NOISE_RIDGE ? sadd2(bc(1.0f), neg2(abs2(s0))) : abs2(s0);
+    float amp = 1.0f;
+    const float2 lac = bc(w.lacunarity);
+    for (int o = 1; o < w.octaves; ++o) {
+        x = smul2(x, lac);
+        y = smul2(y, lac);
+        amp = __fmul_rn(amp, w.gain);
+        const float2 sv = simplex2_pair(T, x, y);
+        if (KIND == HB_NOISE_RIDGE) {
+            const float2 a = abs2(sv);
+            result = sadd2(result, pk(__fmaf_rn(-a.x, amp, 1.0f), __fmaf_rn(-a.y, amp, 1.0f)));
+        } else {
+            result = sadd2(result, abs2(smul2(sv, bc(amp))));
+        }
+    }
+    return result;
+}
+
 // `(noise * 32.0) as i32` (server/src/generator/mod.rs:79): truncating, saturating, NaN -> 0,
 // which is exactly cvt.rzi.s32.f32.
 __device__ __forceinline__ int height_from_noise(float v) { return __float2int_rz(__fmul_rn(v, 32.0f)); }
@@ -229,6 +259,26 @@ __device__ __forceinline__ float fbm3(float x, float y, float z, const WorldDev&
         z = __fmul_rn(z, w.lacunarity);
         amp = __fmul_rn(amp, w.gain);
         result = __fadd_rn(__fmul_rn(simplex3(x, y, z, w.seed_lo), amp), result);
+    }
+    return result;
+}
+
+// Sample32::sample_3d of w.kind: fbm_32.rs:33-47, ridge_32.rs:33-47, turbulence_32.rs:34-48, gradient.rs:82-84
+__device__ __forceinline__ float noise3(float x, float y, float z, const WorldDev& w) {
+    if (w.kind == HB_NOISE_FBM) return fbm3(x, y, z, w);
+    const float s0 = simplex3(x, y, z, w.seed_lo);
+    if (w.kind == HB_NOISE_GRADIENT) return s0;
+    const bool ridge = w.kind == HB_NOISE_RIDGE;
+    float result = ridge ? __fsub_rn(1.0f, fabsf(s0)) : fabsf(s0);
+    float amp = 1.0f;
+    for (int o = 1; o < w.octaves; ++o) {
+        x = __fmul_rn(x, w.lacunarity);
+        y = __fmul_rn(y, w.lacunarity);
+        z = __fmul_rn(z, w.lacunarity);
+        amp = __fmul_rn(amp, w.gain);
+        const float sv = simplex3(x, y, z, w.seed_lo);
+        if (ridge) result = __fadd_rn(result, __fmaf_rn(-fabsf(sv), amp, 1.0f));
+        else result = __fadd_rn(result, fabsf(__fmul_rn(sv, amp)));
     }
     return result;
 }

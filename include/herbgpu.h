@@ -91,6 +91,15 @@ HB_API const char *hb_version(void);
  * (server/src/generator/mod.rs:103-108): freq 0.001, 6 octaves, lacunarity 2.0, gain 0.6.
  * seed is GenerationParams::seed (i64). */
 HB_API int hb_set_world(hb_ctx *ctx, int64_t seed, float freq, int32_t octaves, float lacunarity, float gain);
+/* Which of the crate's noise types the tile walks sample (crates/simd-noise/src/noise/{fbm,ridge,turbulence,
+ * gradient}.rs over functions/{fbm,ridge,turbulence}_32.rs); applies to hb_noise_tiles, hb_noise_fbm3d and to the
+ * heights every generation path derives.  The game uses HB_NOISE_FBM (server/src/generator/mod.rs:103), the default.
+ * Gradient = one simplex evaluation (octaves, lacunarity and gain unused). */
+#define HB_NOISE_FBM 0
+#define HB_NOISE_RIDGE 1
+#define HB_NOISE_TURBULENCE 2
+#define HB_NOISE_GRADIENT 3
+HB_API int hb_set_noise_kind(hb_ctx *ctx, int32_t kind);
 
 /* Palette colours, Material::texture (server/src/chunk/material.rs:27-71): material id m (1-based)
  * has n_colors[m-1] colours, rgba[(m-1)*HB_MAX_COLORS + c][4].  Default = stone, dirt, grass. */

@@ -146,6 +146,45 @@ float hbo_fbm2(float x, float y, const hbo_world *w) {
     return result;
 }
 
+/* functions/ridge_32.rs:18-31 */
+float hbo_ridge2(float x, float y, const hbo_world *w) {
+    float lac = w->lacunarity, gain = w->gain;
+    float result = 1.0f - fabsf(hbo_simplex2(x, y, w->seed, w->fused));
+    float amp = 1.0f;
+    for (int o = 1; o < (w->octaves & 0xff); ++o) {
+        x = x * lac;
+        y = y * lac;
+        amp = amp * gain;
+        result = result + neg_mul_add(fabsf(hbo_simplex2(x, y, w->seed, w->fused)), amp, 1.0f, w->fused);
+    }
+    return result;
+}
+
+/* functions/turbulence_32.rs:18-32 */
+float hbo_turbulence2(float x, float y, const hbo_world *w) {
+    float lac = w->lacunarity, gain = w->gain;
+    float result = fabsf(hbo_simplex2(x, y, w->seed, w->fused));
+    float amp = 1.0f;
+    for (int o = 1; o < (w->octaves & 0xff); ++o) {
+        x = x * lac;
+        y = y * lac;
+        amp = amp * gain;
+        float sv = hbo_simplex2(x, y, w->seed, w->fused) * amp;
+        result = result + fabsf(sv);
+    }
+    return result;
+}
+
+/* Sample32::sample_2d: noise/fbm.rs, ridge.rs:100-102, turbulence.rs:100-102, gradient.rs:77-79 */
+float hbo_sample2(float x, float y, const hbo_world *w) {
+    switch (w->kind) {
+        case HBO_NOISE_RIDGE: return hbo_ridge2(x, y, w);
+        case HBO_NOISE_TURBULENCE: return hbo_turbulence2(x, y, w);
+        case HBO_NOISE_GRADIENT: return hbo_simplex2(x, y, w->seed, w->fused);
+        default: return hbo_fbm2(x, y, w);
+    }
+}
+
 /* noise/f32.rs:69-129 get_2d_noise_helper_f32 with the transform from
  * server/src/generator/mod.rs:74,98-101: start = (cx*32 as f32, cz*32 as f32).
  * Lane coordinates are start + i (then += WIDTH): integers, exact in f32 for |coord| < 2^24,
@@ -159,7 +198,7 @@ void hbo_noise_tile2(const hbo_world *w, int32_t cx, int32_t cz, float out[HBO_C
     for (int row = 0; row < HBO_CHUNK_LENGTH; ++row) {
         float x = start_x;
         for (int col = 0; col < HBO_CHUNK_LENGTH; ++col) {
-            out[i++] = hbo_fbm2(x * freq_x, y * freq_y, w);
+            out[i++] = hbo_sample2(x * freq_x, y * freq_y, w);
             x = x + 1.0f;
         }
         y = y + 1.0f;
@@ -284,6 +323,31 @@ float hbo_fbm3(float x, float y, float z, const hbo_world *w) {
     return result;
 }
 
+/* functions/ridge_32.rs:33-47, turbulence_32.rs:34-48; Sample32::sample_3d */
+float hbo_sample3(float x, float y, float z, const hbo_world *w) {
+    if (w->kind == HBO_NOISE_GRADIENT) return hbo_simplex3(x, y, z, w->seed);
+    if (w->kind != HBO_NOISE_RIDGE && w->kind != HBO_NOISE_TURBULENCE) return hbo_fbm3(x, y, z, w);
+    const int ridge = w->kind == HBO_NOISE_RIDGE;
+    float lac = w->lacunarity, gain = w->gain;
+    float s0 = fabsf(hbo_simplex3(x, y, z, w->seed));
+    float result = ridge ? 1.0f - s0 : s0;
+    float amp = 1.0f;
+    for (int o = 1; o < (w->octaves & 0xff); ++o) {
+        x = x * lac;
+        y = y * lac;
+        z = z * lac;
+        amp = amp * gain;
+        float sv = hbo_simplex3(x, y, z, w->seed);
+        if (ridge) {
+            result = result + neg_mul_add(fabsf(sv), amp, 1.0f, w->fused);
+        } else {
+            float p = sv * amp;
+            result = result + fabsf(p);
+        }
+    }
+    return result;
+}
+
 /* noise/f32.rs:131-198 */
 void hbo_noise_tile3(const hbo_world *w, float sx, float sy, float sz, int nx, int ny, int nz,
                      float fx, float fy, float fz, float *out) {
@@ -294,7 +358,7 @@ void hbo_noise_tile3(const hbo_world *w, float sx, float sy, float sz, int nx, i
         for (int iy = 0; iy < ny; ++iy) {
             float x = sx;
             for (int ix = 0; ix < nx; ++ix) {
-                out[i++] = hbo_fbm3(x * fx, y * fy, z * fz, w);
+                out[i++] = hbo_sample3(x * fx, y * fy, z * fz, w);
                 x = x + 1.0f;
             }
             y = y + 1.0f;

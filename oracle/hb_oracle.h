@@ -49,7 +49,13 @@ typedef struct hbo_world {
     float gain;        /* 0.6 */
     int32_t fused;     /* 1: AVX2/NEON column (true FMA at neg_mul_add),
                           0: SSE/Scalar column (unfused)  simd/ops/f32.rs:141-162 */
+    int32_t kind;      /* HBO_NOISE_*: which Sample32 impl the tile walk calls (noise/{fbm,ridge,turbulence,
+                          gradient}.rs); the game uses FBM (generator/mod.rs:103) */
 } hbo_world;
+#define HBO_NOISE_FBM 0
+#define HBO_NOISE_RIDGE 1
+#define HBO_NOISE_TURBULENCE 2
+#define HBO_NOISE_GRADIENT 3
 
 /* == Cube<Option<PaletteMaterialId>>, server/src/chunk/cube.rs:5-10 (repr(C)) */
 typedef struct hbo_cube {
@@ -90,6 +96,10 @@ typedef struct hbo_cube_mesh {
 /* ---- noise (crates/simd-noise) ---- */
 float hbo_simplex2(float x, float y, int64_t seed, int fused);
 float hbo_fbm2(float x, float y, const hbo_world *w);
+float hbo_ridge2(float x, float y, const hbo_world *w);        /* functions/ridge_32.rs:18-31 */
+float hbo_turbulence2(float x, float y, const hbo_world *w);   /* functions/turbulence_32.rs:18-32 */
+float hbo_sample2(float x, float y, const hbo_world *w);       /* Sample32::sample_2d of w->kind */
+float hbo_sample3(float x, float y, float z, const hbo_world *w);
 void  hbo_noise_tile2(const hbo_world *w, int32_t cx, int32_t cz, float out[HBO_CHUNK_AREA]);
 float hbo_simplex3(float x, float y, float z, int64_t seed);
 float hbo_fbm3(float x, float y, float z, const hbo_world *w);

@@ -75,9 +75,37 @@ def fbm2(x, y, seed, octaves=6, lac=2.0, gain=0.6):
     return result
 
 
-def noise_tile(cx, cz, seed, freq=0.001, **kw):
+def ridge2(x, y, seed, octaves=6, lac=2.0, gain=0.6):
+    """functions/ridge_32.rs:18-31 (neg_mul_add fused, the AVX2 column)."""
+    x = x.astype(f32); y = y.astype(f32)
+    lac = f32(lac); gain = f32(gain)
+    result = (f32(1.0) - np.abs(simplex2(x, y, seed))).astype(f32)
+    amp = f32(1.0)
+    for _ in range(1, octaves):
+        x = x * lac; y = y * lac
+        amp = f32(amp * gain)
+        result = (result + fnma(np.abs(simplex2(x, y, seed)), np.full_like(x, amp), np.full_like(x, f32(1.0)))).astype(f32)
+    return result
+
+
+def turbulence2(x, y, seed, octaves=6, lac=2.0, gain=0.6):
+    """functions/turbulence_32.rs:18-32."""
+    x = x.astype(f32); y = y.astype(f32)
+    lac = f32(lac); gain = f32(gain)
+    result = np.abs(simplex2(x, y, seed)).astype(f32)
+    amp = f32(1.0)
+    for _ in range(1, octaves):
+        x = x * lac; y = y * lac
+        amp = f32(amp * gain)
+        result = (result + np.abs((simplex2(x, y, seed) * amp).astype(f32))).astype(f32)
+    return result
+
+
+def noise_tile(cx, cz, seed, freq=0.001, kind="fbm", **kw):
     """index x + z*32, like get_2d_noise_helper_f32 (noise/f32.rs:69-129)."""
     xs = (f32(cx) * f32(32) + np.arange(32, dtype=f32)).astype(f32)
     zs = (f32(cz) * f32(32) + np.arange(32, dtype=f32)).astype(f32)
     X, Z = np.meshgrid(xs, zs, indexing="xy")  # row = z
-    return fbm2((X * f32(freq)).ravel(), (Z * f32(freq)).ravel(), seed, **kw)
+    fn = {"fbm": fbm2, "ridge": ridge2, "turbulence": turbulence2,
+          "gradient": lambda x, y, seed, **_: simplex2(x.astype(f32), y.astype(f32), seed)}[kind]
+    return fn((X * f32(freq)).ravel(), (Z * f32(freq)).ravel(), seed, **kw)

@@ -19,11 +19,14 @@ from build_oracle import ORACLE_LIB, build_oracle  # noqa: E402
 
 class World(C.Structure):
     _fields_ = [("seed", C.c_int64), ("freq", C.c_float), ("octaves", C.c_int32), ("lacunarity", C.c_float),
-                ("gain", C.c_float), ("fused", C.c_int32)]
+                ("gain", C.c_float), ("fused", C.c_int32), ("kind", C.c_int32)]
 
 
-def world(seed=0, freq=0.001, octaves=6, lacunarity=2.0, gain=0.6, fused=1) -> World:
-    return World(seed, freq, octaves, lacunarity, gain, fused)
+NOISE_FBM, NOISE_RIDGE, NOISE_TURBULENCE, NOISE_GRADIENT = 0, 1, 2, 3
+
+
+def world(seed=0, freq=0.001, octaves=6, lacunarity=2.0, gain=0.6, fused=1, kind=NOISE_FBM) -> World:
+    return World(seed, freq, octaves, lacunarity, gain, fused, kind)
 
 
 class Material(C.Structure):

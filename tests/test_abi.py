@@ -136,20 +136,26 @@ def test_noise_kernel_has_no_unintended_fma_contraction():
     """ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false; the reference's
     operator overloads never fuse (only the six neg_mul_add sites of simplex_2d do).  csrc/noise.cuh routes every
     product that feeds an add across a packed/scalar boundary; this pins the result in the shipped SASS:
-    k_heights evaluates 4 simplex pairs in its instruction stream (2 pairs x {first octave, octave loop}), so it
-    must contain exactly 4 x 6 FFMA2 and no scalar FFMA at all."""
+    the FBM k_heights evaluates 4 simplex pairs in its instruction stream (2 pairs x {first octave, octave loop}),
+    so it must contain exactly 4 x 6 FFMA2 and no scalar FFMA at all.  The other noise kinds (template parameter
+    KIND, HB_NOISE_*): turbulence the same, gradient 2 x 6 (no octave loop), ridge 24 plus its own neg_mul_add
+    (functions/ridge_32.rs:27, fused on AVX2) = one scalar FFMA per lane of each of the 2 packed loop bodies."""
     import shutil
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
     sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
     funcs = re.split(r"\n\s*Function : ", sass)
     heights = [f for f in funcs if "k_heights" in f.split("\n", 1)[0]]
-    assert len(heights) == 2  # ColList and ColRegion instantiations
+    assert len(heights) == 8  # {ColList, ColRegion} x 4 noise kinds
+    want = {0: (24, 0), 1: (24, 4), 2: (24, 0), 3: (12, 0)}  # KIND -> (FFMA2, scalar FFMA)
     for f in heights:
+        kind = int(re.search(r"ELi(\d)EEEv", f.split("\n", 1)[0]).group(1))
         ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", f)
-        assert sum(o.startswith("FFMA2") for o in ops) == 24, "packed FMA count changed: check for contraction"
-        assert not [o for o in ops if o.startswith("FFMA") and not o.startswith("FFMA2")]
+        packed = sum(o.startswith("FFMA2") for o in ops)
+        scalar = sum(o.startswith("FFMA") and not o.startswith("FFMA2") for o in ops)
+        assert (packed, scalar) == want[kind], f"kind {kind}: FMA count changed, check for contraction"
         assert sum(o.startswith("FMUL2") for o in ops) > 0 and sum(o.startswith("FADD2") for o in ops) > 0  # Blackwell packed f32x2
     # the whole library is compiled without FMA contraction in the 3-D noise path too (reference: no FMAs there)
+    # (reference: no FMAs there except ridge_3d's neg_mul_add, functions/ridge_32.rs:43)
     n3 = [f for f in funcs if "k_noise3d" in f.split("\n", 1)[0]]
-    assert n3 and not re.findall(r"\bFFMA\b", n3[0])
+    assert n3 and len(re.findall(r"\bFFMA\b", n3[0])) == 1

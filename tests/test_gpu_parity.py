@@ -480,3 +480,38 @@ def test_mesh_cubes_equals_mesh_on_settled_world(ctx):
     a = ctx.mesh(pts, ref["ids"])
     assert (a["counts"] == ref["counts"]).all()
     ctx.set_world(0)
+
+
+# ---------------------------------------------------------------- other noise kinds of the crate
+@pytest.mark.parametrize("kind", [O.NOISE_RIDGE, O.NOISE_TURBULENCE, O.NOISE_GRADIENT])
+def test_noise_kinds_bit_exact(ctx, kind):
+    """Ridge / turbulence / gradient sampling (functions/{ridge,turbulence}_32.rs, noise/gradient.rs) through the same
+    tile walks: 2-D tiles + heights, the 3-D tile, and block ids generated from those heights."""
+    try:
+        for seed in (0, 5):
+            ctx.set_world(seed)
+            ctx.set_noise_kind(kind)
+            w = O.world(seed, kind=kind)
+            cols = np.array([[0, 0], [-1, -1], [7, -3], [-512, 511], [262143, -262143]], dtype=np.int32)
+            noise, heights = ctx.noise_tiles(cols, want_heights=True)
+            for i, (cx, cz) in enumerate(cols):
+                ref = O.noise_tile2(w, int(cx), int(cz))
+                assert noise[i].view(np.uint32).tolist() == ref.view(np.uint32).tolist(), (kind, seed, cx, cz)
+                assert (heights[i] == O.heights_from_noise(ref).reshape(32, 32).T.ravel()).all()
+            got3 = ctx.noise_fbm3d((-5.0, 100.0, 3.0), (9, 5, 7), (0.013, 0.02, 0.011))
+            ref3 = O.noise_tile3(w, (-5.0, 100.0, 3.0), (9, 5, 7), (0.013, 0.02, 0.011))
+            assert got3.view(np.uint32).tolist() == ref3.view(np.uint32).tolist()
+            pts = region_points((2, -2, 2, 2, 3, 4)) if kind == O.NOISE_RIDGE else region_points((2, -2, 2, 2, -1, 3))
+            ids = ctx.generate(pts)["ids"]
+            want = O.generate_ids(w, [(int(p["x"]), int(p["y"]), int(p["z"])) for p in pts])
+            assert (ids == want).all()
+            assert 0 < (ids != 0).sum() < ids.size  # the surface is inside the sampled layers
+    finally:
+        ctx.set_noise_kind(O.NOISE_FBM)
+        ctx.set_world(0)
+
+
+def test_noise_kind_errors(ctx):
+    with pytest.raises(hb.HerbGpuError) as e:
+        ctx.set_noise_kind(7)
+    assert e.value.code == hb._lib.HB_ERR_INVALID

@@ -9,6 +9,7 @@ import os
 import struct
 
 import numpy as np
+import pytest
 
 import np_noise as N
 import oracle as O
@@ -116,3 +117,21 @@ def test_noise3d_properties():
     assert a[2, 1:4, 4:8].tobytes() == b[0].tobytes()  # pure function of coordinates; index x + y*X + z*X*Y
     assert np.isfinite(a).all() and np.abs(a).max() < 3.0
     assert O.noise_tile3(O.world(4), (0, 0, 0), (8, 4, 3), (0.05, 0.06, 0.07)).tobytes() != a.tobytes()
+
+
+@pytest.mark.parametrize("kind,name", [(O.NOISE_RIDGE, "ridge"), (O.NOISE_TURBULENCE, "turbulence"), (O.NOISE_GRADIENT, "gradient")])
+def test_noise_kinds_match_independent_numpy_restatement(kind, name):
+    """Ridge / turbulence / gradient tiles (crates/simd-noise functions/{ridge,turbulence}_32.rs, noise/gradient.rs):
+    the C oracle against the numpy restatement, bit for bit."""
+    for seed, (cx, cz) in [(0, (0, 0)), (5, (-3, 7)), (12345, (100, -200))]:
+        w = O.world(seed, kind=kind)
+        got = O.noise_tile2(w, cx, cz)
+        want = N.noise_tile(cx, cz, seed, kind=name)
+        assert got.view(np.uint32).tolist() == want.view(np.uint32).tolist(), (name, seed, cx, cz)
+    # ranges: ridge of n octaves lies in (n - sum |s| amp, n]; turbulence is non-negative
+    w = O.world(0, kind=kind)
+    t = O.noise_tile2(w, 3, 3)
+    if kind == O.NOISE_RIDGE:
+        assert (t <= 6.0).all() and (t > 3.0).all()
+    if kind == O.NOISE_TURBULENCE:
+        assert (t >= 0.0).all()
