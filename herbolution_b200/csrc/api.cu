@@ -298,6 +298,11 @@ void hb_destroy(hb_ctx* c) {
                    &c->h_total, &c->h_inst[0], &c->h_inst[1], &c->h_off[0], &c->h_off[1], &c->h_cnt[0], &c->h_cnt[1],
                    &c->h_ids[0], &c->h_ids[1]};
     for (Buf* b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        if (c->stream_plan[i]) hb_region_plan_destroy(c->stream_plan[i]);
+        if (c->ev_kernels[i]) cudaEventDestroy(c->ev_kernels[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
     if (c->d_mats) cudaFree(c->d_mats);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy) cudaStreamDestroy(c->copy);
@@ -763,19 +768,28 @@ int hb_generate_mesh_region_slab(hb_ctx* c, const hb_region* region, int32_t ix_
     }
     width = std::min(width, ix_end - ix_begin);
 
-    hb_region_plan plan[2];
+    // the two plans (device buffers grow-only) and the events live in the ctx: after the first call of a given
+    // shape nothing is allocated or freed here, which matters with several processes on one box (allocation
+    // calls serialise in the driver and cudaFree synchronises the device)
+    hb_region_plan* plan[2];
     for (int b = 0; b < 2; ++b) {
-        plan[b].ctx = c; plan[b].region = *region; plan[b].want_ids = want_ids;
-        plan_target(&plan[b], ix_begin, ix_begin + width);
-        rc = plan_alloc(&plan[b], width);
-        if (rc != HB_OK) goto done;
+        if (!c->stream_plan[b]) {
+            c->stream_plan[b] = new (std::nothrow) hb_region_plan();
+            if (!c->stream_plan[b]) return fail(HB_ERR_NOMEM, "out of host memory");
+            c->stream_plan[b]->ctx = c;
+            HB_CUDA(cudaEventCreateWithFlags(&c->ev_kernels[b], cudaEventDisableTiming));
+            HB_CUDA(cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+        }
+        plan[b] = c->stream_plan[b];
+        plan[b]->region = *region;
+        plan[b]->want_ids = want_ids;
+        plan_target(plan[b], ix_begin, ix_begin + width);
+        rc = plan_alloc(plan[b], width);
+        if (rc != HB_OK) return rc;
     }
     {
-        cudaEvent_t ev_kernels[2], ev_copied[2];
-        for (int b = 0; b < 2; ++b) {
-            cudaEventCreateWithFlags(&ev_kernels[b], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming);
-        }
+        cudaEvent_t* ev_kernels = c->ev_kernels;
+        cudaEvent_t* ev_copied = c->ev_copied;
         struct Pending { bool live; uint64_t first, n, span; } pend[2] = {{false, 0, 0, 0}, {false, 0, 0, 0}};
         uint64_t sum_chunks = 0, sum_quads = 0;
         auto drain = [&](int b) -> int {
@@ -790,7 +804,7 @@ int hb_generate_mesh_region_slab(hb_ctx* c, const hb_region* region, int32_t ix_
         int slab = 0;
         for (int32_t ix0 = ix_begin; ix0 < ix_end && rc == HB_OK; ix0 += width, ++slab) {
             const int b = slab & 1;
-            hb_region_plan* p = &plan[b];
+            hb_region_plan* p = plan[b];
             rc = drain(b);  // buffers of parity b are free again (device out + pinned)
             if (rc != HB_OK) break;
             plan_target(p, ix0, std::min(ix_end, ix0 + width));
@@ -829,18 +843,10 @@ int hb_generate_mesh_region_slab(hb_ctx* c, const hb_region* region, int32_t ix_
         if (rc == HB_OK) rc = drain((slab & 1) ^ 1);
         cudaStreamSynchronize(c->copy);
         cudaStreamSynchronize(c->stream);
-        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_kernels[b]); cudaEventDestroy(ev_copied[b]); }
         if (rc == HB_OK) {
             if (total_chunks) *total_chunks = sum_chunks;
             if (total_quads) *total_quads = sum_quads;
         }
-    }
-done:
-    cudaDeviceSynchronize();
-    for (int b = 0; b < 2; ++b) {
-        Buf* bufs[] = {&plan[b].d_heights, &plan[b].d_counts, &plan[b].d_offsets, &plan[b].d_scan, &plan[b].d_total,
-                       &plan[b].d_out, &plan[b].d_ids, &plan[b].h_total};
-        for (Buf* q : bufs) q->release();
     }
     return rc;
 }

@@ -83,8 +83,11 @@ struct hb_ctx {
     hb::Buf d_pts, d_cols, d_colidx, d_heights, d_noise, d_ids, d_cubes, d_nbr, d_bitmaps, d_summary, d_counts,
         d_offsets, d_scan, d_total, d_out;
     hb::Buf h_total;
-    // region streaming
+    // region streaming: pinned staging, and the two double-buffered plans + events kept across calls so that a
+    // steady-state hb_generate_mesh_region call allocates and frees nothing
     hb::Buf h_inst[2], h_off[2], h_cnt[2], h_ids[2];
+    struct hb_region_plan* stream_plan[2] = {nullptr, nullptr};
+    cudaEvent_t ev_kernels[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     hb_ctx() {
         h_total.pinned = true;
         for (int i = 0; i < 2; ++i) h_inst[i].pinned = h_off[i].pinned = h_cnt[i].pinned = h_ids[i].pinned = true;
