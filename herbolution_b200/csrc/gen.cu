@@ -39,45 +39,38 @@ struct ColRegion {
     }
 };
 
-// One CTA = one chunk column = 32x32 samples.  Sample i: x = i & 31, z = i >> 5 (the crate's tile
-// order x + z*32, noise/f32.rs:95-113).  Heights are written in voxel-column order x*32 + z.
+// One work item = one chunk column = 32x32 samples; persistent CTAs stride through the columns so the tables are
+// staged once per CTA and there is no barrier in the column loop.  Thread mapping: sample i has x = i >> 5,
+// z = i & 31, i.e. heights are produced directly in voxel-column order x*32 + z (coalesced stores, no transpose);
+// the optional raw noise tile keeps the crate's order x + z*32 (noise/f32.rs:95-113) with a strided store.
 template <class Cols, int KIND>
-__global__ void __launch_bounds__(kThreads) k_heights(WorldDev w, Cols cols, int32_t* __restrict__ heights,
+__global__ void __launch_bounds__(kThreads, 8) k_heights(WorldDev w, Cols cols, int ncol, int32_t* __restrict__ heights,
                                                        float* __restrict__ noise) {
     __shared__ NoiseTables s_tab;
-    __shared__ int s_h[32][33];  // padded: the transposed store below is bank-conflict free
     load_noise_tables(s_tab, w.seed_lo);
-    const int col = cols.first() + blockIdx.x;
-    int cx, cz;
-    cols.get(col, cx, cz);
-    // chunk.position.xz().cast() * CHUNK_LENGTH as f32 (generator/mod.rs:74); lane coordinate =
-    // start + i, exact in f32 for |c| <= HB_MAX_CHUNK_COORD
-    const float start_x = __fmul_rn(__int2float_rn(cx), 32.0f);
-    const float start_z = __fmul_rn(__int2float_rn(cz), 32.0f);
     __syncthreads();
-
-    float v[4];
+    for (int c = blockIdx.x; c < ncol; c += gridDim.x) {
+        const int col = cols.first() + c;
+        int cx, cz;
+        cols.get(col, cx, cz);
+        // chunk.position.xz().cast() * CHUNK_LENGTH as f32 (generator/mod.rs:74); lane coordinate =
+        // start + i, exact in f32 for |c| <= HB_MAX_CHUNK_COORD
+        const float start_x = __fmul_rn(__int2float_rn(cx), 32.0f);
+        const float start_z = __fmul_rn(__int2float_rn(cz), 32.0f);
 #pragma unroll
-    for (int k = 0; k < 4; k += 2) {  // two samples per packed evaluation (FFMA2 / FADD2 / FMUL2)
-        const int i0 = threadIdx.x + k * kThreads, i1 = i0 + kThreads;
-        const float2 x = pk(__fadd_rn(start_x, __int2float_rn(i0 & 31)), __fadd_rn(start_x, __int2float_rn(i1 & 31)));
-        const float2 z = pk(__fadd_rn(start_z, __int2float_rn(i0 >> 5)), __fadd_rn(start_z, __int2float_rn(i1 >> 5)));
-        const float2 r = noise2_pair<KIND>(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
-        v[k] = r.x;
-        v[k + 1] = r.y;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = threadIdx.x + k * kThreads;
-        if (noise) noise[(size_t)col * HB_CHUNK_AREA + i] = v[k];
-        s_h[i & 31][i >> 5] = height_from_noise(v[k]);
-    }
-    __syncthreads();
-    if (heights) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = threadIdx.x + k * kThreads;
-            heights[(size_t)col * HB_CHUNK_AREA + i] = s_h[i >> 5][i & 31];
+        for (int k = 0; k < 4; k += 2) {  // two samples per packed evaluation (FFMA2 / FADD2 / FMUL2)
+            const int i0 = threadIdx.x + k * kThreads, i1 = i0 + kThreads;
+            const float2 x = pk(__fadd_rn(start_x, __int2float_rn(i0 >> 5)), __fadd_rn(start_x, __int2float_rn(i1 >> 5)));
+            const float2 z = pk(__fadd_rn(start_z, __int2float_rn(i0 & 31)), __fadd_rn(start_z, __int2float_rn(i1 & 31)));
+            const float2 r = noise2_pair<KIND>(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
+            if (noise) {
+                noise[(size_t)col * HB_CHUNK_AREA + (i0 >> 5) + (i0 & 31) * 32] = r.x;
+                noise[(size_t)col * HB_CHUNK_AREA + (i1 >> 5) + (i1 & 31) * 32] = r.y;
+            }
+            if (heights) {
+                heights[(size_t)col * HB_CHUNK_AREA + i0] = height_from_noise(r.x);
+                heights[(size_t)col * HB_CHUNK_AREA + i1] = height_from_noise(r.y);
+            }
         }
     }
 }
@@ -231,11 +224,14 @@ __global__ void __launch_bounds__(kThreads) k_noise3d(WorldDev w, float sx, floa
 
 template <class Cols>
 void launch_heights_kind(cudaStream_t s, const WorldDev& w, Cols cols, unsigned grid, int32_t* d_heights, float* d_noise) {
+    const int ncol = (int)grid;
+    const unsigned cap = (unsigned)num_sms() * 8u;  // 8 resident CTAs per SM (32 registers x 256 threads)
+    if (grid > cap) grid = cap;
     switch (w.kind) {
-        case HB_NOISE_RIDGE: k_heights<Cols, HB_NOISE_RIDGE><<<grid, kThreads, 0, s>>>(w, cols, d_heights, d_noise); break;
-        case HB_NOISE_TURBULENCE: k_heights<Cols, HB_NOISE_TURBULENCE><<<grid, kThreads, 0, s>>>(w, cols, d_heights, d_noise); break;
-        case HB_NOISE_GRADIENT: k_heights<Cols, HB_NOISE_GRADIENT><<<grid, kThreads, 0, s>>>(w, cols, d_heights, d_noise); break;
-        default: k_heights<Cols, HB_NOISE_FBM><<<grid, kThreads, 0, s>>>(w, cols, d_heights, d_noise); break;
+        case HB_NOISE_RIDGE: k_heights<Cols, HB_NOISE_RIDGE><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); break;
+        case HB_NOISE_TURBULENCE: k_heights<Cols, HB_NOISE_TURBULENCE><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); break;
+        case HB_NOISE_GRADIENT: k_heights<Cols, HB_NOISE_GRADIENT><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); break;
+        default: k_heights<Cols, HB_NOISE_FBM><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); break;
     }
 }
 
