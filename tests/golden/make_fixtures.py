@@ -53,7 +53,59 @@ def oracle_digests():
                           "geometry_sha256": hashlib.sha256(
                               r["instances"]["model"].tobytes() + r["instances"]["ao"].tobytes()).hexdigest(),
                           "colour_sha256": hashlib.sha256(r["instances"]["rgba"].tobytes()).hexdigest()})
+    # the crate's other noise kinds
+    d["noise_kinds"] = []
+    for kind, name in ((O.NOISE_RIDGE, "ridge"), (O.NOISE_TURBULENCE, "turbulence"), (O.NOISE_GRADIENT, "gradient")):
+        for seed in (0, 5):
+            t = O.noise_tile2(O.world(seed, kind=kind), 3, -5)
+            d["noise_kinds"].append({"kind": kind, "name": name, "seed": seed, "col": [3, -5],
+                                     "sha256": hashlib.sha256(t.tobytes()).hexdigest()})
+    # on-disk cube codec
+    d["codec"] = []
+    for seed in (0, 5):
+        w = O.world(seed)
+        for p in [(0, 0, 0), (0, -1, 0), (5, 1, -7), (-3, -2, 9)]:
+            enc = O.rle_encode(O.generate_ids(w, [p])[0])
+            d["codec"].append({"seed": seed, "pt": list(p), "bytes": int(enc.shape[0]),
+                               "sha256": hashlib.sha256(enc.tobytes()).hexdigest()})
+    # device-resident world: load, scripted edits, sync, remesh
+    d["world"] = []
+    for seed in (0, 5):
+        m = O.ChunkMapOracle(O.world(seed))
+        pts, edits = world_script(seed)
+        for p in pts:
+            m.load(p)
+        m.apply(m.drain())
+        for pos, mat in edits:
+            m.set_cube(pos, mat)
+        upd = m.drain()
+        m.apply(upd)
+        cubes = hashlib.sha256(b"".join(m.cubes(p).tobytes() for p in pts)).hexdigest()
+        dirty = sorted(upd)
+        mesh = hashlib.sha256()
+        quads = 0
+        for p in dirty:
+            inst = m.remesh(p)
+            quads += inst.shape[0]
+            mesh.update(inst.tobytes())
+        d["world"].append({"seed": seed, "cubes_sha256": cubes, "dirty": [list(p) for p in dirty],
+                           "update_positions": int(sum(len(set(v["pos"].tolist())) for v in upd.values())),
+                           "quads": quads, "mesh_sha256": mesh.hexdigest()})
+        m.close()
     return d
+
+
+def world_script(seed):
+    """The fixed load set and edit list behind the "world" digests (also used by the GPU golden test)."""
+    import numpy as np
+    pts = [(cx, cy, cz) for cx in (0, 1) for cz in (-1, 0) for cy in (-1, 0)]
+    rng = np.random.default_rng(4242 + seed)
+    edits = []
+    for _ in range(300):
+        wx, wz = int(rng.integers(-2, 66)), int(rng.integers(-34, 34))
+        wy = int(rng.integers(-20, 20))
+        edits.append(((wx, wy, wz), int(rng.choice([0, 0, 1, 2, 3]))))
+    return pts, edits
 
 
 if __name__ == "__main__":
