@@ -42,6 +42,56 @@ __global__ void k_bulk(char* p, size_t nwin) {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// The emit kernel's pattern: every CTA streams through its own contiguous region of `region` bytes (a chunk's
+// instances), regions handed out CTA-strided; inside a region the CTA's warps take consecutive 3200-byte windows.
+// `align` shifts every region start by a multiple of 400 bytes (16-byte but not 128-byte aligned, like chunk starts).
+__global__ void k_bulk_regions(char* p, size_t nregions, size_t region, int misalign) {
+    extern __shared__ __align__(128) char sm[];
+    constexpr int BYTES = 3200;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    char* ws = sm + warp * BYTES;
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ws);
+    const size_t wins = region / BYTES;
+    for (size_t r = blockIdx.x; r < nregions; r += gridDim.x) {
+        const size_t shift = misalign ? ((r * 7) % 8) * 400 : 0;
+        char* base = p + r * region + shift;
+        if (misalign == 2) {
+            // region still starts at a multiple of 400 B, but the windows are cut at absolute multiples of 3200 B:
+            // a short first window, then 128-byte-aligned full windows (the last one short)
+            char* end = base + wins * BYTES;
+            char* first_full = p + ((size_t)(base - p) + BYTES - 1) / BYTES * BYTES;
+            for (size_t w = warp;; w += nw) {
+                char* a = w == 0 ? base : first_full + (w - 1) * BYTES;
+                if (a >= end) break;
+                char* b = w == 0 ? first_full : a + BYTES;
+                if (b > end) b = end;
+                const uint32_t nb = (uint32_t)(b - a);
+                if (nb == 0) continue;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                for (int i = lane * 16; i < BYTES; i += 32 * 16) { uint32_t h = (uint32_t)(w * 977 + i + r) * 2654435761u; *reinterpret_cast<uint4*>(ws + i) = make_uint4(h, ~h, h * 31u, h ^ 0x55u); }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                                 :: "l"(a), "r"(saddr), "r"(nb) : "memory");
+            }
+            continue;
+        }
+        for (size_t w = warp; w < wins; w += nw) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            for (int i = lane * 16; i < BYTES; i += 32 * 16) { uint32_t h = (uint32_t)(w * 977 + i + r) * 2654435761u; *reinterpret_cast<uint4*>(ws + i) = make_uint4(h, ~h, h * 31u, h ^ 0x55u); }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                             :: "l"(base + w * BYTES), "r"(saddr), "r"(BYTES) : "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <class F>
 float timeit(F f) {
     cudaEvent_t a, b;
@@ -74,6 +124,13 @@ int main() {
         ms = timeit([&] { k_bulk<16384><<<148 * ctas, 128, 4 * 16384>>>(d, bytes / 16384); });
         printf("bulk 16 KB/warp,  %d CTA/SM: %.0f GB/s\n", ctas, bytes / ms / 1e6);
     }
+    for (size_t region : {(size_t)102400, (size_t)163200, (size_t)1632000, (size_t)16320000})
+        for (int mis = 0; mis < 3; ++mis) {
+            const size_t nreg = (bytes - 4096) / region;
+            ms = timeit([&] { k_bulk_regions<<<148 * 4, 256, 8 * 3200>>>(d, nreg, region, mis); });
+            printf("bulk 3200 B/warp, 4 CTA/SM, per-CTA regions of %zu B, misalign %d: %.0f GB/s\n", region, mis,
+                   (double)nreg * (region / 3200 * 3200) / ms / 1e6);
+        }
     printf("last error: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
