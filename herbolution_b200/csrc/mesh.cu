@@ -38,6 +38,7 @@ constexpr int kStageCap = kT;   // quads expanded per window (one per thread)
 
 typedef unsigned long long u64;
 
+constexpr int kSeedLayers = 32;
 struct MeshSmem {
     u64 occ[kTileN];                            // 9248 B
     __align__(16) float stage[kStageCap * 25];  // 25600 B
@@ -50,6 +51,7 @@ struct MeshSmem {
     u64 rng_seed;
     int nbr[27];
     int red[3][8];
+    u64 layer_seed[kSeedLayers];                // region kernels: the column's per-layer chunk hashes
 };
 
 // ---- SipHash-1-3 with zero keys over the 12 bytes of ChunkPt: std DefaultHasher as used at
@@ -780,7 +782,11 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
         const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
         __syncthreads();  // previous column's readers of sm.hts / sm.red are done
         int cmax = INT32_MIN, hmin = INT32_MAX, emin = INT32_MAX;
-        load_heights_tile(r, heights, ix, iz, sm.hts, cmax, hmin, emin, rel);
+        const TileRegs tile_regs = fetch_heights_tile(r, heights, ix, iz);
+        // The chunk hashes (SipHash-1-3, ~200 dependent 64-bit operations) of all layers of this column, one lane per
+        // layer, while the heights tile is in flight -- instead of one thread hashing per chunk in front of a barrier.
+        if (EMIT && warp == 2 && lane < min(r.ncy, kSeedLayers)) sm.layer_seed[lane] = siphash13_chunk(r.cx0 + ix, r.cy0 + lane, r.cz0 + iz);
+        store_heights_tile(tile_regs, sm.hts, cmax, hmin, emin, rel);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
         hmin = __reduce_min_sync(0xffffffffu, hmin);
         emin = __reduce_min_sync(0xffffffffu, emin);
@@ -815,7 +821,7 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
                 // Region-bottom slab: the chunk, its four lateral neighbours and the layer above are solid, the chunk
                 // below is absent -> exactly one Down face per column, in column order, and every AO probe (all at
                 // y-1) reads "empty".  No tile, masks, scan or descriptors are needed (k_count_region counted 1024).
-                if (tid == 32) sm.rng_seed = siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
+                if (tid == 32) sm.rng_seed = iy < kSeedLayers ? sm.layer_seed[iy] : siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
                 __syncthreads();
                 const MatHeights mat{sm.hts, a};
                 float* const ws = sm.stage + warp * (32 * 25);
@@ -835,7 +841,7 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
                 const int d = min(max(sm.hts[i] - (a - 1), 0), 34);  // solid voxels at tile bits 0..33
                 sm.occ[i] = ((1ULL << d) - 1ULL) & ymask;
             }
-            if (EMIT && tid == 32) sm.rng_seed = siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
+            if (EMIT && tid == 32) sm.rng_seed = iy < kSeedLayers ? sm.layer_seed[iy] : siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
             __syncthreads();
             const MatHeights mat{sm.hts, a};
             const uint32_t q = mesh_tile<EMIT>(sm, mat, FacesFromOcc{sm.occ}, (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32,
