@@ -515,3 +515,46 @@ def test_noise_kind_errors(ctx):
     with pytest.raises(hb.HerbGpuError) as e:
         ctx.set_noise_kind(7)
     assert e.value.code == hb._lib.HB_ERR_INVALID
+
+
+def test_region_config4_full_size(ctx):
+    """BASELINE config 4 at its full size (256x256 columns x 6 = 393 216 chunks, 175 M quads, 17.5 GB of instances,
+    device-resident plan): size-independent layout properties over all chunks, and bit-exact parity with the oracle
+    on the interior of sampled 6x6-column patches (the patch's outer ring only supplies the neighbours)."""
+    ctx.set_world(0)
+    reg = (-128, -128, 256, 256, -3, 6)
+    region = hb.Region(*reg)
+    plan = ctx.region_plan(region)
+    plan.enqueue(hb.STAGE_ALL_MESH)
+    res = plan.result()
+    n = region.n_chunks
+    assert res["n_chunks"] == n
+    counts = ctx.download(res["d_counts"], np.uint32, n).astype(np.int64)
+    offsets = ctx.download(res["d_offsets"], np.uint64, n).astype(np.int64)
+    spans = (counts + 3) // 4 * 4
+    assert counts.sum() == res["quads"] and spans.sum() == res["span"]
+    assert (offsets == np.concatenate([[0], np.cumsum(spans)[:-1]])).all()     # deterministic exclusive scan, no gaps
+    # every column of the region bottom shows its 1024 Down faces at least
+    per = counts.reshape(256, 256, 6)
+    assert (per[:, :, 0] >= 1024).all()
+    # a second run of the same plan reproduces the same counts (no atomics on the path)
+    plan.enqueue(hb.STAGE_ALL_MESH)
+    res2 = plan.result()
+    assert (ctx.download(res2["d_counts"], np.uint32, n) == counts).all() and res2["quads"] == res["quads"]
+    rng = np.random.default_rng(2024)
+    w = O.world(0)
+    for _ in range(3):
+        px, pz = int(rng.integers(0, 250)), int(rng.integers(0, 250))
+        patch = (reg[0] + px, reg[1] + pz, 6, 6, reg[4], reg[5])
+        ref = O.region_pipeline(w, patch, literal=True, threads=8)
+        roff = np.concatenate([[0], np.cumsum(ref["counts"].astype(np.int64))])
+        for ix in range(1, 5):
+            for iz in range(1, 5):
+                for iy in range(1, 5):  # layers 0 and 5 touch the region's bottom / top on both sides alike, but keep to the interior
+                    g = ((px + ix) * 256 + (pz + iz)) * 6 + iy
+                    k = (ix * 6 + iz) * 6 + iy
+                    assert counts[g] == ref["counts"][k], (px, pz, ix, iz, iy)
+                    if counts[g]:
+                        inst = ctx.download(res2["d_instances"] + int(offsets[g]) * 100, hb.INSTANCE_DTYPE, int(counts[g]))
+                        assert_instances_equal(inst, ref["instances"][roff[k]:roff[k + 1]], f"patch {px},{pz} chunk {ix},{iz},{iy}")
+    plan.close()
