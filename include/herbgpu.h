@@ -243,7 +243,8 @@ typedef struct hb_chunk_cube {
     hb_palette_cube cube;
 } hb_chunk_cube;
 
-/* A store of `capacity` chunk slots (292 KiB of HBM each: cubes, update sets, mesher bitmaps). */
+/* A store of `capacity` chunk slots (292 KiB of HBM each: cubes, update sets, mesher bitmaps).  A world borrows its
+ * ctx (stream, tables, mutex): destroy every world before hb_destroy(ctx).  Calls on one world are serialised. */
 HB_API int hb_world_create(hb_ctx *ctx, size_t capacity, hb_world **out);
 HB_API void hb_world_destroy(hb_world *world);
 HB_API size_t hb_world_len(const hb_world *world);          /* chunks currently loaded */
