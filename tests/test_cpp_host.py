@@ -39,3 +39,15 @@ def test_cpp_mirror_parity_on_gpu():
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "byte-exact" in out.stdout
+
+
+def test_header_is_plain_c():
+    """include/herbgpu.h compiles as C11 (-pedantic) and the library links from C; argument checks need no GPU."""
+    src = os.path.join(ROOT, "tests", "c", "test_header.c")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_header_c")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    libdir = os.path.join(ROOT, "herbolution_b200")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", src, "-o", exe, f"-L{libdir}", "-lherbgpu",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
