@@ -327,12 +327,28 @@ def main():
                "sample": f"{sample[2]}x{sample[3]} columns x {NCY} = {n} chunks (sub-region of the workload), oracle "
                          f"literal path, best of 2 passes, {best:.2f} s"}
 
+    # columns/s and the split of chunks by what they contribute, so that trivial (all-air / buried)
+    # layers cannot inflate the headline.  From this rank's per-chunk quad counts (device -> host, outside timing).
+    split = None
+    if rank == 0:
+        import numpy as np
+        per = ctx.download(res["d_counts"], np.uint32, n_chunks).astype(np.int64).reshape(-1, NCY)
+        with_quads = int((per > 0).sum())
+        slab_only = int((per[:, 0] == 1024).sum())  # region-bottom chunks whose only faces are their 1024 Down faces
+        split = {"columns_per_s": value / NCY, "chunks_with_quads": with_quads, "chunks_without_quads": int(per.size - with_quads),
+                 "region_bottom_slab_only_chunks": slab_only, "surface_chunks": with_quads - slab_only,
+                 "surface_chunks_per_s": (with_quads - slab_only) / per.size * value,
+                 "layers": [{"cy": CY0 + i, "chunks_with_quads": int((per[:, i] > 0).sum()), "quads": int(per[:, i].sum())}
+                            for i in range(NCY)],
+                 "note": "per GPU (rank 0's slab); rates scale the whole-job value by this rank's fractions"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
                 "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * steps, "roofline": roofline, "cpu_baseline": cpu,
-                "kernels": kernels, "quads_per_step_per_gpu": quads, "instance_bytes_per_step_per_gpu": span * 100}
+                "kernels": kernels, "quads_per_step_per_gpu": quads, "instance_bytes_per_step_per_gpu": span * 100,
+                "split": split}
         print(json.dumps(line))
     plan.close()
     ctx.close()
