@@ -537,11 +537,23 @@ k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
            const void* __restrict__ blocks, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
            const uint32_t* __restrict__ summary, const uint32_t* __restrict__ planes, uint32_t* __restrict__ counts,
            const u64* __restrict__ offsets, float* __restrict__ out, u64 capacity, u64* __restrict__ total,
-           const int32_t* __restrict__ list) {
+           const int32_t* __restrict__ list, uint32_t batch) {
     __shared__ MeshSmem sm;
+    __shared__ unsigned long long s_ticket;
     const int tid = threadIdx.x;
     if (EMIT) load_tables(sm, tb);
-    for (size_t item = blockIdx.x; item < n; item += gridDim.x) {
+    // Work distribution: chunks differ wildly in cost (three quarters of a terrain batch emit nothing), so the CTAs
+    // draw batches of `batch` consecutive work items from a ticket counter (total[3], zeroed by the launch wrapper)
+    // instead of striding statically.  This only decides WHICH CTA meshes a chunk; where its quads go is fixed by the
+    // scanned offsets, so the output stays deterministic and the face compaction itself uses no atomics.
+    for (;;) {
+        __syncthreads();  // previous batch's readers of s_ticket / sm are done
+        if (tid == 0) s_ticket = atomicAdd(total + 3, (u64)batch);
+        __syncthreads();
+        const size_t first = (size_t)s_ticket;
+        if (first >= n) break;
+        const size_t last = first + batch < n ? first + batch : n;
+    for (size_t item = first; item < last; ++item) {
         // block-uniform early out: the COUNT stage already knows which chunks have no visible face at all
         // (all air, or buried: k_count_ids), so EMIT needs one load per chunk to skip them
         const uint32_t my_count = counts[item];
@@ -597,6 +609,7 @@ k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
         }
         if (!EMIT && tid == 0) counts[item] = q;
     }
+    }  // ticket loop
     if (EMIT) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
 }
 
@@ -988,23 +1001,26 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
                             uint32_t* d_counts, const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
                             uint64_t* d_total, const int32_t* d_list) {
     if (n == 0) return cudaSuccess;
-    // Persistent CTAs stride through the chunk list.  Batches are usually ordered (ix, iz, iy) with a small number
-    // of layers, so an even stride would hand every CTA the same layer (all surface or all buried) for the whole
-    // launch; an odd stride rotates through the layers and balances the load.
+    // Persistent CTAs.  EMIT draws work from a ticket counter (see k_mesh_ids); COUNT strides statically: batches are
+    // usually ordered (ix, iz, iy) with a small number of layers, so an even stride would hand every CTA the same
+    // layer (all surface or all buried) for the whole launch; an odd stride rotates through the layers.
     size_t grid = ((size_t)num_sms() * kCtasPerSm) - 1;
     if (grid > n) grid = n;
+    // ticket batches: one chunk for small launches (best balance), up to 8 when every CTA still gets >= 16 batches
+    const uint32_t batch = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, n / (grid * 16)));
 #define HB_LAUNCH(E, F)                                                                                              \
     k_mesh_ids<E, F><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, d_pts, n, d_blocks, d_nbr, d_bitmaps, d_summary, d_planes, \
-                                                   d_counts, (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total, d_list)
+                                                   d_counts, (const u64*)d_offsets, (float*)d_out, capacity, (u64*)d_total, d_list, batch)
     if (!emit) {
         size_t cgrid = (size_t)num_sms() * 8 - 1;  // odd, see above
         if (cgrid > n) cgrid = n;
         if (d_planes) k_count_ids<true><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts, d_list);
         else k_count_ids<false><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts, d_list);
-    } else if (d_planes) {
-        HB_LAUNCH(true, true);
     } else {
-        HB_LAUNCH(true, false);
+        const cudaError_t e = cudaMemsetAsync(d_total + 3, 0, sizeof(uint64_t), s);  // the ticket counter
+        if (e != cudaSuccess) return e;
+        if (d_planes) HB_LAUNCH(true, true);
+        else HB_LAUNCH(true, false);
     }
 #undef HB_LAUNCH
     return cudaGetLastError();

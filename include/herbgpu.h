@@ -220,7 +220,8 @@ HB_API int hb_dev_generate(hb_ctx *ctx, void *stream, const int32_t *d_cols_xz, 
                     const hb_chunk_pt *d_pts, const int32_t *d_col_of_chunk, size_t n,
                     int32_t *d_heights, float *d_noise, uint16_t *d_ids, hb_palette_cube *d_cubes);
 /* hb_dev_mesh: d_workspace of hb_dev_mesh_workspace_bytes(n) bytes.  d_total[0] = span (instances),
- * d_total[1] = quads, d_total[2] = error flags (1 = capacity exceeded, 2 = unknown material id). */
+ * d_total[1] = quads, d_total[2] = error flags (1 = capacity exceeded, 2 = unknown material id), d_total[3] = scratch
+ * (the emit kernel's work-ticket counter); d_total is 4 x u64. */
 HB_API size_t hb_dev_mesh_workspace_bytes(size_t n);
 HB_API int hb_dev_mesh(hb_ctx *ctx, void *stream, const hb_chunk_pt *d_pts, size_t n, const uint16_t *d_ids,
                 const int32_t *d_neighbor_index, void *d_workspace, hb_instance3d *d_out,
