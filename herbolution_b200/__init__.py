@@ -10,11 +10,11 @@ from ._lib import (CHUNK_AREA, CHUNK_CUBE_DTYPE, CHUNK_LENGTH, CHUNK_PT_DTYPE, C
 from .context import Context, RegionPlan
 from .generator import ChunkGenerator, ChunkPt, CubeMesh, GenerationParams
 from .mesher import ChunkData, ChunkMap, create_chunk_shell, generate_mesh
-from .world import World
+from .world import ServerChunkMap, World
 
 __all__ = [
     "CHUNK_AREA", "CHUNK_CUBE_DTYPE", "CHUNK_LENGTH", "CHUNK_PT_DTYPE", "CHUNK_VOLUME", "CUBE_DTYPE", "INSTANCE_DTYPE", "HerbGpuError",
     "Region", "STAGE_ALL_MESH", "STAGE_COUNT", "STAGE_EMIT", "STAGE_FILL", "STAGE_HEIGHTS", "STAGE_SCAN",
     "Context", "RegionPlan", "ChunkGenerator", "ChunkPt", "CubeMesh", "GenerationParams",
-    "ChunkData", "ChunkMap", "create_chunk_shell", "generate_mesh", "World",
+    "ChunkData", "ChunkMap", "create_chunk_shell", "generate_mesh", "ServerChunkMap", "World",
 ]

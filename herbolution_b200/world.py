@@ -121,3 +121,55 @@ class World:
             self.close()
         except Exception:
             pass
+
+
+class ServerChunkMap:
+    """The reference's names over a World: server ChunkMap (server/src/chunk/map.rs) + Chunk::sync_with_client
+    (server/src/chunk/mod.rs:35-67) + the client's remesh of updated chunks (client/src/world/chunk.rs:47-76).
+
+        queue_load / queue_unload   map.rs:65-75   (collected; flushed by update())
+        update()                    map.rs:236-245 (load_provided, then unload_requested)
+        set_cube(position, material) map.rs:81-151 (applied immediately, in call order)
+        sync_with_client()          -> {chunk position: CHUNK_CUBE_DTYPE entries}   (CubeUpdate per chunk)
+        remesh()                    -> {chunk position: INSTANCE_DTYPE array} for every chunk that got a CubeUpdate
+    """
+
+    def __init__(self, ctx: Context, capacity: int):
+        self.world = World(ctx, capacity)
+        self._load, self._unload = [], []
+
+    def queue_load(self, position) -> None:
+        self._load.append(tuple(int(v) for v in position))
+
+    def queue_unload(self, position) -> None:
+        self._unload.append(tuple(int(v) for v in position))
+
+    def update(self) -> None:
+        load, self._load = self._load, []
+        unload, self._unload = self._unload, []
+        if load:
+            self.world.load(load)
+        if unload:
+            self.world.unload(unload)
+
+    def set_cube(self, position, material: int) -> None:
+        self.world.set_cube(position, material)
+
+    def __len__(self) -> int:
+        return len(self.world)
+
+    def sync_with_client(self, want_wire: bool = True) -> dict:
+        n, _ = self.world.sync()
+        if not want_wire or n == 0:
+            return {}
+        u = self.world.fetch_updates()
+        return {(int(p["x"]), int(p["y"]), int(p["z"])): u["entries"][int(o):int(o) + int(c)]
+                for p, o, c in zip(u["pts"], u["offsets"], u["counts"])}
+
+    def remesh(self) -> dict:
+        out = self.world.remesh()
+        return {(int(p["x"]), int(p["y"]), int(p["z"])): out["instances"][int(o):int(o) + int(c)]
+                for p, o, c in zip(out["pts"], out["offsets"], out["counts"])}
+
+    def close(self) -> None:
+        self.world.close()

@@ -283,3 +283,43 @@ def test_world_remesh_dev_matches_host(ctx):
         assert (dev["offsets"] == host["offsets"]).all() and (dev["counts"] == host["counts"]).all()
         inst = ctx.download(dev["d_instances"], hb.INSTANCE_DTYPE, dev["span"])
         assert inst.tobytes() == host["instances"].tobytes()
+
+
+def test_server_chunk_map_mirror_and_extreme_coordinates(ctx):
+    """The reference-named mirror (queue_load / update / set_cube / sync_with_client / remesh) at negative chunk
+    coordinates and at the +-262143 coordinate limit."""
+    ora = O.ChunkMapOracle(O.world(0))
+    m = hb.ServerChunkMap(ctx, 16)
+    lim = 262143
+    pts = [(-5, -1, -9), (-4, -1, -9), (-5, 0, -9), (lim, 0, -lim), (lim, -1, -lim), (lim - 1, 0, -lim)]
+    for p in pts:
+        m.queue_load(p)
+        ora.load(p)
+    m.update()
+    assert len(m) == len(pts)
+    edits = [((-5 * 32 + 31, -3, -9 * 32), 0), ((-4 * 32, -3, -9 * 32), 0), ((-5 * 32 + 31, -3, -9 * 32), 3),
+             ((lim * 32 + 31, 5, -lim * 32), 2), ((lim * 32, 5, -lim * 32 + 31), 1), ((lim * 32, -1, -lim * 32 + 7), 0),
+             ((lim * 32, 0, -lim * 32 + 7), 0)]
+    for pos, mat in edits:
+        m.set_cube(pos, mat)
+        ora.set_cube(pos, mat)
+    want = ora.drain()
+    got = m.sync_with_client()
+    assert set(got) == set(want)
+    for pos in want:
+        assert set(got[pos]["pos"].tolist()) == set(want[pos]["pos"].tolist())
+        assert m.world.read_chunk(pos).tobytes() == ora.cubes(pos).tobytes()
+    ora.apply(want)
+    meshes = m.remesh()
+    assert set(meshes) == set(want)
+    for pos, inst in meshes.items():
+        assert_instances_equal(inst, ora.remesh(pos), f"chunk {pos}")
+    m.queue_unload(pts[0])
+    m.update()
+    assert len(m) == len(pts) - 1
+    with pytest.raises(hb.HerbGpuError) as e:
+        m.queue_load((lim + 1, 0, 0))
+        m.update()
+    assert e.value.code == hb._lib.HB_ERR_RANGE
+    m.close()
+    ora.close()
