@@ -558,3 +558,39 @@ def test_region_config4_full_size(ctx):
                         inst = ctx.download(res2["d_instances"] + int(offsets[g]) * 100, hb.INSTANCE_DTYPE, int(counts[g]))
                         assert_instances_equal(inst, ref["instances"][roff[k]:roff[k + 1]], f"patch {px},{pz} chunk {ix},{iz},{iy}")
     plan.close()
+
+
+def test_concurrent_callers_share_one_context(ctx):
+    """The reference calls its generator and mesher from many rayon workers at once (server/src/generator/mod.rs:36,
+    client/src/world/chunk.rs:66-75); every hb_* entry point is thread-safe per ctx.  Eight threads interleave
+    generate / mesh / noise / codec calls on one context; each result equals the single-threaded one."""
+    import threading
+    ctx.set_world(0)
+    jobs = []
+    for t in range(8):
+        reg = (4 * t - 16, 3 - t, 2, 2, -1, 2)
+        pts = region_points(reg)
+        ids = ctx.generate(pts)["ids"]
+        mesh = ctx.mesh(pts, ids)
+        jobs.append((pts, ids, mesh, ctx.noise_tiles([[reg[0], reg[1]]]), ctx.rle_encode(ids)["bytes"]))
+    errors = []
+
+    def worker(k):
+        try:
+            pts, ids, mesh, noise, enc = jobs[k]
+            for _ in range(4):
+                got_ids = ctx.generate(pts)["ids"]
+                assert (got_ids == ids).all()
+                got = ctx.mesh(pts, got_ids)
+                assert got["instances"].tobytes() == mesh["instances"].tobytes() and (got["offsets"] == mesh["offsets"]).all()
+                assert ctx.noise_tiles([[int(pts[0]["x"]), int(pts[0]["z"])]]).tobytes() == noise.tobytes()
+                assert ctx.rle_encode(got_ids)["bytes"].tobytes() == enc.tobytes()
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
