@@ -210,6 +210,80 @@ inline int shell_index(int dx, int dy, int dz) { return (dx + 1) * 9 + (dy + 1) 
 
 const int kNormal[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};  // face.rs:47-58
 
+// Position -> slot map of the loaded chunks (the reference's HashMap<ChunkPt, Chunk>): open addressing over packed
+// 3 x 21-bit keys.  A loader update asks for ~120 000 lookups (27 neighbours per new chunk), which is the host side
+// of hb_world_load; std::unordered_map made that 4 ms for 4 235 chunks.
+class SlotTable {
+   public:
+    void init(size_t capacity) {
+        size_t sz = 64;
+        while (sz < capacity * 4) sz <<= 1;
+        keys_.assign(sz, kEmpty);
+        vals_.assign(sz, -1);
+        mask_ = sz - 1;
+        count_ = filled_ = 0;
+    }
+    size_t size() const { return count_; }
+    int32_t find(int32_t x, int32_t y, int32_t z) const {
+        if (!in_range(x) || !in_range(y) || !in_range(z)) return -1;  // cannot be loaded; and must not alias a packed key
+        const uint64_t k = pack(x, y, z);
+        for (size_t i = hash(k) & mask_;; i = (i + 1) & mask_) {
+            if (keys_[i] == k) return vals_[i];
+            if (keys_[i] == kEmpty) return -1;
+        }
+    }
+    void insert(int32_t x, int32_t y, int32_t z, int32_t v) {  // key must be absent and in range
+        if ((filled_ + 1) * 2 > keys_.size()) rehash();
+        const uint64_t k = pack(x, y, z);
+        size_t i = hash(k) & mask_;
+        while (keys_[i] != kEmpty && keys_[i] != kTomb) i = (i + 1) & mask_;
+        if (keys_[i] == kEmpty) ++filled_;
+        keys_[i] = k;
+        vals_[i] = v;
+        ++count_;
+    }
+    void erase(int32_t x, int32_t y, int32_t z) {
+        if (!in_range(x) || !in_range(y) || !in_range(z)) return;
+        const uint64_t k = pack(x, y, z);
+        for (size_t i = hash(k) & mask_;; i = (i + 1) & mask_) {
+            if (keys_[i] == k) { keys_[i] = kTomb; vals_[i] = -1; --count_; return; }
+            if (keys_[i] == kEmpty) return;
+        }
+    }
+
+   private:
+    static constexpr uint64_t kEmpty = ~0ULL, kTomb = ~0ULL - 1;
+    static bool in_range(int32_t c) { return c >= -(1 << 20) && c < (1 << 20); }
+    static uint64_t pack(int32_t x, int32_t y, int32_t z) {
+        return ((uint64_t)((uint32_t)x & 0x1FFFFFu)) | ((uint64_t)((uint32_t)y & 0x1FFFFFu) << 21) | ((uint64_t)((uint32_t)z & 0x1FFFFFu) << 42);
+    }
+    static size_t hash(uint64_t k) {
+        k ^= k >> 31; k *= 0x9E3779B97F4A7C15ULL; k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ULL; k ^= k >> 32;
+        return (size_t)k;
+    }
+    void rehash() {  // drops the tombstones; the table never grows beyond what init() sized for `capacity` live keys
+        std::vector<uint64_t> ok;
+        std::vector<int32_t> ov;
+        ok.swap(keys_);
+        ov.swap(vals_);
+        keys_.assign(ok.size(), kEmpty);
+        vals_.assign(ok.size(), -1);
+        count_ = filled_ = 0;
+        for (size_t i = 0; i < ok.size(); ++i)
+            if (ok[i] != kEmpty && ok[i] != kTomb) {
+                size_t j = hash(ok[i]) & mask_;
+                while (keys_[j] != kEmpty) j = (j + 1) & mask_;
+                keys_[j] = ok[i];
+                vals_[j] = ov[i];
+                ++count_;
+                ++filled_;
+            }
+    }
+    std::vector<uint64_t> keys_;
+    std::vector<int32_t> vals_;
+    size_t mask_ = 0, count_ = 0, filled_ = 0;
+};
+
 }  // namespace
 
 struct hb_world {
@@ -221,7 +295,7 @@ struct hb_world {
     Buf d_a, d_b, d_c, d_d, d_heights, d_counts, d_offsets, d_scan, d_total, d_out;
     Buf h_pin;
     // host mirror
-    std::unordered_map<KeyXYZ, int32_t, KeyXYZHash> map;
+    SlotTable map;
     std::vector<int32_t> free_slots;
     std::vector<hb_chunk_pt> slot_pt;
     std::vector<uint8_t> used;
@@ -234,10 +308,7 @@ struct hb_world {
     struct SyncRec { int32_t slot; uint32_t epoch; uint32_t count; };
     std::vector<SyncRec> last_sync;
     hb_world() { h_pin.pinned = true; }
-    int find(int32_t x, int32_t y, int32_t z) const {
-        auto it = map.find(KeyXYZ{x, y, z});
-        return it == map.end() ? -1 : it->second;
-    }
+    int find(int32_t x, int32_t y, int32_t z) const { return map.find(x, y, z); }
 };
 
 namespace {
@@ -378,6 +449,7 @@ int hb_world_create(hb_ctx* c, size_t capacity, hb_world** out) {
         w->stale.assign(capacity, 0);
         w->touched.assign(capacity, 0);
         w->remesh.assign(capacity, 0);
+        w->map.init(capacity);
         w->free_slots.resize(capacity);
         for (size_t i = 0; i < capacity; ++i) w->free_slots[i] = (int32_t)(capacity - 1 - i);  // pop_back hands out slot 0 first
     } catch (const std::bad_alloc&) {
@@ -409,42 +481,57 @@ int hb_world_load(hb_world* w, const hb_chunk_pt* pts, size_t n) {
     std::lock_guard<std::mutex> lk(c->mu);
     HB_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
-    // queue_load (map.rs:69-75) ignores loaded chunks; the provider generates each requested position once
+    // queue_load (map.rs:69-75) ignores loaded chunks; the provider generates each requested position once.
+    // Positions are entered into the table as they are accepted (which also rejects repeats inside the batch) and
+    // taken out again if the batch does not fit.
+    for (size_t i = 0; i < n; ++i)
+        if (!coord_ok(pts[i].x) || !coord_ok(pts[i].y) || !coord_ok(pts[i].z))
+            return fail(HB_ERR_RANGE, "chunk %zu outside +-%d", i, HB_MAX_CHUNK_COORD);
     std::vector<hb_chunk_pt> fresh;
-    {
-        std::unordered_map<KeyXYZ, int32_t, KeyXYZHash> seen;
-        for (size_t i = 0; i < n; ++i) {
-            if (!coord_ok(pts[i].x) || !coord_ok(pts[i].y) || !coord_ok(pts[i].z))
-                return fail(HB_ERR_RANGE, "chunk %zu outside +-%d", i, HB_MAX_CHUNK_COORD);
-            const KeyXYZ k{pts[i].x, pts[i].y, pts[i].z};
-            if (w->map.count(k) || !seen.emplace(k, 0).second) continue;
-            fresh.push_back(pts[i]);
+    std::vector<int32_t> slots;
+    bool full = false;
+    for (size_t i = 0; i < n && !full; ++i) {
+        if (w->find(pts[i].x, pts[i].y, pts[i].z) >= 0) continue;
+        if (w->free_slots.empty()) { full = true; break; }
+        const int32_t slot = w->free_slots.back();
+        w->free_slots.pop_back();
+        w->map.insert(pts[i].x, pts[i].y, pts[i].z, slot);
+        fresh.push_back(pts[i]);
+        slots.push_back(slot);
+    }
+    if (full) {
+        size_t wanted = fresh.size();
+        for (size_t i = 0; i < n; ++i) wanted += w->find(pts[i].x, pts[i].y, pts[i].z) < 0;  // upper bound incl. repeats
+        for (size_t i = fresh.size(); i-- > 0;) {
+            w->map.erase(fresh[i].x, fresh[i].y, fresh[i].z);
+            w->free_slots.push_back(slots[i]);
         }
+        return fail(HB_ERR_CAPACITY, "world holds %zu of %zu chunks, about %zu more requested", w->map.size(), w->capacity, wanted);
     }
     const size_t m = fresh.size();
     if (m == 0) return HB_OK;
-    if (m > w->free_slots.size())
-        return fail(HB_ERR_CAPACITY, "world holds %zu of %zu chunks, %zu more requested", w->map.size(), w->capacity, m);
     // columns: all cy layers of one (cx, cz) share a heights tile
-    std::vector<int32_t> cols, colidx(m), slots(m);
+    std::vector<int32_t> cols, colidx(m);
     {
-        std::unordered_map<KeyXZ, int32_t, KeyXZHash> colmap;
+        SlotTable colmap;
+        colmap.init(m);
         for (size_t i = 0; i < m; ++i) {
-            auto ins = colmap.emplace(KeyXZ{fresh[i].x, fresh[i].z}, (int32_t)(cols.size() / 2));
-            if (ins.second) { cols.push_back(fresh[i].x); cols.push_back(fresh[i].z); }
-            colidx[i] = ins.first->second;
+            int32_t ci = colmap.find(fresh[i].x, 0, fresh[i].z);
+            if (ci < 0) {
+                ci = (int32_t)(cols.size() / 2);
+                colmap.insert(fresh[i].x, 0, fresh[i].z, ci);
+                cols.push_back(fresh[i].x);
+                cols.push_back(fresh[i].z);
+            }
+            colidx[i] = ci;
         }
     }
     const size_t ncol = cols.size() / 2;
     std::vector<uint8_t> is_new(w->capacity, 0);
     for (size_t i = 0; i < m; ++i) {
-        const int32_t slot = w->free_slots.back();
-        w->free_slots.pop_back();
-        slots[i] = slot;
-        is_new[slot] = 1;
-        w->map[KeyXYZ{fresh[i].x, fresh[i].y, fresh[i].z}] = slot;
-        w->slot_pt[slot] = fresh[i];
-        w->used[slot] = 1;
+        is_new[slots[i]] = 1;
+        w->slot_pt[slots[i]] = fresh[i];
+        w->used[slots[i]] = 1;
     }
     for (size_t i = 0; i < m; ++i) wire_neighbours(w, fresh[i], slots[i], true);
     // load_provided (map.rs:203-228): one cull per (new chunk, loaded face neighbour); a pair of two new chunks once
@@ -483,17 +570,16 @@ int hb_world_unload(hb_world* w, const hb_chunk_pt* pts, size_t n) {
     std::lock_guard<std::mutex> lk(c->mu);
     HB_CUDA(cudaSetDevice(c->device));
     for (size_t i = 0; i < n; ++i) {
-        auto it = w->map.find(KeyXYZ{pts[i].x, pts[i].y, pts[i].z});
-        if (it == w->map.end()) continue;
-        const int32_t slot = it->second;
-        w->map.erase(it);
+        const int32_t slot = w->find(pts[i].x, pts[i].y, pts[i].z);
+        if (slot < 0) continue;
+        w->map.erase(pts[i].x, pts[i].y, pts[i].z);
         wire_neighbours(w, pts[i], slot, false);
         for (int k = 0; k < 27; ++k) w->h_nbr[(size_t)slot * 27 + k] = -1;
         w->used[slot] = 0;
         w->epoch[slot]++;
         w->stale[slot] = w->touched[slot] = w->remesh[slot] = 0;
-        HB_CUDA(cudaMemsetAsync(w->d_touched.as<uint32_t>() + (size_t)slot * HB_CHUNK_AREA, 0, HB_CHUNK_AREA * sizeof(uint32_t), c->stream));
-        HB_CUDA(cudaMemsetAsync(w->d_pending.as<uint32_t>() + (size_t)slot * HB_CHUNK_AREA, 0, HB_CHUNK_AREA * sizeof(uint32_t), c->stream));
+        // the slot's update sets need no clearing: a freed slot is never a sync candidate, the next load overwrites
+        // `touched` completely (k_fill_cubes) and the sync after it overwrites `pending`
         w->free_slots.push_back(slot);
     }
     HB_CUDA(cudaStreamSynchronize(c->stream));
