@@ -1,6 +1,6 @@
 """Does pinned-buffer NUMA placement explain the ~100 GB/s aggregate device->host ceiling seen beyond 2 GPUs?
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/probe_numa.py
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/probe_d2h_multi.py
 
 Every rank copies 2 GiB device->pinned host 6 times concurrently with the others, (a) with the pinned buffer allocated
 wherever the process happens to run, (b) after pinning the process to the CPUs of its GPU's NUMA node (read from
