@@ -795,9 +795,15 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
     if (EMIT) load_tables(sm, tb);
     const RelHeight rel{(long long)r.cy0 * 32, 32 * r.ncy + 8};
     const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
-    for (int colw = blockIdx.x; colw < ncols; colw += gridDim.x) {
+    __shared__ int s_col;
+    for (int colw = blockIdx.x;;) {
+        if (colw >= ncols) break;
         const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
         __syncthreads();  // previous column's readers of sm.hts / sm.red are done
+        // next column: drawn from a ticket counter (total[3], zeroed by the launch wrapper) so that CTAs that meet
+        // cheap columns take more of them; tickets are handed out in column order, which keeps all CTAs writing inside
+        // one moving window of the output
+        if (tid == 0) s_col = (int)gridDim.x + (int)atomicAdd(total + 3, 1ULL);
         int cmax = INT32_MIN, hmin = INT32_MAX, emin = INT32_MAX;
         const TileRegs tile_regs = fetch_heights_tile(r, heights, ix, iz);
         // The chunk hashes (SipHash-1-3, ~200 dependent 64-bit operations) of all layers of this column, one lane per
@@ -865,6 +871,7 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
                                                mats, EMIT ? out + off * 25ULL : nullptr);
             if (!EMIT && tid == 0) counts[chunk] = q;
         }
+        colw = s_col;  // written before this column's first barrier, read after several more
     }
     if (EMIT) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
 }
@@ -1039,9 +1046,12 @@ cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, 
     if (ctas_per_sm < 1 || ctas_per_sm > kCtasPerSm) ctas_per_sm = kCtasPerSm;
     size_t grid = (size_t)num_sms() * ctas_per_sm;  // persistent CTAs
     if (grid > ncols) grid = ncols;
-    if (emit)
+    if (emit) {
+        const cudaError_t e = cudaMemsetAsync(d_total + 3, 0, sizeof(uint64_t), s);  // the column ticket counter
+        if (e != cudaSuccess) return e;
         k_mesh_region<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
                                                           (float*)d_out, capacity, (u64*)d_total);
+    }
     else
         k_count_region<<<(unsigned)std::min<size_t>(ncols, (size_t)num_sms() * 8), kT, 0, s>>>(r, d_heights, d_counts);
     return cudaGetLastError();
