@@ -109,17 +109,7 @@ struct hb_region_plan {
     uint64_t capacity = 0;
     Buf d_heights, d_counts, d_offsets, d_scan, d_total, d_out, d_ids;
     Buf h_total;
-    // pipelined enqueue: the ALU-bound heights/count kernels of sub-slab s+1 run on `side` while the
-    // HBM-bound emit kernel of sub-slab s runs on the caller's stream
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr;
-    std::vector<cudaEvent_t> ev_ready;
     hb_region_plan() { h_total.pinned = true; }
-    ~hb_region_plan() {
-        for (cudaEvent_t e : ev_ready) cudaEventDestroy(e);
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        if (side) cudaStreamDestroy(side);
-    }
     size_t n_chunks() const { return (size_t)(dev.ix_end - dev.ix_begin) * dev.ncz * dev.ncy; }
 };
 
@@ -159,74 +149,9 @@ int plan_alloc(hb_region_plan* p, int32_t max_width) {
     return HB_OK;
 }
 
-constexpr int kMaxSubSlabs = 8;
-
-// HEIGHTS+COUNT+SCAN+EMIT of one plan, software-pipelined over x sub-slabs on two streams.
-int plan_enqueue_pipelined(hb_region_plan* p, cudaStream_t s) {
-    hb_ctx* c = p->ctx;
-    const RegionDev full = p->dev;
-    const int width = full.ix_end - full.ix_begin;
-    const int nsub = std::min(kMaxSubSlabs, width);
-    if (!p->side) {
-        HB_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
-        HB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-    }
-    while ((int)p->ev_ready.size() < nsub) {
-        cudaEvent_t e;
-        HB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        p->ev_ready.push_back(e);
-    }
-    auto sub_begin = [&](int k) { return full.ix_begin + (int)((long long)width * k / nsub); };
-    // heights-buffer columns needed by sub-slab k (its own ix range; the plan's apron goes with the first/last)
-    auto hcol_begin = [&](int k) { return (size_t)((k == 0 ? full.hx_begin : sub_begin(k)) - full.hx_begin) * full.ncz; };
-    auto hcol_end = [&](int k) { return (size_t)((k == nsub - 1 ? full.hx_end : sub_begin(k + 1)) - full.hx_begin) * full.ncz; };
-    auto sub_dev = [&](int k) { RegionDev d = full; d.ix_begin = sub_begin(k); d.ix_end = sub_begin(k + 1); return d; };
-    auto chunk_off = [&](int k) { return (size_t)(sub_begin(k) - full.ix_begin) * full.ncz * full.ncy; };
-    int32_t* H = p->d_heights.as<int32_t>();
-    uint32_t* counts = p->d_counts.as<uint32_t>();
-    uint64_t* offsets = p->d_offsets.as<uint64_t>();
-
-    HB_CUDA(cudaEventRecord(p->ev_fork, s));
-    HB_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-    HB_CUDA(cudaMemsetAsync(p->d_total.p, 0, 4 * sizeof(uint64_t), s));
-    // side stream: H0, H1, C0, ready0, H2, C1, ready1, ... (count/emit of sub-slab k read heights of k-1..k+1)
-    HB_CUDA(launch_heights_region(p->side, c->world, full, H, hcol_begin(0), hcol_end(0)));
-    for (int k = 0; k < nsub; ++k) {
-        if (k + 1 < nsub) HB_CUDA(launch_heights_region(p->side, c->world, full, H, hcol_begin(k + 1), hcol_end(k + 1)));
-        HB_CUDA(launch_mesh_region(p->side, false, c->tables, c->d_mats, sub_dev(k), H, counts + chunk_off(k), nullptr,
-                                   nullptr, 0, p->d_total.as<uint64_t>()));
-        HB_CUDA(cudaEventRecord(p->ev_ready[k], p->side));
-    }
-    // caller's stream: scan (chained offsets) + emit per sub-slab
-    for (int k = 0; k < nsub; ++k) {
-        const RegionDev d = sub_dev(k);
-        const size_t nch = (size_t)(d.ix_end - d.ix_begin) * d.ncz * d.ncy;
-        HB_CUDA(cudaStreamWaitEvent(s, p->ev_ready[k], 0));
-        HB_CUDA(launch_scan(s, counts + chunk_off(k), nch, offsets + chunk_off(k), p->d_scan.p, p->d_total.as<uint64_t>(), true));
-        // 3 of the 4 possible CTAs per SM: leaves a quarter of the register file to the side stream's kernels
-        HB_CUDA(launch_mesh_region(s, true, c->tables, c->d_mats, d, H, counts + chunk_off(k), offsets + chunk_off(k),
-                                   p->d_out.as<hb_instance3d>(), p->capacity, p->d_total.as<uint64_t>(), 3));
-    }
-    return HB_OK;
-}
-
-// Off by default: measured on B200 (config 4) the two-stream overlap gains only ~3 % (6.25 vs 6.45 ms at equal
-// occupancy) and costs 5 % against the 4-CTA/SM emit grid, because the co-resident heights CTAs run at a
-// quarter of their occupancy and become the critical path.  HB_PIPELINE=1 enables it for experiments.
-bool pipelining_enabled() {
-    static const int v = [] { const char* e = getenv("HB_PIPELINE"); return e ? atoi(e) : 0; }();
-    return v != 0;
-}
-
 int plan_enqueue(hb_region_plan* p, int stages, cudaStream_t s) {
     hb_ctx* c = p->ctx;
     const size_t hcols = (size_t)(p->dev.hx_end - p->dev.hx_begin) * p->dev.ncz;
-    if ((stages & HB_STAGE_ALL_MESH) == HB_STAGE_ALL_MESH && pipelining_enabled() && p->dev.ix_end - p->dev.ix_begin >= 2) {
-        if (!p->d_out.p) return fail(HB_ERR_INVALID, "plan has no instance buffer");
-        int rc = plan_enqueue_pipelined(p, s);
-        if (rc != HB_OK) return rc;
-        stages &= ~HB_STAGE_ALL_MESH;
-    }
     if (stages & HB_STAGE_HEIGHTS) HB_CUDA(launch_heights_region(s, c->world, p->dev, p->d_heights.as<int32_t>(), 0, hcols));
     if (stages & HB_STAGE_COUNT) {
         HB_CUDA(cudaMemsetAsync(p->d_total.p, 0, 4 * sizeof(uint64_t), s));
@@ -699,11 +624,6 @@ int hb_region_plan_enqueue(hb_region_plan* p, int stages, void* stream) {
 int hb_region_plan_launches(const hb_region_plan* p, int stages) {
     if (!p) return 0;
     int n = 0;
-    if ((stages & HB_STAGE_ALL_MESH) == HB_STAGE_ALL_MESH && pipelining_enabled() && p->dev.ix_end - p->dev.ix_begin >= 2) {
-        const int nsub = std::min(kMaxSubSlabs, p->dev.ix_end - p->dev.ix_begin);
-        n += nsub * (1 + 1 + 3 + 1);  // heights, count, 3 scan kernels, emit per sub-slab
-        stages &= ~HB_STAGE_ALL_MESH;
-    }
     if (stages & HB_STAGE_HEIGHTS) n += 1;
     if (stages & HB_STAGE_COUNT) n += 1;
     if (stages & HB_STAGE_SCAN) n += 3;

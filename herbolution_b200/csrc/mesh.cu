@@ -721,7 +721,7 @@ __device__ __forceinline__ void load_heights_tile(const RegionDev& r, const int3
 //   down   : r > 0 and the chunk below is absent            (inside the terrain y-1 is always solid)
 // which is exactly what k_mesh_region<EMIT> emits from the occupancy tile (parity tests cover both).
 __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const int32_t* __restrict__ heights,
-                                                      uint32_t* __restrict__ counts) {
+                                                      uint32_t* __restrict__ counts, u64* __restrict__ ticket) {
     __shared__ uint32_t s_acc[kT / 32][32];  // per warp, per layer of the current group of 32 layers
     __shared__ int s_h[kTileN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -729,15 +729,19 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
     const int last = r.ncy - 1;
     const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
     // the next column's tile is fetched into registers while the current one is counted
+    __shared__ int s_next;
     TileRegs next{};
     if ((int)blockIdx.x < ncols) next = fetch_heights_tile(r, heights, r.ix_begin + (int)blockIdx.x / r.ncz, (int)blockIdx.x % r.ncz);
-    for (int colw = blockIdx.x; colw < ncols; colw += gridDim.x) {
+    for (int colw = blockIdx.x; colw < ncols;) {
     int cmax = INT32_MIN, hmin = INT32_MAX, emin = INT32_MAX;
-    __syncthreads();  // previous column's readers of s_h are done
+    __syncthreads();  // previous column's readers of s_h / s_next are done
+    // columns are drawn from a ticket counter (`ticket`, zeroed by the launch wrapper): the per-column cost follows
+    // the terrain (how many layers a column's surface spans), and a static stride left a tail of late CTAs
+    if (tid == 0) s_next = (int)gridDim.x + (int)atomicAdd(ticket, 1ULL);
     store_heights_tile(next, s_h, cmax, hmin, emin, rel);
-    const int coln = colw + (int)gridDim.x;
-    if (coln < ncols) next = fetch_heights_tile(r, heights, r.ix_begin + coln / r.ncz, coln % r.ncz);
     __syncthreads();
+    const int coln = s_next;
+    if (coln < ncols) next = fetch_heights_tile(r, heights, r.ix_begin + coln / r.ncz, coln % r.ncz);
     for (int iy0 = 0; iy0 < r.ncy; iy0 += 32) {
         const int nl = min(32, r.ncy - iy0);
         s_acc[warp][lane] = 0;
@@ -782,6 +786,7 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
         }
         __syncthreads();
     }
+    colw = coln;
     }  // persistent column loop
 }
 
@@ -1052,8 +1057,11 @@ cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, 
         k_mesh_region<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
                                                           (float*)d_out, capacity, (u64*)d_total);
     }
-    else
-        k_count_region<<<(unsigned)std::min<size_t>(ncols, (size_t)num_sms() * 8), kT, 0, s>>>(r, d_heights, d_counts);
+    else {
+        const cudaError_t e = cudaMemsetAsync(d_total + 3, 0, sizeof(uint64_t), s);  // the column ticket counter
+        if (e != cudaSuccess) return e;
+        k_count_region<<<(unsigned)std::min<size_t>(ncols, (size_t)num_sms() * 8), kT, 0, s>>>(r, d_heights, d_counts, (u64*)d_total + 3);
+    }
     return cudaGetLastError();
 }
 
