@@ -35,8 +35,11 @@ __global__ void __launch_bounds__(kCT) k_rle_encode(const uint16_t* __restrict__
     // EMIT: a chunk's records are assembled here and leave as coalesced 32-bit stores (terrain chunks have about
     // 1 100 records = 3.4 KB); a chunk with more than kStageBytes of records falls back to direct byte stores
     __shared__ uint32_t s_stage[EMIT ? kStageBytes / 4 : 1];
+    __shared__ unsigned long long s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+    // chunks are drawn from a ticket counter (total[3], zeroed by the launch wrapper): their cost follows the number of
+    // runs, and a static stride leaves a tail of late CTAs
+    for (size_t chunk = blockIdx.x; chunk < n;) {
         const uint16_t* src = ids + chunk * HB_CHUNK_VOLUME + tid * kSeg;
         // run-start mask of the segment: bit i set iff ids[i] != ids[i-1]; position 0 always starts a run (the
         // encoder's initial (None, 0) state either merges with a leading None run or is closed as an empty record)
@@ -75,7 +78,10 @@ __global__ void __launch_bounds__(kCT) k_rle_encode(const uint16_t* __restrict__
         if (lane == 31) after = HB_CHUNK_VOLUME;
         __syncthreads();  // previous chunk's readers of the shared arrays are done
         if (lane == 0) s_wmin[warp] = incl;
+        if (tid == 0) s_next = (unsigned long long)gridDim.x + atomicAdd(total + 3, 1ULL);
         __syncthreads();
+        const size_t this_chunk = chunk;
+        chunk = (size_t)s_next;  // the loop's `continue`s below move on to the next ticket
         for (int w2 = warp + 1; w2 < kCT / 32; ++w2) after = min(after, s_wmin[w2]);
 
         // records owned by this thread
@@ -114,10 +120,10 @@ __global__ void __launch_bounds__(kCT) k_rle_encode(const uint16_t* __restrict__
             all += s_wsum[w2];
         }
         if (!EMIT) {
-            if (tid == 0) counts[chunk] = all;
+            if (tid == 0) counts[this_chunk] = all;
             continue;
         }
-        const u64 off = offsets[chunk];
+        const u64 off = offsets[this_chunk];
         if (off + (((u64)all + 3ULL) & ~3ULL) > capacity_records) {
             if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
             continue;
@@ -215,6 +221,8 @@ cudaError_t launch_rle_encode(cudaStream_t s, bool emit, const uint16_t* d_ids, 
     if (n == 0) return cudaSuccess;
     size_t grid = (size_t)num_sms() * 8;
     if (grid > n) grid = n;
+    const cudaError_t e0 = cudaMemsetAsync(d_total + 3, 0, sizeof(uint64_t), s);  // the chunk ticket counter
+    if (e0 != cudaSuccess) return e0;
     if (emit) k_rle_encode<true><<<(unsigned)grid, kCT, 0, s>>>(d_ids, n, d_counts, (const u64*)d_offsets, d_out, capacity_records, (u64*)d_total);
     else k_rle_encode<false><<<(unsigned)grid, kCT, 0, s>>>(d_ids, n, d_counts, nullptr, nullptr, 0, (u64*)d_total);
     return cudaGetLastError();
