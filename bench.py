@@ -281,8 +281,8 @@ def main():
     ncols_noise = reg.ncx * reg.ncz
     noise_tflops = flops_per_column * ncols_noise / (stage_ms["heights"] * 1e-3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture of this exact
-    # workload (profiles/r1_ncu_full_summary.csv: 0.320 GB read + 17.480 GB written per launch)
-    traffic = 17.800e9 if (cols == 256 and world == 1) else None
+    # workload (profiles/r1_ncu_full_summary.csv: 0.274 GB read + 17.480 GB written per launch)
+    traffic = 17.755e9 if (cols == 256 and world == 1) else None
     roofline = {"kernel": "k_mesh_region<EMIT=true>", "bound": "hbm", "achieved": emit_gbs, "peak": peak, "unit": "GB/s",
                 "frac": emit_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": emit_bytes, "avg_launch_ms": stage_ms["emit"],
