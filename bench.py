@@ -77,8 +77,8 @@ class ClockSampler:
 
     nvidia-smi is started before the warm-up (it needs ~100 ms to come up) and polls every 20 ms; every line is
     time-stamped on arrival.  stop() reports the samples that arrived between begin() and end() -- the timed
-    region -- and, if that region was too short to catch one, the samples up to stop(), which the caller places
-    after the per-stage timing loops that run the same kernels back to back ("window" says which)."""
+    region -- and, if that region was too short to catch one, every sample since begin() up to stop() ("window"
+    says which)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -126,7 +126,7 @@ class ClockSampler:
         window = "timed region"
         if not timed:
             timed = [ln for ts, ln in self.lines if t0 <= ts <= t_stop]
-            window = "timed region + per-stage timing loops (timed region shorter than one sample period)"
+            window = "begin() .. stop() (timed region shorter than one sample period)"
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in timed:
@@ -248,30 +248,25 @@ def main():
     res = plan.result(stream)
     n_chunks, quads, span = res["n_chunks"], res["quads"], res["span"]
 
+    # The timed region: K steps, each enqueued stage by stage with a CUDA event between the stages (all on the
+    # launching stream), so the per-kernel durations behind the roofline come from the timed steps themselves.
+    stage_names = [("heights", hb.STAGE_HEIGHTS), ("count", hb.STAGE_COUNT), ("scan", hb.STAGE_SCAN), ("emit", hb.STAGE_EMIT)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)] for _ in range(steps)]
     barrier()
     sampler.begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(tstream)
-    for _ in range(steps):
-        plan.enqueue(ALL, stream)
-    ev1.record(tstream)
-    barrier()
-    sampler.end()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    total_chunks = sum_over_ranks(float(n_chunks))
-    value = total_chunks * steps / (ms_total * 1e-3)
-
-    # per-kernel durations (same stream, CUDA events), for the roofline of the dominant kernel
-    stage_names = [("heights", hb.STAGE_HEIGHTS), ("count", hb.STAGE_COUNT), ("scan", hb.STAGE_SCAN), ("emit", hb.STAGE_EMIT)]
-    reps = 5
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)] for _ in range(reps)]
-    for r in range(reps):
+    for r in range(steps):
         evs[r][0].record(tstream)
         for i, (_, st) in enumerate(stage_names):
             plan.enqueue(st, stream)
             evs[r][i + 1].record(tstream)
-    torch.cuda.synchronize()
+    barrier()
+    sampler.end()
+    ev0, ev1 = evs[0][0], evs[-1][-1]
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    total_chunks = sum_over_ranks(float(n_chunks))
+    value = total_chunks * steps / (ms_total * 1e-3)
     clocks = sampler.stop()
+    reps = steps
     stage_ms = {nm: statistics.mean(evs[r][i].elapsed_time(evs[r][i + 1]) for r in range(reps))
                 for i, (nm, _) in enumerate(stage_names)}
     peak, peak_src = measured_peaks()
