@@ -316,7 +316,7 @@ HB_API int hb_rle_encode(hb_ctx *ctx, const uint16_t *ids, size_t n, uint8_t *ou
 HB_API int hb_rle_decode(hb_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, const uint64_t *offsets,
                   const uint32_t *sizes, size_t n, uint16_t *out_ids);
 /* Device-pointer form of the encoder: counts -> offsets (in records; x3 for bytes) -> records if d_out.
- * d_scan_workspace as for hb_dev_mesh; d_total[0] = span in records, d_total[2] & 1 = capacity exceeded.  d_ids must be
+ * d_scan_workspace as for hb_dev_mesh; d_total (4 x u64): [0] = span in records, [2] & 1 = capacity exceeded, [3] = scratch (work tickets).  d_ids must be
  * 16-byte aligned and d_out 4-byte aligned (any cudaMalloc pointer is); d_out should be zeroed first if the gaps matter. */
 HB_API int hb_dev_rle_encode(hb_ctx *ctx, void *stream, const uint16_t *d_ids, size_t n, void *d_scan_workspace,
                       uint8_t *d_out, uint64_t capacity_records, uint64_t *d_offsets, uint32_t *d_counts,
