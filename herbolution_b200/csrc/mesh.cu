@@ -335,7 +335,7 @@ __device__ __forceinline__ void load_tables(MeshSmem& sm, const MeshTables& tb) 
 // K3a: u16 ids -> 1 bit per voxel (bitmap[c] for column c = x*32+z, bit y) + a per-chunk summary
 // word: bit0 any solid, bit1 all solid, bit(2+f) boundary slab at face f entirely solid.
 // One 128-bit streaming load per thread per 8 voxels; the chunk's 64 KiB are read exactly once.
-__global__ void __launch_bounds__(kT) k_pack(const uint16_t* __restrict__ ids, size_t n, int n_materials,
+__global__ void __launch_bounds__(kT, 3) k_pack(const uint16_t* __restrict__ ids, size_t n, int n_materials,
                                              uint32_t* __restrict__ bitmaps, uint32_t* __restrict__ summary,
                                              u64* __restrict__ total) {
     __shared__ uint32_t s_red[8][8];
@@ -343,17 +343,26 @@ __global__ void __launch_bounds__(kT) k_pack(const uint16_t* __restrict__ ids, s
     for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         const uint4* src = reinterpret_cast<const uint4*>(ids + chunk * HB_CHUNK_VOLUME);
         uint32_t any = 0, all = ~0u, fE = ~0u, fW = ~0u, fN = ~0u, fS = ~0u, bad = 0;
-        const uint32_t nm2 = (uint32_t)n_materials * 0x10001u;  // palette size in both halfwords
+        // Two ids per 32-bit word, tested with plain integer SWAR (the __v*2 video intrinsics are emulated with long
+        // sequences on this architecture).  With guard = 0x8000 in both halfwords:
+        //   nonzero:  ((w & 0x7FFF7FFF) + 0x7FFF7FFF) | w   has the halfword's top bit set iff the id is non-zero
+        //   in range: (n_materials | guard) - w             keeps the halfword's top bit iff id <= n_materials (ids with
+        //             their own top bit set are flagged separately; a borrow can only start in a halfword that is
+        //             already out of range)
+        const uint32_t guard = 0x80008000u, nmg = ((uint32_t)n_materials * 0x10001u) | guard;
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
             const int u = it * kT + tid;
             const uint4 v = __ldg(src + u);
-            // per-halfword SIMD compares: 0xFFFF where the id is non-zero / above the palette size
-            const uint32_t z0 = __vcmpne2(v.x, 0u), z1 = __vcmpne2(v.y, 0u), z2 = __vcmpne2(v.z, 0u), z3 = __vcmpne2(v.w, 0u);
-            bad |= __vcmpgtu2(v.x, nm2) | __vcmpgtu2(v.y, nm2) | __vcmpgtu2(v.z, nm2) | __vcmpgtu2(v.w, nm2);
-            // bit 0 and bit 16 of each compare word -> bits 2k and 2k+1 of the 8-bit occupancy mask
-            const uint32_t m8 = ((z0 & 1u) | ((z0 >> 15) & 2u)) | (((z1 & 1u) | ((z1 >> 15) & 2u)) << 2) |
-                                (((z2 & 1u) | ((z2 >> 15) & 2u)) << 4) | (((z3 & 1u) | ((z3 >> 15) & 2u)) << 6);
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            uint32_t t = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t y = (((w4[k] & 0x7FFF7FFFu) + 0x7FFF7FFFu) | w4[k]) & guard;
+                t |= y >> (15 - 2 * k);  // low id -> bit 2k, high id -> bit 16 + 2k
+                bad |= (~(nmg - w4[k]) | w4[k]) & guard;
+            }
+            const uint32_t m8 = (t & 0x55u) | ((t >> 15) & 0xAAu);  // bit j = id j of this 8-id unit is non-zero
             uint32_t w = m8 << ((u & 3) * 8);
             w |= __shfl_xor_sync(0xffffffffu, w, 1);
             w |= __shfl_xor_sync(0xffffffffu, w, 2);
