@@ -323,3 +323,20 @@ def test_server_chunk_map_mirror_and_extreme_coordinates(ctx):
     assert e.value.code == hb._lib.HB_ERR_RANGE
     m.close()
     ora.close()
+
+
+def test_readme_example_runs(ctx):
+    """The usage snippet of README.md, kept honest."""
+    gen = ctx.generate([(0, 0, 0), (0, -1, 0)], want_cubes=True)
+    mesh = ctx.mesh([(0, 0, 0), (0, -1, 0)], gen["ids"])
+    assert mesh["counts"].sum() > 0 and gen["cubes"].shape[0] == 2
+    tot = ctx.generate_mesh_region(hb.Region(-8, -8, 16, 16, -3, 6), sink=lambda first, off, cnt, inst, ids: None)
+    assert tot["chunks"] == 16 * 16 * 6 and tot["quads"] > 0
+    world = hb.ServerChunkMap(ctx, capacity=64)
+    world.queue_load((0, 0, 0))
+    world.update()
+    world.set_cube((3, 5, 7), 0)
+    updates = world.sync_with_client()
+    meshes = world.remesh()
+    assert set(updates) == set(meshes) == {(0, 0, 0)}
+    world.close()
