@@ -27,7 +27,9 @@ HB_ERR_RANGE = -4
 HB_ERR_NOMEM = -5
 
 STAGE_HEIGHTS, STAGE_COUNT, STAGE_SCAN, STAGE_EMIT, STAGE_FILL = 1, 2, 4, 8, 16
+STAGE_EMIT_PACKED = 32
 STAGE_ALL_MESH = 15
+TRANSPORT_PACKED, TRANSPORT_INSTANCES = 0, 1
 NOISE_FBM, NOISE_RIDGE, NOISE_TURBULENCE, NOISE_GRADIENT = 0, 1, 2, 3
 
 # == hb_chunk_pt / lib::point::ChunkPt
@@ -102,6 +104,12 @@ PROTOTYPES = {
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_generate_mesh_region_slab": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_int, REGION_SINK,
                                                C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "hb_set_region_transport": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hb_set_host_threads": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hb_generate_mesh_region_packed": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_int, REGION_SINK,
+                                                 C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "hb_expand_quads": (C.c_int, [C.c_void_p, ChunkPtC, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "hb_region_plan_packed": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "hb_region_plan_create": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_uint64, C.c_int,
                                         C.POINTER(C.c_void_p)]),
     "hb_region_plan_destroy": (None, [C.c_void_p]),
@@ -123,7 +131,7 @@ PROTOTYPES = {
     "hb_world_set_cubes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "hb_world_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
     "hb_world_fetch_updates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
-                                         C.c_uint64]),
+                                         C.c_uint64, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
     "hb_world_remesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                   C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
     "hb_world_remesh_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,

@@ -7,6 +7,7 @@ generator.py / mesher.py on top of this.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Callable, Optional
 
 import numpy as np
@@ -56,6 +57,12 @@ class RegionPlan:
                                               *[C.byref(x) for x in p]))
         return {"n_chunks": n.value, "quads": q.value, "span": span.value, "d_instances": p[0].value,
                 "d_offsets": p[1].value, "d_counts": p[2].value, "d_ids": p[3].value, "d_heights": p[4].value}
+
+    def packed_ptr(self) -> int:
+        """Raw device pointer of the hb_packed_quad words written by STAGE_EMIT_PACKED (0 before the first one)."""
+        p = C.c_void_p()
+        check(self._lib.hb_region_plan_packed(self._h, C.byref(p)))
+        return p.value or 0
 
     def close(self) -> None:
         if self._h:
@@ -211,12 +218,68 @@ class Context:
                                                      C.byref(tc), C.byref(tq)))
         return {"chunks": tc.value, "quads": tq.value}
 
+    def set_region_transport(self, transport: int) -> None:
+        """_lib.TRANSPORT_PACKED (default: 4 B/quad over the link, host threads rebuild the records) or
+        TRANSPORT_INSTANCES (100 B/quad copied as they are)."""
+        check(self._lib.hb_set_region_transport(self._h, int(transport)))
+
+    def set_host_threads(self, n: int) -> None:
+        check(self._lib.hb_set_host_threads(self._h, int(n)))
+
+    def generate_mesh_region_packed(self, region: Region, want_ids: bool = False,
+                                    sink: Optional[Callable[..., None]] = None, ix_begin: int = 0,
+                                    ix_end: Optional[int] = None) -> dict:
+        """Like generate_mesh_region, but sink(first_chunk, offsets, counts, packed u32[span], ids or None) receives
+        the hb_packed_quad words; expand them with expand_quads."""
+
+        def _cb(_user, first, n, p_off, p_cnt, p_q, span, p_ids):
+            if sink is None:
+                return
+            off = np.frombuffer((C.c_uint64 * n).from_address(p_off), dtype=np.uint64) if n else np.zeros(0, np.uint64)
+            cnt = np.frombuffer((C.c_uint32 * n).from_address(p_cnt), dtype=np.uint32) if n else np.zeros(0, np.uint32)
+            q = np.frombuffer((C.c_uint32 * span).from_address(p_q), dtype=np.uint32) if span else np.zeros(0, np.uint32)
+            ids = None
+            if p_ids:
+                ids = np.frombuffer((C.c_uint16 * (n * CHUNK_VOLUME)).from_address(p_ids), dtype=np.uint16)
+                ids = ids.reshape(n, CHUNK_VOLUME)
+            sink(first, off, cnt, q, ids)
+
+        cb = _lib.REGION_SINK(_cb)
+        tc, tq = C.c_uint64(0), C.c_uint64(0)
+        ix_end = region.ncx if ix_end is None else ix_end
+        check(self._lib.hb_generate_mesh_region_packed(self._h, C.byref(region), ix_begin, ix_end, int(want_ids), cb, None,
+                                                       C.byref(tc), C.byref(tq)))
+        return {"chunks": tc.value, "quads": tq.value}
+
+    def expand_quads(self, position, packed: np.ndarray) -> np.ndarray:
+        """hb_expand_quads: the Instance3d records of one chunk's packed quads."""
+        x, y, z = (int(v) for v in position)
+        packed = np.ascontiguousarray(packed, dtype=np.uint32).reshape(-1)
+        n = packed.shape[0]
+        raw = np.zeros(((n + 3) & ~3) * 100 + 16, dtype=np.uint8)
+        o = (-raw.ctypes.data) & 15
+        out = raw[o:o + ((n + 3) & ~3) * 100].view(INSTANCE_DTYPE)
+        check(self._lib.hb_expand_quads(self._h, _lib.ChunkPtC(x, y, z), ptr(packed), n, C.c_void_p(out.ctypes.data)))
+        return out[:n]
+
     def download(self, dev_ptr: int, dtype, count: int) -> np.ndarray:
         """Blocking device->host copy of `count` items at a raw device pointer (plan results)."""
         out = np.empty(count, dtype=dtype)
         if count:
             check(self._lib.hb_dev_download(self._h, ptr(out), C.c_void_p(dev_ptr), out.nbytes))
         return out
+
+    def pinned_empty(self, count: int, dtype) -> np.ndarray:
+        """Uninitialised array in pinned host memory (hb_host_alloc); freed when the array is garbage-collected."""
+        dt = np.dtype(dtype)
+        nbytes = max(1, count * dt.itemsize)
+        p = C.c_void_p()
+        check(self._lib.hb_host_alloc(self._h, nbytes, C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt, count=count)
+        lib = self._lib
+        weakref.finalize(buf, lib.hb_host_free, None, C.c_void_p(p.value))
+        return arr
 
     def region_plan(self, region: Region, **kw) -> RegionPlan:
         return RegionPlan(self, region, **kw)

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <mutex>
@@ -31,6 +32,38 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+
+int copy_to_host(hb_ctx* c, cudaStream_t s, void* dst, const void* d_src, size_t bytes) {
+    if (bytes == 0) return HB_OK;
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // an unregistered pointer is not an error here
+    if (pinned) {
+        HB_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
+        HB_CUDA(cudaStreamSynchronize(s));
+        return HB_OK;
+    }
+    const size_t piece = (size_t)16 << 20;
+    for (int b = 0; b < 2; ++b) {
+        HB_CUDA(c->h_bounce[b].reserve(piece));
+        if (!c->ev_bounce[b]) HB_CUDA(cudaEventCreateWithFlags(&c->ev_bounce[b], cudaEventDisableTiming));
+    }
+    const size_t np = (bytes + piece - 1) / piece;
+    auto issue = [&](size_t k) -> cudaError_t {
+        const size_t o = k * piece, len = std::min(piece, bytes - o);
+        cudaError_t e = cudaMemcpyAsync(c->h_bounce[k & 1].p, static_cast<const char*>(d_src) + o, len, cudaMemcpyDeviceToHost, s);
+        return e != cudaSuccess ? e : cudaEventRecord(c->ev_bounce[k & 1], s);
+    };
+    HB_CUDA(issue(0));
+    for (size_t k = 0; k < np; ++k) {
+        if (k + 1 < np) HB_CUDA(issue(k + 1));
+        HB_CUDA(cudaEventSynchronize(c->ev_bounce[k & 1]));
+        const size_t o = k * piece, len = std::min(piece, bytes - o);
+        memcpy(static_cast<char*>(dst) + o, c->h_bounce[k & 1].p, len);
+    }
+    return HB_OK;
+}
+
 }  // namespace hb
 
 namespace {
@@ -107,7 +140,7 @@ struct hb_region_plan {
     int want_ids = 0;
     size_t max_chunks = 0, max_hcols = 0;
     uint64_t capacity = 0;
-    Buf d_heights, d_counts, d_offsets, d_scan, d_total, d_out, d_ids;
+    Buf d_heights, d_counts, d_offsets, d_scan, d_total, d_out, d_ids, d_packed;
     Buf h_total;
     hb_region_plan() { h_total.pinned = true; }
     size_t n_chunks() const { return (size_t)(dev.ix_end - dev.ix_begin) * dev.ncz * dev.ncy; }
@@ -167,6 +200,12 @@ int plan_enqueue(hb_region_plan* p, int stages, cudaStream_t s) {
                                    p->d_counts.as<uint32_t>(), p->d_offsets.as<uint64_t>(),
                                    p->d_out.as<hb_instance3d>(), p->capacity, p->d_total.as<uint64_t>()));
     }
+    if (stages & HB_STAGE_EMIT_PACKED) {
+        HB_CUDA(p->d_packed.reserve(std::max<uint64_t>(p->capacity, 4) * sizeof(hb_packed_quad)));
+        HB_CUDA(launch_mesh_region(s, true, c->tables, c->d_mats, p->dev, p->d_heights.as<int32_t>(),
+                                   p->d_counts.as<uint32_t>(), p->d_offsets.as<uint64_t>(), p->d_packed.p, p->capacity,
+                                   p->d_total.as<uint64_t>(), 0, true));
+    }
     if (stages & HB_STAGE_FILL) {
         if (!p->want_ids) return fail(HB_ERR_INVALID, "plan was created without want_ids");
         HB_CUDA(launch_fill_region(s, p->dev, p->d_heights.as<int32_t>(), p->d_ids.as<uint16_t>()));
@@ -201,15 +240,19 @@ int hb_create(int device, hb_ctx** out) {
     hb_ctx* c = new (std::nothrow) hb_ctx();
     if (!c) return fail(HB_ERR_NOMEM, "out of host memory");
     c->device = device;
-    HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    HB_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     c->seed = 0;
     c->world = WorldDev{0, 0.001f, 6, 2.0f, 0.6f};
     for (int f = 0; f < 6; ++f) face_matrix(f, c->tables.face_mat[f]);
     for (int k = 0; k < 4; ++k) c->tables.ao_lut[k] = ao_value(k);
     default_materials(&c->mats);
-    HB_CUDA(cudaMalloc(&c->d_mats, sizeof(MaterialsDev)));
-    HB_CUDA(cudaMemcpy(c->d_mats, &c->mats, sizeof(MaterialsDev), cudaMemcpyHostToDevice));
+    cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_mats, sizeof(MaterialsDev));
+    if (ce == cudaSuccess) ce = cudaMemcpy(c->d_mats, &c->mats, sizeof(MaterialsDev), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        hb_destroy(c);  // releases whatever was created; nothing leaks on a failed create
+        return fail(HB_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(ce));
+    }
     *out = c;
     return HB_OK;
 }
@@ -221,13 +264,16 @@ void hb_destroy(hb_ctx* c) {
     Buf* bufs[] = {&c->d_pts, &c->d_cols, &c->d_colidx, &c->d_heights, &c->d_noise, &c->d_ids, &c->d_cubes, &c->d_nbr,
                    &c->d_bitmaps, &c->d_summary, &c->d_counts, &c->d_offsets, &c->d_scan, &c->d_total, &c->d_out,
                    &c->h_total, &c->h_inst[0], &c->h_inst[1], &c->h_off[0], &c->h_off[1], &c->h_cnt[0], &c->h_cnt[1],
-                   &c->h_ids[0], &c->h_ids[1]};
+                   &c->h_ids[0], &c->h_ids[1], &c->h_bounce[0], &c->h_bounce[1], &c->h_packed[0], &c->h_packed[1]};
     for (Buf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         if (c->stream_plan[i]) hb_region_plan_destroy(c->stream_plan[i]);
         if (c->ev_kernels[i]) cudaEventDestroy(c->ev_kernels[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_bounce[i]) cudaEventDestroy(c->ev_bounce[i]);
     }
+    c->pool.resize(0);
+    free(c->h_expanded);
     if (c->d_mats) cudaFree(c->d_mats);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy) cudaStreamDestroy(c->copy);
@@ -267,6 +313,7 @@ int hb_set_materials(hb_ctx* c, int32_t n_materials, const int32_t* n_colors, co
         memcpy(m.rgba[i], rgba + (size_t)i * HB_MAX_COLORS * 4, sizeof(float) * HB_MAX_COLORS * 4);
     }
     c->mats = m;
+    c->xt_valid = false;
     HB_CUDA(cudaMemcpyAsync(c->d_mats, &c->mats, sizeof(MaterialsDev), cudaMemcpyHostToDevice, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
     return HB_OK;
@@ -280,7 +327,7 @@ int hb_host_alloc(hb_ctx* c, size_t bytes, void** out) {
 }
 
 int hb_host_free(hb_ctx* c, void* p) {
-    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    (void)c;  // pinned memory is not tied to the ctx: it may be freed after hb_destroy (ctx may be NULL)
     if (p) HB_CUDA(cudaFreeHost(p));
     return HB_OK;
 }
@@ -610,13 +657,15 @@ void hb_region_plan_destroy(hb_region_plan* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
-    Buf* bufs[] = {&p->d_heights, &p->d_counts, &p->d_offsets, &p->d_scan, &p->d_total, &p->d_out, &p->d_ids, &p->h_total};
+    Buf* bufs[] = {&p->d_heights, &p->d_counts, &p->d_offsets, &p->d_scan, &p->d_total, &p->d_out, &p->d_ids, &p->d_packed,
+                   &p->h_total};
     for (Buf* b : bufs) b->release();
     delete p;
 }
 
 int hb_region_plan_enqueue(hb_region_plan* p, int stages, void* stream) {
     if (!p) return fail(HB_ERR_INVALID, "plan is null");
+    std::lock_guard<std::mutex> lk(p->ctx->mu);  // reads ctx->world / tables: serialised with hb_set_world etc.
     HB_CUDA(cudaSetDevice(p->ctx->device));
     return plan_enqueue(p, stages, stream ? (cudaStream_t)stream : p->ctx->stream);
 }
@@ -628,6 +677,7 @@ int hb_region_plan_launches(const hb_region_plan* p, int stages) {
     if (stages & HB_STAGE_COUNT) n += 1;
     if (stages & HB_STAGE_SCAN) n += 3;
     if (stages & HB_STAGE_EMIT) n += 1;
+    if (stages & HB_STAGE_EMIT_PACKED) n += 1;
     if (stages & HB_STAGE_FILL) n += 1;
     return n;
 }
@@ -636,6 +686,7 @@ int hb_region_plan_result(hb_region_plan* p, void* stream, uint64_t* n_chunks, u
                           const hb_instance3d** d_instances, const uint64_t** d_offsets, const uint32_t** d_counts,
                           const uint16_t** d_ids, const int32_t** d_heights) {
     if (!p) return fail(HB_ERR_INVALID, "plan is null");
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
     HB_CUDA(cudaSetDevice(p->ctx->device));
     uint64_t tot[4];
     int rc = plan_totals(p, stream ? (cudaStream_t)stream : p->ctx->stream, tot);
@@ -661,14 +712,54 @@ int hb_dev_download(hb_ctx* c, void* host_dst, const void* dev_src, size_t bytes
     return HB_OK;
 }
 
-int hb_generate_mesh_region(hb_ctx* c, const hb_region* region, int want_ids, hb_region_sink sink, void* user,
-                            uint64_t* total_chunks, uint64_t* total_quads) {
-    if (!region) return fail(HB_ERR_INVALID, "region is null");
-    return hb_generate_mesh_region_slab(c, region, 0, region->ncx, want_ids, sink, user, total_chunks, total_quads);
+}  // extern "C"
+
+namespace {
+
+enum StreamMode { kRawInstances = 0, kPackedExpand = 1, kPackedSink = 2 };
+
+// plain host memory for the expanded slab: grow-only, 2 MiB aligned and huge-page advised so that the expander's
+// stores do not pay a TLB miss every 4 KiB; the pages are touched once (first call of a given shape)
+int reserve_expanded(hb_ctx* c, size_t bytes) {
+    if (bytes <= c->h_expanded_cap) return HB_OK;
+    free(c->h_expanded);
+    c->h_expanded = nullptr;
+    c->h_expanded_cap = 0;
+    const size_t want = ((bytes + bytes / 8) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    void* p = aligned_alloc((size_t)2 << 20, want);
+    if (!p) return fail(HB_ERR_NOMEM, "out of host memory for the expanded slab (%zu bytes)", want);
+    madvise(p, want, MADV_HUGEPAGE);
+    c->h_expanded = p;
+    c->h_expanded_cap = want;
+    return HB_OK;
 }
 
-int hb_generate_mesh_region_slab(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t ix_end, int want_ids,
-                                 hb_region_sink sink, void* user, uint64_t* total_chunks, uint64_t* total_quads) {
+void ensure_expander(hb_ctx* c) {
+    if (!c->xt_valid) {
+        c->xt.build(c->tables, c->mats);
+        c->xt_valid = true;
+    }
+    if (c->host_threads == 0) {
+        c->host_threads = default_host_threads();
+        c->pool.resize(c->host_threads);
+    }
+}
+
+// packed words of the chunks [0, n) of one slab -> Instance3d at the same offsets, on all host threads
+void expand_slab(hb_ctx* c, const hb_region& r, uint64_t first_chunk, size_t n, const uint64_t* off, const uint32_t* cnt,
+                 const uint32_t* packed, hb_instance3d* out) {
+    const ExpandTables& T = c->xt;
+    const uint64_t per_ix = (uint64_t)r.ncz * r.ncy;
+    c->pool.run(n, 8, [&](size_t i) {
+        if (cnt[i] == 0) return;
+        const uint64_t g = first_chunk + i;
+        const hb_chunk_pt pt{r.cx0 + (int32_t)(g / per_ix), r.cy0 + (int32_t)(g % r.ncy), r.cz0 + (int32_t)((g / r.ncy) % r.ncz)};
+        expand_chunk(T, pt, packed + off[i], cnt[i], out + off[i]);
+    });
+}
+
+int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t ix_end, int want_ids, StreamMode mode,
+                  hb_region_sink sink, hb_region_packed_sink psink, void* user, uint64_t* total_chunks, uint64_t* total_quads) {
     if (!c) return fail(HB_ERR_INVALID, "ctx is null");
     int rc = region_check(region);
     if (rc != HB_OK) return rc;
@@ -678,6 +769,8 @@ int hb_generate_mesh_region_slab(hb_ctx* c, const hb_region* region, int32_t ix_
     if (ix_begin == ix_end) return HB_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     HB_CUDA(cudaSetDevice(c->device));
+    const bool packed = mode != kRawInstances;
+    if (mode == kPackedExpand) ensure_expander(c);
     // slab width: aim at ~384 MiB of instances per slab (about 300 KB per column on this terrain),
     // bounded so that the optional id image (64 KiB/chunk) stays below ~1 GiB per slab
     const size_t per_col = 300 * 1024;
@@ -707,68 +800,147 @@ int hb_generate_mesh_region_slab(hb_ctx* c, const hb_region* region, int32_t ix_
         rc = plan_alloc(plan[b], width);
         if (rc != HB_OK) return rc;
     }
-    {
-        cudaEvent_t* ev_kernels = c->ev_kernels;
-        cudaEvent_t* ev_copied = c->ev_copied;
-        struct Pending { bool live; uint64_t first, n, span; } pend[2] = {{false, 0, 0, 0}, {false, 0, 0, 0}};
-        uint64_t sum_chunks = 0, sum_quads = 0;
-        auto drain = [&](int b) -> int {
-            if (!pend[b].live) return HB_OK;
-            HB_CUDA(cudaEventSynchronize(ev_copied[b]));
-            if (sink)
-                sink(user, pend[b].first, pend[b].n, c->h_off[b].as<uint64_t>(), c->h_cnt[b].as<uint32_t>(),
-                     c->h_inst[b].as<hb_instance3d>(), pend[b].span, want_ids ? c->h_ids[b].as<uint16_t>() : nullptr);
-            pend[b].live = false;
-            return HB_OK;
-        };
-        int slab = 0;
-        for (int32_t ix0 = ix_begin; ix0 < ix_end && rc == HB_OK; ix0 += width, ++slab) {
-            const int b = slab & 1;
-            hb_region_plan* p = plan[b];
-            rc = drain(b);  // buffers of parity b are free again (device out + pinned)
-            if (rc != HB_OK) break;
-            plan_target(p, ix0, std::min(ix_end, ix0 + width));
-            const size_t nch = p->n_chunks();
-            rc = plan_enqueue(p, HB_STAGE_HEIGHTS | HB_STAGE_COUNT | HB_STAGE_SCAN, c->stream);
-            if (rc != HB_OK) break;
-            uint64_t tot[4];
-            rc = plan_totals(p, c->stream, tot);
-            if (rc != HB_OK) break;
-            p->capacity = tot[0];
-            cudaError_t e = p->d_out.reserve(std::max<uint64_t>(tot[0], 4) * sizeof(hb_instance3d));
-            if (e == cudaSuccess) e = c->h_inst[b].reserve(std::max<uint64_t>(tot[0], 4) * sizeof(hb_instance3d));
-            if (e == cudaSuccess) e = c->h_off[b].reserve(nch * sizeof(uint64_t));
-            if (e == cudaSuccess) e = c->h_cnt[b].reserve(nch * sizeof(uint32_t));
-            if (e == cudaSuccess && want_ids) e = c->h_ids[b].reserve(nch * HB_CHUNK_VOLUME * sizeof(uint16_t));
-            if (e != cudaSuccess) { rc = fail(HB_ERR_CUDA, "slab buffer allocation failed: %s", cudaGetErrorString(e)); break; }
-            rc = plan_enqueue(p, HB_STAGE_EMIT | (want_ids ? HB_STAGE_FILL : 0), c->stream);
-            if (rc != HB_OK) break;
-            cudaEventRecord(ev_kernels[b], c->stream);
-            cudaStreamWaitEvent(c->copy, ev_kernels[b], 0);
-            cudaMemcpyAsync(c->h_off[b].p, p->d_offsets.p, nch * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->copy);
-            cudaMemcpyAsync(c->h_cnt[b].p, p->d_counts.p, nch * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy);
-            if (tot[0])
+    cudaEvent_t* ev_kernels = c->ev_kernels;
+    cudaEvent_t* ev_copied = c->ev_copied;
+    struct Pending { bool live; uint64_t first, n, span; } pend[2] = {{false, 0, 0, 0}, {false, 0, 0, 0}};
+    uint64_t sum_chunks = 0, sum_quads = 0;
+    // hand slab `b` to the sink: wait for its copies; packed+expand writes the Instance3d records on the host threads
+    auto drain = [&](int b) -> int {
+        if (!pend[b].live) return HB_OK;
+        pend[b].live = false;
+        HB_CUDA(cudaEventSynchronize(ev_copied[b]));
+        const uint64_t* off = c->h_off[b].as<uint64_t>();
+        const uint32_t* cnt = c->h_cnt[b].as<uint32_t>();
+        const uint16_t* ids = want_ids ? c->h_ids[b].as<uint16_t>() : nullptr;
+        if (mode == kPackedSink) {
+            if (psink) psink(user, pend[b].first, pend[b].n, off, cnt, c->h_packed[b].as<hb_packed_quad>(), pend[b].span, ids);
+        } else if (mode == kPackedExpand) {
+            if (!sink) return HB_OK;  // nobody looks at the records
+            const int rc2 = reserve_expanded(c, std::max<uint64_t>(pend[b].span, 4) * sizeof(hb_instance3d));
+            if (rc2 != HB_OK) return rc2;
+            hb_instance3d* inst = static_cast<hb_instance3d*>(c->h_expanded);
+            expand_slab(c, *region, pend[b].first, pend[b].n, off, cnt, c->h_packed[b].as<uint32_t>(), inst);
+            sink(user, pend[b].first, pend[b].n, off, cnt, inst, pend[b].span, ids);
+        } else if (sink) {
+            sink(user, pend[b].first, pend[b].n, off, cnt, c->h_inst[b].as<hb_instance3d>(), pend[b].span, ids);
+        }
+        return HB_OK;
+    };
+    int slab = 0;
+    for (int32_t ix0 = ix_begin; ix0 < ix_end && rc == HB_OK; ix0 += width, ++slab) {
+        const int b = slab & 1;
+        hb_region_plan* p = plan[b];
+        rc = drain(b);  // buffers of parity b are free again (device out + pinned)
+        if (rc != HB_OK) break;
+        plan_target(p, ix0, std::min(ix_end, ix0 + width));
+        const size_t nch = p->n_chunks();
+        rc = plan_enqueue(p, HB_STAGE_HEIGHTS | HB_STAGE_COUNT | HB_STAGE_SCAN, c->stream);
+        if (rc != HB_OK) break;
+        uint64_t tot[4];
+        rc = plan_totals(p, c->stream, tot);
+        if (rc != HB_OK) break;
+        p->capacity = tot[0];
+        const uint64_t span4 = std::max<uint64_t>(tot[0], 4);
+        cudaError_t e = cudaSuccess;
+        if (packed) e = c->h_packed[b].reserve(span4 * sizeof(hb_packed_quad));
+        else {
+            e = p->d_out.reserve(span4 * sizeof(hb_instance3d));
+            if (e == cudaSuccess) e = c->h_inst[b].reserve(span4 * sizeof(hb_instance3d));
+        }
+        if (e == cudaSuccess) e = c->h_off[b].reserve(nch * sizeof(uint64_t));
+        if (e == cudaSuccess) e = c->h_cnt[b].reserve(nch * sizeof(uint32_t));
+        if (e == cudaSuccess && want_ids) e = c->h_ids[b].reserve(nch * HB_CHUNK_VOLUME * sizeof(uint16_t));
+        if (e != cudaSuccess) { rc = fail(HB_ERR_CUDA, "slab buffer allocation failed: %s", cudaGetErrorString(e)); break; }
+        rc = plan_enqueue(p, (packed ? HB_STAGE_EMIT_PACKED : HB_STAGE_EMIT) | (want_ids ? HB_STAGE_FILL : 0), c->stream);
+        if (rc != HB_OK) break;
+        cudaEventRecord(ev_kernels[b], c->stream);
+        cudaStreamWaitEvent(c->copy, ev_kernels[b], 0);
+        cudaMemcpyAsync(c->h_off[b].p, p->d_offsets.p, nch * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->copy);
+        cudaMemcpyAsync(c->h_cnt[b].p, p->d_counts.p, nch * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy);
+        if (tot[0]) {
+            if (packed)
+                cudaMemcpyAsync(c->h_packed[b].p, p->d_packed.p, tot[0] * sizeof(hb_packed_quad), cudaMemcpyDeviceToHost, c->copy);
+            else
                 cudaMemcpyAsync(c->h_inst[b].p, p->d_out.p, tot[0] * sizeof(hb_instance3d), cudaMemcpyDeviceToHost, c->copy);
-            if (want_ids)
-                cudaMemcpyAsync(c->h_ids[b].p, p->d_ids.p, nch * HB_CHUNK_VOLUME * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->copy);
-            cudaError_t ce = cudaEventRecord(ev_copied[b], c->copy);
-            if (ce != cudaSuccess) { rc = fail(HB_ERR_CUDA, "slab copy failed: %s", cudaGetErrorString(ce)); break; }
-            pend[b] = Pending{true, (uint64_t)ix0 * region->ncz * region->ncy, nch, tot[0]};
-            sum_chunks += nch;
-            sum_quads += tot[1];
-            // hand the previous slab to the sink while this one is computed and copied
-            rc = drain(b ^ 1);
         }
-        if (rc == HB_OK) rc = drain((slab & 1));
-        if (rc == HB_OK) rc = drain((slab & 1) ^ 1);
-        cudaStreamSynchronize(c->copy);
-        cudaStreamSynchronize(c->stream);
-        if (rc == HB_OK) {
-            if (total_chunks) *total_chunks = sum_chunks;
-            if (total_quads) *total_quads = sum_quads;
-        }
+        if (want_ids)
+            cudaMemcpyAsync(c->h_ids[b].p, p->d_ids.p, nch * HB_CHUNK_VOLUME * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->copy);
+        cudaError_t ce = cudaEventRecord(ev_copied[b], c->copy);
+        if (ce != cudaSuccess) { rc = fail(HB_ERR_CUDA, "slab copy failed: %s", cudaGetErrorString(ce)); break; }
+        pend[b] = Pending{true, (uint64_t)ix0 * region->ncz * region->ncy, nch, tot[0]};
+        sum_chunks += nch;
+        sum_quads += tot[1];
+        // hand the previous slab to the sink while this one is computed and copied
+        rc = drain(b ^ 1);
+    }
+    if (rc == HB_OK) rc = drain((slab & 1));
+    if (rc == HB_OK) rc = drain((slab & 1) ^ 1);
+    cudaStreamSynchronize(c->copy);
+    cudaStreamSynchronize(c->stream);
+    if (rc == HB_OK) {
+        if (total_chunks) *total_chunks = sum_chunks;
+        if (total_quads) *total_quads = sum_quads;
     }
     return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_set_region_transport(hb_ctx* c, int32_t transport) {
+    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    if (transport != HB_TRANSPORT_PACKED && transport != HB_TRANSPORT_INSTANCES) return fail(HB_ERR_INVALID, "unknown transport %d", transport);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->transport = transport;
+    return HB_OK;
+}
+
+int hb_set_host_threads(hb_ctx* c, int32_t n) {
+    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    if (n < 1 || n > 256) return fail(HB_ERR_INVALID, "host threads must be in 1..256");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->host_threads = n;
+    c->pool.resize(n);
+    return HB_OK;
+}
+
+int hb_generate_mesh_region(hb_ctx* c, const hb_region* region, int want_ids, hb_region_sink sink, void* user,
+                            uint64_t* total_chunks, uint64_t* total_quads) {
+    if (!region) return fail(HB_ERR_INVALID, "region is null");
+    return hb_generate_mesh_region_slab(c, region, 0, region->ncx, want_ids, sink, user, total_chunks, total_quads);
+}
+
+int hb_generate_mesh_region_slab(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t ix_end, int want_ids,
+                                 hb_region_sink sink, void* user, uint64_t* total_chunks, uint64_t* total_quads) {
+    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    const StreamMode mode = c->transport == HB_TRANSPORT_INSTANCES ? kRawInstances : kPackedExpand;
+    return stream_region(c, region, ix_begin, ix_end, want_ids, mode, sink, nullptr, user, total_chunks, total_quads);
+}
+
+int hb_generate_mesh_region_packed(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t ix_end, int want_ids,
+                                   hb_region_packed_sink sink, void* user, uint64_t* total_chunks, uint64_t* total_quads) {
+    return stream_region(c, region, ix_begin, ix_end, want_ids, kPackedSink, nullptr, sink, user, total_chunks, total_quads);
+}
+
+int hb_expand_quads(hb_ctx* c, hb_chunk_pt pt, const hb_packed_quad* quads, uint32_t n, hb_instance3d* out) {
+    if (!c || (n && (!quads || !out))) return fail(HB_ERR_INVALID, "null argument");
+    if ((uintptr_t)out & 15u) return fail(HB_ERR_INVALID, "out must be 16-byte aligned");
+    if (!c->xt_valid) {  // tables are rebuilt under the lock; afterwards concurrent callers only read them
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->xt_valid) {
+            c->xt.build(c->tables, c->mats);
+            c->xt_valid = true;
+        }
+    }
+    expand_chunk(c->xt, pt, quads, n, out);
+    return HB_OK;
+}
+
+int hb_region_plan_packed(hb_region_plan* p, const hb_packed_quad** d_packed) {
+    if (!p || !d_packed) return fail(HB_ERR_INVALID, "null argument");
+    *d_packed = p->d_packed.as<hb_packed_quad>();
+    return HB_OK;
 }
 
 }  // extern "C"

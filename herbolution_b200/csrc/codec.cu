@@ -203,6 +203,8 @@ __global__ void __launch_bounds__(kCT) k_rle_decode(const uint8_t* __restrict__ 
             for (uint32_t k = 0; k < cnt; ++k)
                 if (pos + k < (uint32_t)HB_CHUNK_VOLUME) dst[pos + k] = (uint16_t)raw;
             running += all;
+            // block-uniform; one pass adds at most kCT * 255, so `running` can never wrap however long the stream is
+            if (running > (uint32_t)HB_CHUNK_VOLUME) break;
         }
         if (running > (uint32_t)HB_CHUNK_VOLUME) {
             if (tid == 0) atomicOr(total + 2, 4ULL);  // the reference indexes past the chunk and panics

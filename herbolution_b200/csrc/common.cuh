@@ -73,8 +73,8 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
                             uint64_t* d_total, const int32_t* d_list = nullptr);
 cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
                                const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
-                               const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
-                               uint64_t* d_total, int ctas_per_sm = 0);
+                               const uint64_t* d_offsets, void* d_out, uint64_t capacity,
+                               uint64_t* d_total, int ctas_per_sm = 0, bool packed = false);
 // counts -> offsets (each chunk's start rounded up to 4 instances); d_total[0]=span, d_total[1]=quads.
 // accumulate: offsets start at the current d_total[0] and the totals are advanced (slab chaining).
 size_t scan_workspace_bytes(size_t n);

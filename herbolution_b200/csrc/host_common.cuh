@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <functional>
 #include <mutex>
 
 #include "common.cuh"
@@ -67,6 +69,33 @@ struct KeyXYZHash {
 
 inline bool coord_ok(int32_t c) { return c >= -HB_MAX_CHUNK_COORD && c <= HB_MAX_CHUNK_COORD; }
 
+// ---- packed-quad transport, host half (expand.cu) ----
+// Everything an Instance3d holds besides the packed word and the chunk position.
+struct ExpandTables {
+    alignas(16) float face_mat[6][12];
+    alignas(16) float ao4[256][4];                              // ao byte -> Instance3d::ao
+    alignas(16) float rgba[HB_MAX_MATERIALS][HB_MAX_COLORS][4];
+    float color_scale[HB_MAX_MATERIALS];                        // (len - 1) as f32, material.rs:69
+    void build(const MeshTables& tb, const MaterialsDev& m);
+};
+uint64_t chunk_color_seed(int32_t x, int32_t y, int32_t z);
+void expand_chunk(const ExpandTables& T, hb_chunk_pt pt, const uint32_t* packed, uint32_t n, hb_instance3d* out);
+
+// Persistent host worker pool (the caller participates): run() returns when fn(i) ran for every i in [0, n_items).
+class HostPool {
+   public:
+    HostPool();
+    ~HostPool();
+    void resize(int n_threads);  // total threads incl. the caller; <= 1 = run inline
+    int threads() const;
+    void run(size_t n_items, size_t grain, const std::function<void(size_t)>& fn);
+
+   private:
+    struct Impl;
+    Impl* impl_;
+};
+int default_host_threads();  // min(hardware threads, 32), or $HB_HOST_THREADS
+
 }  // namespace hb
 
 struct hb_ctx {
@@ -83,6 +112,17 @@ struct hb_ctx {
     hb::Buf d_pts, d_cols, d_colidx, d_heights, d_noise, d_ids, d_cubes, d_nbr, d_bitmaps, d_summary, d_counts,
         d_offsets, d_scan, d_total, d_out;
     hb::Buf h_total;
+    // packed-quad transport: expander tables (rebuilt when the materials change), worker pool, the expanded slab
+    hb::ExpandTables xt;
+    std::atomic<bool> xt_valid{false};
+    hb::HostPool pool;
+    int host_threads = 0;           // 0 = not started yet (default_host_threads() on first use)
+    int transport = 0;              // HB_TRANSPORT_*
+    void* h_expanded = nullptr;     // plain (pageable, huge-page advised) host memory: the sink's Instance3d view
+    size_t h_expanded_cap = 0;
+    hb::Buf h_packed[2];            // pinned landing buffers of the packed words
+    hb::Buf h_bounce[2];            // pinned bounce buffers of copy_to_host (pageable destinations)
+    cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
     // region streaming: pinned staging, and the two double-buffered plans + events kept across calls so that a
     // steady-state hb_generate_mesh_region call allocates and frees nothing
     hb::Buf h_inst[2], h_off[2], h_cnt[2], h_ids[2];
@@ -90,7 +130,15 @@ struct hb_ctx {
     cudaEvent_t ev_kernels[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     hb_ctx() {
         h_total.pinned = true;
+        h_bounce[0].pinned = h_bounce[1].pinned = true;
+        h_packed[0].pinned = h_packed[1].pinned = true;
         for (int i = 0; i < 2; ++i) h_inst[i].pinned = h_off[i].pinned = h_cnt[i].pinned = h_ids[i].pinned = true;
     }
 };
 
+namespace hb {
+// Blocking device->host copy on stream `s` (c->mu held by the caller).  A pinned destination (hb_host_alloc,
+// cudaHostAlloc, cudaHostRegister) is one DMA at link speed; a pageable one is streamed through two pinned bounce
+// buffers so that the DMA of piece k+1 overlaps the memcpy of piece k (instead of the driver's staged path).
+int copy_to_host(hb_ctx* c, cudaStream_t s, void* dst, const void* d_src, size_t bytes);
+}  // namespace hb

@@ -198,9 +198,12 @@ __device__ __forceinline__ void emit_window(MeshSmem& sm, const MaterialsDev* __
     if (active) {
         // Material::get_color(perms[face]) (server/src/chunk/material.rs:67-71)
         const float p = wyrand_f32_at(sm.rng_seed, 6u * L + f);
-        const int nc = __ldg(&mats->n_colors[id - 1]);
+        // ids above the palette are reported through total[2] & 2 by the pack stage; the device-pointer entry points
+        // emit regardless, so keep the table reads in bounds (such a quad gets material 1's colours)
+        const uint32_t mi = id - 1u < (uint32_t)HB_MAX_MATERIALS ? id - 1u : 0u;
+        const int nc = __ldg(&mats->n_colors[mi]);
         const int ci = __float2int_rz(__fmul_rn(__int2float_rn(nc > 0 ? nc - 1 : 0), p));
-        rgba = __ldg(reinterpret_cast<const float4*>(mats->rgba[id - 1][ci]));
+        rgba = __ldg(reinterpret_cast<const float4*>(mats->rgba[mi][ci]));
     }
     if (lane == 0) bulk_wait_read();  // previous window of this warp has left the staging buffer
     __syncwarp();
@@ -233,7 +236,11 @@ __device__ __forceinline__ void emit_window(MeshSmem& sm, const MaterialsDev* __
 // owns columns (x = k*8 + t/32, z = t%32), k = 0..3, so a warp reads 32 consecutive tile words.
 // Returns the chunk's quad count (all threads).  EMIT additionally writes the instances at `out`
 // (16-byte aligned), zero-filling up to the next multiple of 4 instances.
-template <bool EMIT, class MatFn, class FacesFn>
+//
+// PACKED (with EMIT): instead of the 100-byte instance, `out` receives one 32-bit word per quad (hb_packed_quad:
+// L | face << 15 | ao << 18 | (material - 1) << 26), the gap zero-filled the same way.  The colour is not part of
+// the word: it is a pure function of (chunk, L, face) and the expander recomputes it (expand.cpp).
+template <bool EMIT, bool PACKED = false, class MatFn, class FacesFn>
 __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, const FacesFn& faces, int bx, int by, int bz,
                                               const MaterialsDev* __restrict__ mats, float* __restrict__ out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -289,6 +296,22 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, co
         }
         __syncthreads();
         const uint32_t nd = min((uint32_t)kDescCap, total - d0);
+        if constexpr (PACKED) {
+            // (b') one thread per quad: AO probes + material -> one coalesced 32-bit store
+            uint32_t* const o32 = reinterpret_cast<uint32_t*>(out) + d0;
+            const uint32_t nd4 = (d0 + nd == total) ? ((nd + 3u) & ~3u) : nd;  // zero-fill the gap after the last quad
+            for (uint32_t q = tid; q < nd4; q += kT) {
+                uint32_t w = 0u;
+                if (q < nd) {
+                    const uint32_t d = sm.desc[q];
+                    const uint32_t L = d & 0x7FFFu, f = d >> 15;
+                    const uint32_t ao = ao_bits(sm.occ, sm.ao_tab[f], L >> 10, L & 31, (L >> 5) & 31);
+                    const uint32_t id = mat(L, L >> 10, L & 31, (L >> 5) & 31);
+                    w = d | (ao << 18) | (((id - 1u) & 15u) << 26);
+                }
+                __stcs(o32 + q, w);
+            }
+        } else {
         // (b) each warp expands windows of 32 descriptors (one quad per lane) and streams them out; no block-level
         //     barrier inside this loop
         // The descriptor and the material of the NEXT window are fetched before the current one is expanded, so a
@@ -313,6 +336,7 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, co
             if ((uint32_t)lane < nw) ao = ao_bits(sm.occ, sm.ao_tab[f], L >> 10, L & 31, (L >> 5) & 31);
             emit_window(sm, mats, ws, ws_shared, out_bytes + (d0 + q0) * 100u, nw, L, f, ao, id, bx, by, bz);  // < 2^24 B / chunk
         }
+        }  // !PACKED
         if (d0 + kDescCap < total) __syncthreads();  // descriptors are rewritten in the next round
     }
     }  // if constexpr (EMIT)
@@ -799,7 +823,7 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
     }  // persistent column loop
 }
 
-template <bool EMIT>
+template <bool EMIT, bool PACKED = false>
 __global__ void __launch_bounds__(kT, kCtasPerSm)
 k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const RegionDev r,
               const int32_t* __restrict__ heights, uint32_t* __restrict__ counts, const u64* __restrict__ offsets,
@@ -822,7 +846,7 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
         const TileRegs tile_regs = fetch_heights_tile(r, heights, ix, iz);
         // The chunk hashes (SipHash-1-3, ~200 dependent 64-bit operations) of all layers of this column, one lane per
         // layer, while the heights tile is in flight -- instead of one thread hashing per chunk in front of a barrier.
-        if (EMIT && warp == 2 && lane < min(r.ncy, kSeedLayers)) sm.layer_seed[lane] = siphash13_chunk(r.cx0 + ix, r.cy0 + lane, r.cz0 + iz);
+        if (EMIT && !PACKED && warp == 2 && lane < min(r.ncy, kSeedLayers)) sm.layer_seed[lane] = siphash13_chunk(r.cx0 + ix, r.cy0 + lane, r.cz0 + iz);
         store_heights_tile(tile_regs, sm.hts, cmax, hmin, emin, rel);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
         hmin = __reduce_min_sync(0xffffffffu, hmin);
@@ -858,9 +882,17 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
                 // Region-bottom slab: the chunk, its four lateral neighbours and the layer above are solid, the chunk
                 // below is absent -> exactly one Down face per column, in column order, and every AO probe (all at
                 // y-1) reads "empty".  No tile, masks, scan or descriptors are needed (k_count_region counted 1024).
+                const MatHeights mat{sm.hts, a};
+                if constexpr (PACKED) {
+                    uint32_t* const o32 = reinterpret_cast<uint32_t*>(out) + off;
+                    for (uint32_t q = tid; q < (uint32_t)HB_CHUNK_AREA; q += kT) {
+                        const uint32_t L = q << 5;
+                        __stcs(o32 + q, L | (3u << 15) | (((mat(L, L >> 10, 0, (L >> 5) & 31) - 1u) & 15u) << 26));
+                    }
+                    continue;
+                }
                 if (tid == 32) sm.rng_seed = iy < kSeedLayers ? sm.layer_seed[iy] : siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
                 __syncthreads();
-                const MatHeights mat{sm.hts, a};
                 float* const ws = sm.stage + warp * (32 * 25);
                 const uint32_t ws_shared = (uint32_t)__cvta_generic_to_shared(ws);
                 char* const out_bytes = reinterpret_cast<char*>(out + off * 25ULL);
@@ -878,16 +910,16 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
                 const int d = min(max(sm.hts[i] - (a - 1), 0), 34);  // solid voxels at tile bits 0..33
                 sm.occ[i] = ((1ULL << d) - 1ULL) & ymask;
             }
-            if (EMIT && tid == 32) sm.rng_seed = iy < kSeedLayers ? sm.layer_seed[iy] : siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
+            if (EMIT && !PACKED && tid == 32) sm.rng_seed = iy < kSeedLayers ? sm.layer_seed[iy] : siphash13_chunk(r.cx0 + ix, cy, r.cz0 + iz);
             __syncthreads();
             const MatHeights mat{sm.hts, a};
-            const uint32_t q = mesh_tile<EMIT>(sm, mat, FacesFromOcc{sm.occ}, (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32,
-                                               mats, EMIT ? out + off * 25ULL : nullptr);
+            const uint32_t q = mesh_tile<EMIT, PACKED>(sm, mat, FacesFromOcc{sm.occ}, (r.cx0 + ix) * 32, cy * 32, (r.cz0 + iz) * 32,
+                                                       mats, EMIT ? (PACKED ? out + off : out + off * 25ULL) : nullptr);
             if (!EMIT && tid == 0) counts[chunk] = q;
         }
         colw = s_col;  // written before this column's first barrier, read after several more
     }
-    if (EMIT) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
+    if (EMIT && !PACKED) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1053,8 +1085,8 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
 
 cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
                                const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
-                               const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
-                               uint64_t* d_total, int ctas_per_sm) {
+                               const uint64_t* d_offsets, void* d_out, uint64_t capacity,
+                               uint64_t* d_total, int ctas_per_sm, bool packed) {
     const size_t ncols = (size_t)(r.ix_end - r.ix_begin) * r.ncz;
     if (ncols == 0 || r.ncy == 0) return cudaSuccess;
     if (ctas_per_sm < 1 || ctas_per_sm > kCtasPerSm) ctas_per_sm = kCtasPerSm;
@@ -1063,8 +1095,12 @@ cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, 
     if (emit) {
         const cudaError_t e = cudaMemsetAsync(d_total + 3, 0, sizeof(uint64_t), s);  // the column ticket counter
         if (e != cudaSuccess) return e;
-        k_mesh_region<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
-                                                          (float*)d_out, capacity, (u64*)d_total);
+        if (packed)
+            k_mesh_region<true, true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
+                                                                    (float*)d_out, capacity, (u64*)d_total);
+        else
+            k_mesh_region<true><<<(unsigned)grid, kT, 0, s>>>(tb, d_mats, r, d_heights, d_counts, (const u64*)d_offsets,
+                                                              (float*)d_out, capacity, (u64*)d_total);
     }
     else {
         const cudaError_t e = cudaMemsetAsync(d_total + 3, 0, sizeof(uint64_t), s);  // the column ticket counter

@@ -391,6 +391,7 @@ int remesh_impl(hb_world* w, hb_chunk_pt* out_pts, size_t pts_capacity, uint64_t
     uint64_t tot[4];
     memcpy(tot, w->h_pin.p, sizeof(tot));
     *out_total = tot[0];
+    if (tot[2] & 2) return fail(HB_ERR_INVALID, "a loaded chunk holds a material id above the palette size %d", c->mats.n_materials);
     if (n > pts_capacity || (host_out && tot[0] > out_capacity))
         return fail(HB_ERR_CAPACITY, "remesh needs room for %zu chunks and %llu instances", n, (unsigned long long)tot[0]);
     HB_CUDA(cudaMemcpyAsync(out_offsets, w->d_offsets.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -545,23 +546,41 @@ int hb_world_load(hb_world* w, const hb_chunk_pt* pts, size_t n) {
             w->stale[o] = w->touched[o] = 1;
         }
     }
-    int rc;
-    if ((rc = upload(s, w->d_a, cols.data(), cols.size() * sizeof(int32_t))) != HB_OK) return rc;
-    if ((rc = upload(s, w->d_b, colidx.data(), m * sizeof(int32_t))) != HB_OK) return rc;
-    if ((rc = upload(s, w->d_c, fresh.data(), m * sizeof(hb_chunk_pt))) != HB_OK) return rc;
-    if ((rc = upload(s, w->d_d, slots.data(), m * sizeof(int32_t))) != HB_OK) return rc;
-    HB_CUDA(w->d_heights.reserve(ncol * HB_CHUNK_AREA * sizeof(int32_t)));
-    HB_CUDA(launch_heights(s, c->world, w->d_a.as<int32_t>(), ncol, w->d_heights.as<int32_t>(), nullptr));
-    HB_CUDA(launch_fill_world(s, w->d_c.as<hb_chunk_pt>(), w->d_b.as<int32_t>(), m, w->d_heights.as<int32_t>(),
-                              w->d_cubes.as<hb_palette_cube>(), w->d_d.as<int32_t>(), w->d_touched.as<uint32_t>()));
-    if (!pairs.empty()) {
-        if ((rc = upload(s, w->d_a, pairs.data(), pairs.size() * sizeof(CullPair))) != HB_OK) return rc;
-        k_world_cull<<<(unsigned)pairs.size(), kWT, 0, s>>>(w->d_cubes.as<hb_palette_cube>(), w->d_touched.as<uint32_t>(),
-                                                            w->d_a.as<CullPair>());
-        HB_CUDA(cudaGetLastError());
+    // device side; if anything here fails the host mirror is taken back to where it was, so no chunk is left
+    // "loaded" with cubes that were never written (neighbours a failed cull may have touched keep valid, if stale,
+    // flags; a CUDA error at this point is sticky for the context anyway)
+    auto device_side = [&]() -> int {
+        int rc;
+        if ((rc = upload(s, w->d_a, cols.data(), cols.size() * sizeof(int32_t))) != HB_OK) return rc;
+        if ((rc = upload(s, w->d_b, colidx.data(), m * sizeof(int32_t))) != HB_OK) return rc;
+        if ((rc = upload(s, w->d_c, fresh.data(), m * sizeof(hb_chunk_pt))) != HB_OK) return rc;
+        if ((rc = upload(s, w->d_d, slots.data(), m * sizeof(int32_t))) != HB_OK) return rc;
+        HB_CUDA(w->d_heights.reserve(ncol * HB_CHUNK_AREA * sizeof(int32_t)));
+        HB_CUDA(launch_heights(s, c->world, w->d_a.as<int32_t>(), ncol, w->d_heights.as<int32_t>(), nullptr));
+        HB_CUDA(launch_fill_world(s, w->d_c.as<hb_chunk_pt>(), w->d_b.as<int32_t>(), m, w->d_heights.as<int32_t>(),
+                                  w->d_cubes.as<hb_palette_cube>(), w->d_d.as<int32_t>(), w->d_touched.as<uint32_t>()));
+        if (!pairs.empty()) {
+            if ((rc = upload(s, w->d_a, pairs.data(), pairs.size() * sizeof(CullPair))) != HB_OK) return rc;
+            k_world_cull<<<(unsigned)pairs.size(), kWT, 0, s>>>(w->d_cubes.as<hb_palette_cube>(), w->d_touched.as<uint32_t>(),
+                                                                w->d_a.as<CullPair>());
+            HB_CUDA(cudaGetLastError());
+        }
+        HB_CUDA(cudaStreamSynchronize(s));
+        return HB_OK;
+    };
+    const int rc = device_side();
+    if (rc != HB_OK) {
+        for (size_t i = m; i-- > 0;) {
+            w->map.erase(fresh[i].x, fresh[i].y, fresh[i].z);
+            wire_neighbours(w, fresh[i], slots[i], false);
+            for (int k = 0; k < 27; ++k) w->h_nbr[(size_t)slots[i] * 27 + k] = -1;
+            w->used[slots[i]] = 0;
+            w->epoch[slots[i]]++;
+            w->stale[slots[i]] = w->touched[slots[i]] = w->remesh[slots[i]] = 0;
+            w->free_slots.push_back(slots[i]);
+        }
     }
-    HB_CUDA(cudaStreamSynchronize(s));
-    return HB_OK;
+    return rc;
 }
 
 int hb_world_unload(hb_world* w, const hb_chunk_pt* pts, size_t n) {
@@ -657,8 +676,10 @@ int hb_world_sync(hb_world* w, size_t* n_dirty, uint64_t* n_entries) {
 }
 
 int hb_world_fetch_updates(hb_world* w, hb_chunk_pt* out_pts, size_t pts_capacity, uint64_t* out_offsets, uint32_t* out_counts,
-                           hb_chunk_cube* out_entries, uint64_t entries_capacity) {
-    if (!w) return fail(HB_ERR_INVALID, "null argument");
+                           hb_chunk_cube* out_entries, uint64_t entries_capacity, size_t* n_runs, uint64_t* n_entries) {
+    if (!w || !n_runs || !n_entries) return fail(HB_ERR_INVALID, "null argument");
+    *n_runs = 0;
+    *n_entries = 0;
     hb_ctx* c = w->ctx;
     std::lock_guard<std::mutex> lk(c->mu);
     HB_CUDA(cudaSetDevice(c->device));
@@ -675,6 +696,8 @@ int hb_world_fetch_updates(hb_world* w, hb_chunk_pt* out_pts, size_t pts_capacit
         total += r.count;
     }
     const size_t n = list.size();
+    *n_runs = n;
+    *n_entries = total;
     if (n == 0) return HB_OK;
     if (n > pts_capacity || total > entries_capacity)
         return fail(HB_ERR_CAPACITY, "updates need room for %zu chunks and %llu entries", n, (unsigned long long)total);
@@ -686,8 +709,7 @@ int hb_world_fetch_updates(hb_world* w, hb_chunk_pt* out_pts, size_t pts_capacit
     k_world_updates<<<(unsigned)n, kWT, 0, s>>>(w->d_cubes.as<hb_palette_cube>(), w->d_pending.as<uint32_t>(), w->d_a.as<int32_t>(),
                                                 w->d_b.as<uint64_t>(), w->d_out.as<uint32_t>());
     HB_CUDA(cudaGetLastError());
-    HB_CUDA(cudaMemcpyAsync(out_entries, w->d_out.p, total * sizeof(hb_chunk_cube), cudaMemcpyDeviceToHost, s));
-    HB_CUDA(cudaStreamSynchronize(s));
+    if ((rc = copy_to_host(c, s, out_entries, w->d_out.p, total * sizeof(hb_chunk_cube))) != HB_OK) return rc;
     for (size_t i = 0; i < n; ++i) {
         out_pts[i] = w->slot_pt[list[i]];
         out_offsets[i] = offsets[i];

@@ -348,8 +348,8 @@ class ServerChunkMap {
         std::vector<uint64_t> off(n);
         std::vector<uint32_t> cnt(n);
         std::vector<ChunkCube> entries(e);
-        check(hb_world_fetch_updates(w_, pts.data(), n, off.data(), cnt.data(), entries.data(), e));
-        out.resize(n);
+        check(hb_world_fetch_updates(w_, pts.data(), n, off.data(), cnt.data(), entries.data(), e, &n, &e));
+        out.resize(n);  // chunks unloaded since the sync are skipped: n may have shrunk
         for (size_t i = 0; i < n; ++i) {
             out[i].chunk = ChunkPt{pts[i].x, pts[i].y, pts[i].z};
             out[i].overwrites.assign(entries.begin() + (ptrdiff_t)off[i], entries.begin() + (ptrdiff_t)(off[i] + cnt[i]));

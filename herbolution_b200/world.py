@@ -67,9 +67,14 @@ class World:
         pts = np.zeros(n, dtype=CHUNK_PT_DTYPE)
         offsets = np.zeros(n, dtype=np.uint64)
         counts = np.zeros(n, dtype=np.uint32)
-        entries = np.zeros(e, dtype=CHUNK_CUBE_DTYPE)
-        check(self._lib.hb_world_fetch_updates(self._h, ptr(pts), n, ptr(offsets), ptr(counts), ptr(entries), e))
-        return {"pts": pts, "offsets": offsets, "counts": counts, "entries": entries}
+        # the entries land in pinned memory (hb_host_alloc): one DMA at link speed instead of the pageable path
+        entries = self.ctx.pinned_empty(e, CHUNK_CUBE_DTYPE)
+        nr, ne = C.c_size_t(0), C.c_uint64(0)
+        check(self._lib.hb_world_fetch_updates(self._h, ptr(pts), n, ptr(offsets), ptr(counts), ptr(entries), e,
+                                               C.byref(nr), C.byref(ne)))
+        # chunks unloaded since the sync are skipped: only the first nr runs / ne entries were written
+        k = nr.value
+        return {"pts": pts[:k], "offsets": offsets[:k], "counts": counts[:k], "entries": entries[:ne.value]}
 
     def remesh(self) -> dict:
         """{"pts", "offsets", "counts", "instances"} for every chunk that received a CubeUpdate since the last remesh."""

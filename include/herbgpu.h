@@ -75,6 +75,15 @@ typedef struct hb_palette_cube {
     uint32_t flags;   /* CubeFlags: bit0 opaque tag, bits1..6 faces (cube.rs:27-72) */
 } hb_palette_cube;
 
+/* The information content of one Instance3d, as the device sends it to the host (4 bytes instead of 100):
+ *   bits  0-14  voxel index L = x*1024 + z*32 + y            (lib/src/vector.rs:1274-1276)
+ *   bits 15-17  face (East, West, Up, Down, North, South)    (lib/src/spatial/face.rs:13-25)
+ *   bits 18-25  the four vertex_ao values, 2 bits each, in Instance3d::ao order (client/src/world/chunk.rs:255-276)
+ *   bits 26-29  material id - 1
+ * Everything else in the 100-byte record (face matrix, world position, colour draw, light, ao floats) is a pure
+ * function of these bits and the chunk position: hb_expand_quads rebuilds it bit for bit. */
+typedef uint32_t hb_packed_quad;
+
 /* A box of chunks: cx in [cx0,cx0+ncx), cz in [cz0,cz0+ncz), cy in [cy0,cy0+ncy).
  * Chunk index inside a region = ((ix*ncz)+iz)*ncy+iy.  Chunks outside the region are ABSENT:
  * border faces toward them are emitted and AO probes into them read "empty", exactly like
@@ -107,7 +116,7 @@ HB_API int hb_set_materials(hb_ctx *ctx, int32_t n_materials, const int32_t *n_c
 
 /* Pinned host memory for full-speed async copies (optional; any host pointer is accepted). */
 HB_API int hb_host_alloc(hb_ctx *ctx, size_t bytes, void **out);
-HB_API int hb_host_free(hb_ctx *ctx, void *p);
+HB_API int hb_host_free(hb_ctx *ctx, void *p);   /* ctx may be NULL (the memory outlives the ctx) */
 
 /* ---- generation ---- */
 
@@ -164,8 +173,10 @@ HB_API int hb_mesh_cubes(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, const hb
 
 /* Sink for hb_generate_mesh_region: called once per slab (a contiguous range of region chunk
  * indices [first_chunk, first_chunk+n_chunks)), in order, from the calling thread.  Pointers are
- * pinned host buffers owned by the library and valid only during the call.  offsets are relative
- * to `instances`.  ids is NULL unless want_ids. */
+ * host buffers owned by the library and valid only during the call.  offsets are relative
+ * to `instances`.  ids is NULL unless want_ids.
+ * The sink runs while the ctx is locked: it must NOT call back into the library on the same ctx (or on a world of
+ * that ctx) -- that would deadlock; hand the data to another thread or use a second ctx instead. */
 typedef void (*hb_region_sink)(void *user, uint64_t first_chunk, uint64_t n_chunks,
                                const uint64_t *offsets, const uint32_t *counts,
                                const hb_instance3d *instances, uint64_t n_instances,
@@ -178,6 +189,17 @@ HB_API int hb_generate_mesh_region(hb_ctx *ctx, const hb_region *region, int wan
                             hb_region_sink sink, void *user,
                             uint64_t *total_chunks, uint64_t *total_quads);
 
+/* How hb_generate_mesh_region[_slab] moves a slab's quads from the device to the sink's Instance3d buffer:
+ *   HB_TRANSPORT_PACKED (default): the device writes hb_packed_quad words (4 B/quad), they cross the link, and the
+ *     library's host threads (hb_set_host_threads; default min(hardware threads, 32) or $HB_HOST_THREADS) rebuild the
+ *     100-byte records with non-temporal stores into a library-owned host buffer -- 25x less link traffic;
+ *   HB_TRANSPORT_INSTANCES: the device writes the 100-byte records and they are copied as they are (pinned buffers).
+ * The sink sees byte-identical data either way. */
+#define HB_TRANSPORT_PACKED 0
+#define HB_TRANSPORT_INSTANCES 1
+HB_API int hb_set_region_transport(hb_ctx *ctx, int32_t transport);
+HB_API int hb_set_host_threads(hb_ctx *ctx, int32_t n_threads);
+
 /* Same for the x-slab ix in [ix_begin, ix_end) of `region` only: how a region is sharded across GPUs (one ctx per
  * GPU, herbolution_b200/sharding.py).  The slab's border columns see their neighbours inside the region (the
  * one-column apron of heights is recomputed from the noise function, no exchange); first_chunk passed to the sink
@@ -185,6 +207,21 @@ HB_API int hb_generate_mesh_region(hb_ctx *ctx, const hb_region *region, int wan
 HB_API int hb_generate_mesh_region_slab(hb_ctx *ctx, const hb_region *region, int32_t ix_begin, int32_t ix_end,
                                         int want_ids, hb_region_sink sink, void *user,
                                         uint64_t *total_chunks, uint64_t *total_quads);
+
+/* The packed transport without the expansion: the sink receives the hb_packed_quad words themselves (chunk i of the
+ * slab at quads[offsets[i] .. + counts[i]), offsets multiples of 4, gaps zero) and expands what it needs, when it
+ * needs it, on its own threads with hb_expand_quads -- e.g. straight into a mapped vertex buffer.  Sink rules as above. */
+typedef void (*hb_region_packed_sink)(void *user, uint64_t first_chunk, uint64_t n_chunks,
+                                      const uint64_t *offsets, const uint32_t *counts,
+                                      const hb_packed_quad *quads, uint64_t n_quads,
+                                      const uint16_t *ids);
+HB_API int hb_generate_mesh_region_packed(hb_ctx *ctx, const hb_region *region, int32_t ix_begin, int32_t ix_end,
+                                          int want_ids, hb_region_packed_sink sink, void *user,
+                                          uint64_t *total_chunks, uint64_t *total_quads);
+/* n packed quads of chunk `pt` -> out[0 .. n) (zero-filled up to the next multiple of 4 records, so `out` needs room
+ * for (n + 3) & ~3 records and must be 16-byte aligned).  No GPU work, no lock: any number of host threads may call
+ * it concurrently on one ctx (as long as nobody changes the materials meanwhile).  Uses the ctx's palette colours. */
+HB_API int hb_expand_quads(hb_ctx *ctx, hb_chunk_pt pt, const hb_packed_quad *quads, uint32_t n, hb_instance3d *out);
 
 /* ---- device-resident pipeline (kernel-only measurement, chaining with other CUDA work) ----
  * A plan owns the device buffers for region chunks with ix in [ix_begin, ix_end).  Stages only
@@ -196,6 +233,7 @@ enum {
     HB_STAGE_SCAN = 4,     /* exclusive scan -> offsets */
     HB_STAGE_EMIT = 8,     /* write hb_instance3d */
     HB_STAGE_FILL = 16,    /* write u16 block ids (plan created with want_ids) */
+    HB_STAGE_EMIT_PACKED = 32, /* write hb_packed_quad words at the same offsets (hb_region_plan_packed) */
     HB_STAGE_ALL_MESH = 15
 };
 /* quad_capacity 0 = size the instance buffer by running HEIGHTS+COUNT+SCAN once (synchronous). */
@@ -208,6 +246,8 @@ HB_API int hb_region_plan_result(hb_region_plan *plan, void *stream, uint64_t *n
                           uint64_t *total_span, const hb_instance3d **d_instances,
                           const uint64_t **d_offsets, const uint32_t **d_counts,
                           const uint16_t **d_ids, const int32_t **d_heights);
+/* Device pointer of the packed words HB_STAGE_EMIT_PACKED wrote (NULL before the first such enqueue). */
+HB_API int hb_region_plan_packed(hb_region_plan *plan, const hb_packed_quad **d_packed);
 /* Number of kernel launches a given stage mask enqueues (for launch accounting). */
 HB_API int hb_region_plan_launches(const hb_region_plan *plan, int stages);
 /* Blocking device->host copy of plan / hb_dev_* results (synchronises the ctx device). */
@@ -276,9 +316,14 @@ HB_API int hb_world_sync(hb_world *world, size_t *n_dirty, uint64_t *n_entries);
 /* The CubeUpdates of the last hb_world_sync, one run per dirty chunk: out_pts[i] = chunk, its entries are
  * out_entries[out_offsets[i] .. +out_counts[i]) in ascending voxel index, each carrying the cube as it is now.
  * Optional (a fused server+client can skip the wire format and go straight to hb_world_remesh).
- * HB_ERR_CAPACITY if pts_capacity / entries_capacity are too small. */
+ * *n_runs / *n_entries (required) receive how many runs / entries there are: chunks unloaded since the sync are
+ * skipped, so this can be fewer than hb_world_sync reported -- only out_*[0 .. *n_runs) are written.
+ * HB_ERR_CAPACITY (nothing written, *n_runs / *n_entries hold the requirement) if pts_capacity / entries_capacity
+ * are too small.  out_entries from hb_host_alloc (pinned) is one DMA at link speed; pageable memory is accepted
+ * and streamed through pinned bounce buffers. */
 HB_API int hb_world_fetch_updates(hb_world *world, hb_chunk_pt *out_pts, size_t pts_capacity, uint64_t *out_offsets,
-                           uint32_t *out_counts, hb_chunk_cube *out_entries, uint64_t entries_capacity);
+                           uint32_t *out_counts, hb_chunk_cube *out_entries, uint64_t entries_capacity,
+                           size_t *n_runs, uint64_t *n_entries);
 
 /* Client ChunkMap::update (client/src/world/chunk.rs:47-76): generate_mesh (faces read from cube.flags, AO and
  * occupancy through the 27-chunk shell of loaded chunks) for every chunk of the remesh set that is still loaded.

@@ -258,8 +258,10 @@ def test_world_errors_and_two_call_remesh(ctx):
         pts = np.zeros(1, dtype=hb.CHUNK_PT_DTYPE)
         off, cnt = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint32)
         small = np.zeros(10, dtype=hb.CHUNK_CUBE_DTYPE)
+        nr, ne = C.c_size_t(0), C.c_uint64(0)
         assert lib.hb_world_fetch_updates(world._h, hb._lib.ptr(pts), 1, hb._lib.ptr(off), hb._lib.ptr(cnt),
-                                          hb._lib.ptr(small), 10) == hb._lib.HB_ERR_CAPACITY
+                                          hb._lib.ptr(small), 10, C.byref(nr), C.byref(ne)) == hb._lib.HB_ERR_CAPACITY
+        assert nr.value == 1 and ne.value == 32768
         assert world.fetch_updates()["entries"].shape[0] == 32768
         # remesh: sizing call keeps the remesh set
         n, total = C.c_size_t(0), C.c_uint64(0)
@@ -340,3 +342,27 @@ def test_readme_example_runs(ctx):
     meshes = world.remesh()
     assert set(updates) == set(meshes) == {(0, 0, 0)}
     world.close()
+
+
+def test_fetch_updates_after_unload_reports_what_it_wrote(ctx):
+    """sync -> unload -> fetch: runs of chunks unloaded since the sync are skipped, and the call says how many runs
+    and entries it actually wrote (no zero-padded (0,0,0) run can reach ServerChunkMap.sync_with_client)."""
+    import ctypes as C
+    ctx.set_world(0)
+    lib = hb._lib.load()
+    with hb.World(ctx, 8) as world:
+        pts = [(0, -2, 0), (1, -2, 0), (2, -2, 0)]
+        world.load(pts)
+        n_dirty, n_entries = world.sync()
+        assert n_dirty == 3
+        world.unload([pts[1]])
+        upd = world.fetch_updates()
+        assert [key(p) for p in upd["pts"]] == [pts[0], pts[2]]
+        assert upd["offsets"].shape[0] == 2 and upd["counts"].shape[0] == 2
+        assert upd["entries"].shape[0] == int(upd["counts"].sum()) < n_entries
+        # nothing left: the outputs report zero runs instead of leaving the caller's arrays untouched
+        world.unload([pts[0], pts[2]])
+        nr, ne = C.c_size_t(99), C.c_uint64(99)
+        assert lib.hb_world_fetch_updates(world._h, None, 0, None, None, None, 0, C.byref(nr), C.byref(ne)) == hb._lib.HB_OK
+        assert nr.value == 0 and ne.value == 0
+        assert lib.hb_world_fetch_updates(world._h, None, 0, None, None, None, 0, None, None) == hb._lib.HB_ERR_INVALID
