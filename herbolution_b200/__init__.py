@@ -6,7 +6,7 @@ ABI.  Importing it never touches the CPU oracle under oracle/; using it without 
 library, or without a GPU, raises.
 """
 from ._lib import (CHUNK_AREA, CHUNK_CUBE_DTYPE, CHUNK_LENGTH, CHUNK_PT_DTYPE, CHUNK_VOLUME, CUBE_DTYPE, INSTANCE_DTYPE, HerbGpuError,
-                   Region, STAGE_ALL_MESH, STAGE_COUNT, STAGE_EMIT, STAGE_EMIT_PACKED, STAGE_FILL, STAGE_HEIGHTS, STAGE_SCAN,
+                   Region, STAGE_ALL_MESH, STAGE_COUNT, STAGE_EMIT, STAGE_EMIT_PACKED, STAGE_FILL, STAGE_FUSED, STAGE_HEIGHTS, STAGE_SCAN,
                    TRANSPORT_INSTANCES, TRANSPORT_PACKED)
 from .context import Context, RegionPlan
 from .generator import ChunkGenerator, ChunkPt, CubeMesh, GenerationParams
@@ -15,7 +15,7 @@ from .world import ServerChunkMap, World
 
 __all__ = [
     "CHUNK_AREA", "CHUNK_CUBE_DTYPE", "CHUNK_LENGTH", "CHUNK_PT_DTYPE", "CHUNK_VOLUME", "CUBE_DTYPE", "INSTANCE_DTYPE", "HerbGpuError",
-    "Region", "STAGE_ALL_MESH", "STAGE_COUNT", "STAGE_EMIT", "STAGE_EMIT_PACKED", "STAGE_FILL", "STAGE_HEIGHTS", "STAGE_SCAN",
+    "Region", "STAGE_ALL_MESH", "STAGE_COUNT", "STAGE_EMIT", "STAGE_EMIT_PACKED", "STAGE_FILL", "STAGE_FUSED", "STAGE_HEIGHTS", "STAGE_SCAN",
     "TRANSPORT_INSTANCES", "TRANSPORT_PACKED",
     "Context", "RegionPlan", "ChunkGenerator", "ChunkPt", "CubeMesh", "GenerationParams",
     "ChunkData", "ChunkMap", "create_chunk_shell", "generate_mesh", "ServerChunkMap", "World",

@@ -28,6 +28,7 @@ HB_ERR_NOMEM = -5
 
 STAGE_HEIGHTS, STAGE_COUNT, STAGE_SCAN, STAGE_EMIT, STAGE_FILL = 1, 2, 4, 8, 16
 STAGE_EMIT_PACKED = 32
+STAGE_FUSED = 64
 STAGE_ALL_MESH = 15
 TRANSPORT_PACKED, TRANSPORT_INSTANCES = 0, 1
 NOISE_FBM, NOISE_RIDGE, NOISE_TURBULENCE, NOISE_GRADIENT = 0, 1, 2, 3
@@ -109,6 +110,8 @@ PROTOTYPES = {
     "hb_generate_mesh_region_packed": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_int, REGION_SINK,
                                                  C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_expand_quads": (C.c_int, [C.c_void_p, ChunkPtC, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "hb_probe_d2h": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
+    "hb_probe_host_write": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
     "hb_region_plan_packed": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "hb_region_plan_create": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_uint64, C.c_int,
                                         C.POINTER(C.c_void_p)]),

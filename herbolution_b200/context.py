@@ -262,6 +262,18 @@ class Context:
         check(self._lib.hb_expand_quads(self._h, _lib.ChunkPtC(x, y, z), ptr(packed), n, C.c_void_p(out.ctypes.data)))
         return out[:n]
 
+    def probe_d2h(self, nbytes: int = 1 << 30, reps: int = 4) -> float:
+        """GB/s of plain device -> pinned host copies (the link ceiling of the end-to-end path)."""
+        g = C.c_double(0.0)
+        check(self._lib.hb_probe_d2h(self._h, nbytes, reps, C.byref(g)))
+        return g.value
+
+    def probe_host_write(self, nbytes: int = 1 << 30, reps: int = 4) -> float:
+        """GB/s of the expander's worker pool writing host memory with non-temporal stores."""
+        g = C.c_double(0.0)
+        check(self._lib.hb_probe_host_write(self._h, nbytes, reps, C.byref(g)))
+        return g.value
+
     def download(self, dev_ptr: int, dtype, count: int) -> np.ndarray:
         """Blocking device->host copy of `count` items at a raw device pointer (plan results)."""
         out = np.empty(count, dtype=dtype)

@@ -6,9 +6,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <emmintrin.h>
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <unordered_map>
@@ -140,7 +142,7 @@ struct hb_region_plan {
     int want_ids = 0;
     size_t max_chunks = 0, max_hcols = 0;
     uint64_t capacity = 0;
-    Buf d_heights, d_counts, d_offsets, d_scan, d_total, d_out, d_ids, d_packed;
+    Buf d_heights, d_counts, d_offsets, d_scan, d_total, d_out, d_ids, d_packed, d_status;
     Buf h_total;
     hb_region_plan() { h_total.pinned = true; }
     size_t n_chunks() const { return (size_t)(dev.ix_end - dev.ix_begin) * dev.ncz * dev.ncy; }
@@ -185,6 +187,21 @@ int plan_alloc(hb_region_plan* p, int32_t max_width) {
 int plan_enqueue(hb_region_plan* p, int stages, cudaStream_t s) {
     hb_ctx* c = p->ctx;
     const size_t hcols = (size_t)(p->dev.hx_end - p->dev.hx_begin) * p->dev.ncz;
+    if (stages & HB_STAGE_FUSED) {
+        // heights + count + scan + emit as one launch; regions the fused kernel does not cover take the staged kernels
+        stages &= ~HB_STAGE_FUSED;
+        if (region_fused_supported(c->world, p->dev)) {
+            if (!p->d_out.p && p->capacity) return fail(HB_ERR_INVALID, "plan has no instance buffer");
+            HB_CUDA(p->d_status.reserve(region_fused_status_bytes(p->dev)));
+            HB_CUDA(launch_region_fused(s, c->tables, c->d_mats, c->world, p->dev, p->d_heights.as<int32_t>(),
+                                        p->d_counts.as<uint32_t>(), p->d_offsets.as<uint64_t>(), p->d_out.as<hb_instance3d>(),
+                                        p->capacity, p->d_total.as<uint64_t>(), p->d_status.as<uint64_t>(),
+                                        noise_fast_index_ok(c->world)));
+            stages &= ~HB_STAGE_ALL_MESH;
+        } else {
+            stages |= HB_STAGE_ALL_MESH;
+        }
+    }
     if (stages & HB_STAGE_HEIGHTS) HB_CUDA(launch_heights_region(s, c->world, p->dev, p->d_heights.as<int32_t>(), 0, hcols));
     if (stages & HB_STAGE_COUNT) {
         HB_CUDA(cudaMemsetAsync(p->d_total.p, 0, 4 * sizeof(uint64_t), s));
@@ -658,7 +675,7 @@ void hb_region_plan_destroy(hb_region_plan* p) {
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
     Buf* bufs[] = {&p->d_heights, &p->d_counts, &p->d_offsets, &p->d_scan, &p->d_total, &p->d_out, &p->d_ids, &p->d_packed,
-                   &p->h_total};
+                   &p->d_status, &p->h_total};
     for (Buf* b : bufs) b->release();
     delete p;
 }
@@ -673,6 +690,11 @@ int hb_region_plan_enqueue(hb_region_plan* p, int stages, void* stream) {
 int hb_region_plan_launches(const hb_region_plan* p, int stages) {
     if (!p) return 0;
     int n = 0;
+    if (stages & HB_STAGE_FUSED) {
+        stages &= ~HB_STAGE_FUSED;
+        if (region_fused_supported(p->ctx->world, p->dev)) { n += 1; stages &= ~HB_STAGE_ALL_MESH; }
+        else stages |= HB_STAGE_ALL_MESH;
+    }
     if (stages & HB_STAGE_HEIGHTS) n += 1;
     if (stages & HB_STAGE_COUNT) n += 1;
     if (stages & HB_STAGE_SCAN) n += 3;
@@ -934,6 +956,58 @@ int hb_expand_quads(hb_ctx* c, hb_chunk_pt pt, const hb_packed_quad* quads, uint
         }
     }
     expand_chunk(c->xt, pt, quads, n, out);
+    return HB_OK;
+}
+
+// ---- in-run ceilings for the end-to-end numbers (measurement helpers; they move bytes, nothing else) ----
+
+int hb_probe_d2h(hb_ctx* c, size_t bytes, int32_t reps, double* gbs) {
+    if (!c || !gbs || bytes == 0 || reps < 1) return fail(HB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    HB_CUDA(cudaSetDevice(c->device));
+    HB_CUDA(c->d_out.reserve(bytes));
+    HB_CUDA(c->h_inst[0].reserve(bytes));
+    cudaEvent_t e0, e1;
+    HB_CUDA(cudaEventCreate(&e0));
+    HB_CUDA(cudaEventCreate(&e1));
+    cudaMemcpyAsync(c->h_inst[0].p, c->d_out.p, bytes, cudaMemcpyDeviceToHost, c->copy);  // warm-up
+    cudaEventRecord(e0, c->copy);
+    for (int r = 0; r < reps; ++r) cudaMemcpyAsync(c->h_inst[0].p, c->d_out.p, bytes, cudaMemcpyDeviceToHost, c->copy);
+    cudaEventRecord(e1, c->copy);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) return fail(HB_ERR_CUDA, "D2H probe failed: %s", cudaGetErrorString(e));
+    *gbs = (double)bytes * reps / (ms * 1e-3) / 1e9;
+    return HB_OK;
+}
+
+int hb_probe_host_write(hb_ctx* c, size_t bytes, int32_t reps, double* gbs) {
+    if (!c || !gbs || bytes < ((size_t)1 << 20) || reps < 1) return fail(HB_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    ensure_expander(c);
+    int rc = reserve_expanded(c, bytes);
+    if (rc != HB_OK) return rc;
+    char* base = static_cast<char*>(c->h_expanded);
+    const size_t piece = (size_t)1 << 20, np = bytes / piece;
+    auto fill = [&](size_t i) {
+        const __m128i v = _mm_set1_epi32((int)i);
+        char* p = base + i * piece;
+        for (size_t o = 0; o < piece; o += 64) {
+            _mm_stream_si128((__m128i*)(p + o), v);
+            _mm_stream_si128((__m128i*)(p + o + 16), v);
+            _mm_stream_si128((__m128i*)(p + o + 32), v);
+            _mm_stream_si128((__m128i*)(p + o + 48), v);
+        }
+        _mm_sfence();
+    };
+    c->pool.run(np, 4, fill);  // touches the pages
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) c->pool.run(np, 4, fill);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *gbs = (double)np * piece * reps / dt / 1e9;
     return HB_OK;
 }
 

@@ -75,6 +75,16 @@ cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, 
                                const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
                                const uint64_t* d_offsets, void* d_out, uint64_t capacity,
                                uint64_t* d_total, int ctas_per_sm = 0, bool packed = false);
+// Single-launch fused pipeline (noise + count + offsets + emit); see k_region_fused.  d_status: one u64 per column.
+// d_heights (nullable) receives the centre tiles like launch_heights_region (apron columns of the slab are not
+// written).  `fast` = noise_fast_index_ok(w).
+bool region_fused_supported(const WorldDev& w, const RegionDev& r);
+size_t region_fused_status_bytes(const RegionDev& r);
+cudaError_t launch_region_fused(cudaStream_t s, const MeshTables& tb, const MaterialsDev* d_mats, const WorldDev& w,
+                                const RegionDev& r, int32_t* d_heights, uint32_t* d_counts, uint64_t* d_offsets,
+                                hb_instance3d* d_out, uint64_t capacity, uint64_t* d_total, uint64_t* d_status, bool fast,
+                                int ctas_per_sm = 0);
+bool noise_fast_index_ok(const WorldDev& w);
 // counts -> offsets (each chunk's start rounded up to 4 instances); d_total[0]=span, d_total[1]=quads.
 // accumulate: offsets start at the current d_total[0] and the totals are advanced (slab chaining).
 size_t scan_workspace_bytes(size_t n);

@@ -11,6 +11,8 @@
 //   k_fill_cubes : heights -> 8-byte PaletteCube image incl. the in-chunk face flags CubeMesh::set
 //               leaves behind (server/src/chunk/mesh.rs:125-232).
 //   k_noise3d : 3-D simplex FBM tile (crates/simd-noise/src/noise/f32.rs:131-198).
+#include <math.h>
+
 #include "noise.cuh"
 
 namespace hb {
@@ -43,7 +45,7 @@ struct ColRegion {
 // staged once per CTA and there is no barrier in the column loop.  Thread mapping: sample i has x = i >> 5,
 // z = i & 31, i.e. heights are produced directly in voxel-column order x*32 + z (coalesced stores, no transpose);
 // the optional raw noise tile keeps the crate's order x + z*32 (noise/f32.rs:95-113) with a strided store.
-template <class Cols, int KIND>
+template <class Cols, int KIND, bool FAST>
 __global__ void __launch_bounds__(kThreads, 8) k_heights(WorldDev w, Cols cols, int ncol, int32_t* __restrict__ heights,
                                                        float* __restrict__ noise) {
     __shared__ NoiseTables s_tab;
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_heights(WorldDev w, Cols cols, 
             const int i0 = threadIdx.x + k * kThreads, i1 = i0 + kThreads;
             const float2 x = pk(__fadd_rn(start_x, __int2float_rn(i0 >> 5)), __fadd_rn(start_x, __int2float_rn(i1 >> 5)));
             const float2 z = pk(__fadd_rn(start_z, __int2float_rn(i0 & 31)), __fadd_rn(start_z, __int2float_rn(i1 & 31)));
-            const float2 r = noise2_pair<KIND>(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
+            const float2 r = noise2_pair<KIND, FAST>(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
             if (noise) {
                 noise[(size_t)col * HB_CHUNK_AREA + (i0 >> 5) + (i0 & 31) * 32] = r.x;
                 noise[(size_t)col * HB_CHUNK_AREA + (i1 >> 5) + (i1 & 31) * 32] = r.y;
@@ -222,20 +224,40 @@ __global__ void __launch_bounds__(kThreads) k_noise3d(WorldDev w, float sx, floa
     }
 }
 
+// FAST needs every lattice coordinate floor(x + F2*(x + y)) below 2^20 in magnitude (noise.cuh).  World block
+// coordinates are bounded by the chunk-coordinate limit, each octave multiplies by the lacunarity, and the skew adds
+// at most 2*F2 < 0.74 of the larger coordinate; 1.75 leaves a margin for rounding.
+bool fast_index_ok_impl(const WorldDev& w) {
+    const double c = ((double)HB_MAX_CHUNK_COORD + 1.0) * 32.0 * fabs((double)w.freq);
+    const double l = fabs((double)w.lacunarity) > 1.0 ? fabs((double)w.lacunarity) : 1.0;
+    const int oct = w.kind == HB_NOISE_GRADIENT ? 1 : w.octaves;
+    const double top = c * pow(l, oct - 1) * 1.75;
+    return top == top && top < 1048576.0;
+}
+
 template <class Cols>
 void launch_heights_kind(cudaStream_t s, const WorldDev& w, Cols cols, unsigned grid, int32_t* d_heights, float* d_noise) {
     const int ncol = (int)grid;
     const unsigned cap = (unsigned)num_sms() * 16u;  // two waves of the 8 resident CTAs per SM: measured best (8: +2 %, one CTA per column: +2 %)
     if (grid > cap) grid = cap;
+#define HB_LAUNCH_KIND(K)                                                                               \
+    do {                                                                                                \
+        if (fast) k_heights<Cols, K, true><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); \
+        else k_heights<Cols, K, false><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise);    \
+    } while (0)
+    const bool fast = fast_index_ok_impl(w);
     switch (w.kind) {
-        case HB_NOISE_RIDGE: k_heights<Cols, HB_NOISE_RIDGE><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); break;
-        case HB_NOISE_TURBULENCE: k_heights<Cols, HB_NOISE_TURBULENCE><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); break;
-        case HB_NOISE_GRADIENT: k_heights<Cols, HB_NOISE_GRADIENT><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); break;
-        default: k_heights<Cols, HB_NOISE_FBM><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); break;
+        case HB_NOISE_RIDGE: HB_LAUNCH_KIND(HB_NOISE_RIDGE); break;
+        case HB_NOISE_TURBULENCE: HB_LAUNCH_KIND(HB_NOISE_TURBULENCE); break;
+        case HB_NOISE_GRADIENT: HB_LAUNCH_KIND(HB_NOISE_GRADIENT); break;
+        default: HB_LAUNCH_KIND(HB_NOISE_FBM); break;
     }
+#undef HB_LAUNCH_KIND
 }
 
 }  // namespace
+
+bool noise_fast_index_ok(const WorldDev& w) { return fast_index_ok_impl(w); }
 
 cudaError_t launch_heights(cudaStream_t s, const WorldDev& w, const int32_t* d_cols_xz, size_t ncol,
                            int32_t* d_heights, float* d_noise) {

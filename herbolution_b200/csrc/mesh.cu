@@ -22,7 +22,7 @@
 // vector store is 16-byte aligned.
 #include <algorithm>
 
-#include "common.cuh"
+#include "noise.cuh"
 
 namespace hb {
 
@@ -39,10 +39,13 @@ constexpr int kStageCap = kT;   // quads expanded per window (one per thread)
 typedef unsigned long long u64;
 
 constexpr int kSeedLayers = 32;
-struct MeshSmem {
+// DESC = descriptors staged per round (the fused region kernel halves it to fit 5 CTAs per SM)
+template <int DESC>
+struct MeshSmemT {
+    static constexpr int kDesc = DESC;
     u64 occ[kTileN];                            // 9248 B
     __align__(16) float stage[kStageCap * 25];  // 25600 B
-    uint32_t desc[kDescCap];                    // 8192 B
+    uint32_t desc[DESC];                        // 8192 B
     int hts[kTileN];                            // 4624 B (region kernels: heights halo tile)
     __align__(16) float face_mat[6][12];
     float ao_lut[4];
@@ -53,6 +56,7 @@ struct MeshSmem {
     int red[3][8];
     u64 layer_seed[kSeedLayers];                // region kernels: the column's per-layer chunk hashes
 };
+using MeshSmem = MeshSmemT<kDescCap>;
 
 // ---- SipHash-1-3 with zero keys over the 12 bytes of ChunkPt: std DefaultHasher as used at
 // client/src/world/chunk.rs:182-184 ----
@@ -186,7 +190,8 @@ struct FacesFromPlanes {
 // one TMA bulk shared->global copy (UBLKCP) of the whole window by lane 0 instead of 200 LDS.128 + STG.128 through
 // the LSU.  The window is zero-padded to a multiple of 4 quads.  The wait for the engine to release the buffer from
 // this warp's previous window sits after the register work so the two overlap.
-__device__ __forceinline__ void emit_window(MeshSmem& sm, const MaterialsDev* __restrict__ mats, float* __restrict__ ws,
+template <class SM>
+__device__ __forceinline__ void emit_window(SM& sm, const MaterialsDev* __restrict__ mats, float* __restrict__ ws,
                                             uint32_t ws_shared, char* __restrict__ gdst, uint32_t nw, uint32_t L, uint32_t f,
                                             uint32_t ao, uint32_t id, int bx, int by, int bz) {
     const int lane = threadIdx.x & 31;
@@ -240,8 +245,8 @@ __device__ __forceinline__ void emit_window(MeshSmem& sm, const MaterialsDev* __
 // PACKED (with EMIT): instead of the 100-byte instance, `out` receives one 32-bit word per quad (hb_packed_quad:
 // L | face << 15 | ao << 18 | (material - 1) << 26), the gap zero-filled the same way.  The colour is not part of
 // the word: it is a pure function of (chunk, L, face) and the expander recomputes it (expand.cpp).
-template <bool EMIT, bool PACKED = false, class MatFn, class FacesFn>
-__device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, const FacesFn& faces, int bx, int by, int bz,
+template <bool EMIT, bool PACKED = false, class SM, class MatFn, class FacesFn>
+__device__ __forceinline__ uint32_t mesh_tile(SM& sm, const MatFn& mat, const FacesFn& faces, int bx, int by, int bz,
                                               const MaterialsDev* __restrict__ mats, float* __restrict__ out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t cnt[4], incl[4];
@@ -270,12 +275,12 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, co
     float* const ws = sm.stage + warp * (32 * 25);  // warp-private staging: 32 quads = 3200 B
     const uint32_t ws_shared = (uint32_t)__cvta_generic_to_shared(ws);
     char* const out_bytes = reinterpret_cast<char*>(out);
-    for (uint32_t d0 = 0; d0 < total; d0 += kDescCap) {
+    for (uint32_t d0 = 0; d0 < total; d0 += SM::kDesc) {
         // (a) visible faces of my columns -> descriptors (L | face << 15), in emission order
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             uint32_t o = base[k];
-            if (cnt[k] == 0 || o >= d0 + kDescCap || o + cnt[k] <= d0) continue;
+            if (cnt[k] == 0 || o >= d0 + SM::kDesc || o + cnt[k] <= d0) continue;
             const uint32_t Lc = (uint32_t)(((k * 8 + warp) << 10) | (lane << 5));
             uint32_t m[6];
             faces(k * 8 + warp, lane, m);  // cheap to re-evaluate; keeps registers free
@@ -289,13 +294,13 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, co
                 while (b) {  // faces of this voxel in bit order E, W, U, D, N, S
                     const uint32_t f = (uint32_t)__ffs(b) - 1u;
                     b &= b - 1u;
-                    if (o - d0 < (uint32_t)kDescCap) sm.desc[o - d0] = Ly | (f << 15);  // unsigned: also rejects o < d0
+                    if (o - d0 < (uint32_t)SM::kDesc) sm.desc[o - d0] = Ly | (f << 15);  // unsigned: also rejects o < d0
                     ++o;
                 }
             }
         }
         __syncthreads();
-        const uint32_t nd = min((uint32_t)kDescCap, total - d0);
+        const uint32_t nd = min((uint32_t)SM::kDesc, total - d0);
         if constexpr (PACKED) {
             // (b') one thread per quad: AO probes + material -> one coalesced 32-bit store
             uint32_t* const o32 = reinterpret_cast<uint32_t*>(out) + d0;
@@ -337,13 +342,14 @@ __device__ __forceinline__ uint32_t mesh_tile(MeshSmem& sm, const MatFn& mat, co
             emit_window(sm, mats, ws, ws_shared, out_bytes + (d0 + q0) * 100u, nw, L, f, ao, id, bx, by, bz);  // < 2^24 B / chunk
         }
         }  // !PACKED
-        if (d0 + kDescCap < total) __syncthreads();  // descriptors are rewritten in the next round
+        if (d0 + SM::kDesc < total) __syncthreads();  // descriptors are rewritten in the next round
     }
     }  // if constexpr (EMIT)
     return total;
 }
 
-__device__ __forceinline__ void load_tables(MeshSmem& sm, const MeshTables& tb) {
+template <class SM>
+__device__ __forceinline__ void load_tables(SM& sm, const MeshTables& tb) {
     for (int i = threadIdx.x; i < 72; i += kT) (&sm.face_mat[0][0])[i] = (&tb.face_mat[0][0])[i];
     if (threadIdx.x < 4) sm.ao_lut[threadIdx.x] = tb.ao_lut[threadIdx.x];
     if (threadIdx.x >= 64 && threadIdx.x < 112) {
@@ -922,6 +928,239 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
     if (EMIT && !PACKED) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Single-pass fused region kernel: noise -> heights -> count -> offsets -> emit in ONE launch.
+//
+// The staged pipeline runs k_heights (FP32/ALU-issue bound), k_count_region (ALU/latency) and the emit kernel (HBM-write
+// bound) one after the other, so the ALU-bound third of the step leaves HBM idle and the emit kernel leaves the ALUs
+// idle.  Here every persistent CTA takes one chunk column at a time and does all of it: the 34x34 heights halo is
+// evaluated from the noise function straight into shared memory (the one-column apron is recomputed: +13 % samples,
+// no heights round trip through HBM), the per-layer face counts come from the closed form of k_count_region, and the
+// column's place in the output comes from a chained scan over the columns in ticket order ("decoupled look-back":
+// each column publishes its span, then its inclusive prefix, in one 64-bit status word).  With four CTAs per SM in
+// different phases the SM's issue slots serve the noise of one column while the TMA engine streams another's quads.
+//
+// Offsets are the same exclusive scan over chunk index as launch_scan produces (tickets are handed out in column
+// order and a column's chunks are consecutive), so the output is bit-identical to the staged pipeline's.
+// Requires ncy <= 32 and the FBM noise kind; the launch wrapper falls back to the staged kernels otherwise.
+// ------------------------------------------------------------------------------------------------
+// Shared memory is what limits residency (5 CTAs/SM need <= 45 670 B each), so the buffers of the noise/count phase
+// live inside buffers only the emit phase uses: the noise tables (5 KB, rebuilt per column) over the occupancy tile,
+// the per-warp count accumulators over the descriptor buffer.
+constexpr int kFusedCtasPerSm = 5;
+using FusedMesh = MeshSmemT<1024>;
+struct FusedSmem {
+    FusedMesh sm;
+    uint32_t cnt[32];           // the column's quad count per layer
+    u64 off[32];                // and where each layer's quads go
+    int next_col;
+};
+static_assert(sizeof(NoiseTables) <= sizeof(u64) * kTileN, "noise tables alias the occupancy tile");
+static_assert(sizeof(uint32_t) * (kT / 32) * 32 <= sizeof(uint32_t) * FusedMesh::kDesc, "count accumulators alias the descriptors");
+static_assert((sizeof(FusedSmem) + 1024) * kFusedCtasPerSm <= 228 * 1024, "fused kernel: shared memory per SM");
+
+constexpr u64 kStatusAggregate = 1ULL << 62, kStatusPrefix = 2ULL << 62, kStatusValue = (1ULL << 62) - 1ULL;
+
+__device__ __forceinline__ u64 ld_status(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(u64* p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(kT, kFusedCtasPerSm)
+k_region_fused(const MeshTables tb, const MaterialsDev* __restrict__ mats, const WorldDev w, const RegionDev r,
+               int32_t* __restrict__ heights_out, uint32_t* __restrict__ counts, u64* __restrict__ offsets,
+               float* __restrict__ out, u64 capacity, u64* __restrict__ total, u64* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char fused_smem_raw[];
+    FusedSmem& fs = *reinterpret_cast<FusedSmem*>(fused_smem_raw);
+    FusedMesh& sm = fs.sm;
+    NoiseTables& nt = *reinterpret_cast<NoiseTables*>(sm.occ);                      // noise phase only
+    uint32_t (*const acc)[32] = reinterpret_cast<uint32_t (*)[32]>(sm.desc);       // count phase only
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_tables(sm, tb);
+    const RelHeight rel{(long long)r.cy0 * 32, 32 * r.ncy + 8};
+    const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
+    const int last = r.ncy - 1;
+    // every column, the first included, is drawn from the ticket counter (total[3]) at the moment its CTA starts on
+    // it: a ticket is only ever held by a CTA that is already evaluating that column's noise, so the look-back below
+    // waits at most one noise phase for a predecessor (drawing the next ticket early, while the current column is
+    // still being emitted, makes every successor wait for that emit: measured 6x slower)
+    for (;;) {
+        __syncthreads();  // previous column's readers of fs.* are done
+        if (tid == 0) fs.next_col = (int)atomicAdd(total + 3, 1ULL);
+        __syncthreads();
+        const int colw = fs.next_col;
+        if (colw >= ncols) break;
+        const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
+        const int cx = r.cx0 + ix, cz = r.cz0 + iz;
+        load_noise_tables(nt, w.seed_lo);  // the previous column's occupancy tile overwrote them
+        if (warp == 2 && lane < r.ncy) sm.layer_seed[lane] = siphash13_chunk(cx, r.cy0 + lane, cz);
+        __syncthreads();
+
+        // ---- 1. noise: the 34 x 34 halo of heights, two samples per packed evaluation (element e = xi*34 + zi;
+        //         pair = elements e and e + 578, i.e. tile rows xi and xi + 17)
+        int cmax = INT32_MIN, hmin = INT32_MAX, emin = INT32_MAX;
+        for (int p = tid; p < kTileN / 2; p += kT) {
+            const int xa = p / kTile, zi = p - xa * kTile, xb = xa + kTile / 2;
+            // world block coordinates are exact in f32 (|c| <= HB_MAX_CHUNK_COORD): the same values as the
+            // reference's start + i of whichever chunk the sample belongs to (noise/f32.rs:87-112)
+            const float2 x = pk(__int2float_rn(cx * 32 + xa - 1), __int2float_rn(cx * 32 + xb - 1));
+            const float2 z = bc(__int2float_rn(cz * 32 + zi - 1));
+            const float2 v = noise2_pair<HB_NOISE_FBM, FAST>(nt, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);
+            const int raw[2] = {height_from_noise(v.x), height_from_noise(v.y)};
+            const int dz = zi == 0 ? -1 : (zi == kTile - 1 ? 1 : 0);
+            const bool z_in = (unsigned)(iz + dz) < (unsigned)r.ncz;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int xi = k ? xb : xa;
+                const int dx = xi == 0 ? -1 : (xi == kTile - 1 ? 1 : 0);
+                const bool present = z_in && (unsigned)(ix + dx) < (unsigned)r.ncx;  // columns outside the region are ABSENT
+                const int h = rel(present ? raw[k] : kHeightAbsent);
+                sm.hts[xi * kTile + zi] = h;
+                const bool edge_x = dx != 0, edge_z = dz != 0;
+                hmin = min(hmin, h);
+                if (!(edge_x && edge_z)) emin = min(emin, h);
+                if (!edge_x && !edge_z) {
+                    cmax = max(cmax, h);
+                    if (heights_out)
+                        heights_out[((size_t)(ix - r.hx_begin) * r.ncz + iz) * HB_CHUNK_AREA + (xi - 1) * 32 + (zi - 1)] = raw[k];
+                }
+            }
+        }
+        cmax = __reduce_max_sync(0xffffffffu, cmax);
+        hmin = __reduce_min_sync(0xffffffffu, hmin);
+        emin = __reduce_min_sync(0xffffffffu, emin);
+        if (lane == 0) { sm.red[0][warp] = cmax; sm.red[1][warp] = hmin; sm.red[2][warp] = emin; }
+        acc[warp][lane] = 0;
+        __syncthreads();
+        cmax = __reduce_max_sync(0xffffffffu, lane < 8 ? sm.red[0][lane] : INT32_MIN);
+        hmin = __reduce_min_sync(0xffffffffu, lane < 8 ? sm.red[1][lane] : INT32_MAX);
+        emin = __reduce_min_sync(0xffffffffu, lane < 8 ? sm.red[2][lane] : INT32_MAX);
+
+        // ---- 2. count: closed form per layer, exactly k_count_region's (same masks as the emit stage)
+        for (int k = 0; k < 4; ++k) {
+            const int* o = sm.hts + (k * 8 + warp + 1) * kTile + (lane + 1);
+            const int hc = o[0], hE = o[kTile], hW = o[-kTile], hN = o[1], hS = o[-1];
+            int lo = min(min(hc - 1, hE), min(min(hW, hN), hS));
+            lo = hc > 0 ? (lo < 0 ? 0 : lo >> 5) : INT32_MAX;
+            const int hi = hc > 0 ? (hc - 1) >> 5 : -1;
+            const int wlo = __reduce_min_sync(0xffffffffu, lo);
+            const int whi = __reduce_max_sync(0xffffffffu, hi);
+            const int nsolid = __popc(__ballot_sync(0xffffffffu, hc > 0));
+            const int j1 = min(whi, last);
+            for (int j = max(wlo, 0); j <= j1; ++j) {  // warp-uniform bounds
+                const int a = j * 32;
+                const int rc = min(max(hc - a, 0), 32);
+                uint32_t v = 0;
+                if (rc > 0) {
+                    v = max(0, rc - min(max(hE - a, 0), 32)) + max(0, rc - min(max(hW - a, 0), 32)) +
+                        max(0, rc - min(max(hN - a, 0), 32)) + max(0, rc - min(max(hS - a, 0), 32));
+                    v += (hc - a <= 32 || j == last) ? 1u : 0u;
+                    v += (j == 0) ? 1u : 0u;
+                }
+                v = __reduce_add_sync(0xffffffffu, v);
+                if (lane == 0) acc[warp][j] += v;
+            }
+            if (lane == 0 && nsolid) {
+                if (wlo > 0) acc[warp][0] += nsolid * (last == 0 ? 2 : 1);
+                if (last > 0 && last < wlo) acc[warp][last] += nsolid;
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. offsets: warp 0 scans the column's layers and chains the column into the global order
+        if (warp == 0) {
+            uint32_t c = 0;
+            if (lane < r.ncy) {
+#pragma unroll
+                for (int wq = 0; wq < kT / 32; ++wq) c += acc[wq][lane];
+            }
+            const u64 span = ((u64)c + 3ULL) & ~3ULL;
+            u64 incl = span;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const u64 col_span = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t col_quads = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) st_status(status + colw, kStatusAggregate | col_span);
+            // look back over the preceding columns, 32 at a time: sum aggregates down to the nearest inclusive prefix
+            u64 excl = 0;
+            for (int j = colw - 1; j >= 0;) {
+                const int idx = j - lane;
+                u64 v;
+                do {
+                    v = idx >= 0 ? ld_status(status + idx) : kStatusPrefix;  // before column 0: prefix 0
+                } while (__any_sync(0xffffffffu, (v >> 62) == 0ULL));
+                const uint32_t is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2ULL);
+                const int stop = is_prefix ? __ffs(is_prefix) - 1 : 32;  // nearest prefix (lowest lane = closest column)
+                u64 part = lane <= stop ? (v & kStatusValue) : 0ULL;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                excl += part;
+                if (is_prefix) break;
+                j -= 32;
+            }
+            if (lane == 0) {
+                st_status(status + colw, kStatusPrefix | (excl + col_span));
+                if (col_quads) atomicAdd(total + 1, (u64)col_quads);
+                if (colw == ncols - 1) total[0] = excl + col_span;
+            }
+            if (lane < r.ncy) {
+                const u64 o = excl + incl - span;
+                fs.cnt[lane] = c;
+                fs.off[lane] = o;
+                counts[(size_t)colw * r.ncy + lane] = c;
+                offsets[(size_t)colw * r.ncy + lane] = o;
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. emit, layer by layer (the body of k_mesh_region<true>)
+        for (int iy = 0; iy < r.ncy; ++iy) {
+            const uint32_t my_count = fs.cnt[iy];
+            if (my_count == 0) continue;  // block-uniform: all air, buried, or no visible face
+            const u64 off = fs.off[iy];
+            if (off + (((u64)my_count + 3ULL) & ~3ULL) > capacity) {
+                if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
+                continue;
+            }
+            const int cy = r.cy0 + iy;
+            const int a = iy * 32;
+            const MatHeights mat{sm.hts, a};
+            if (iy == 0 && r.ncy > 1 && emin >= a + 33) {  // region-bottom slab: one Down face per column
+                if (tid == 32) sm.rng_seed = sm.layer_seed[iy];
+                __syncthreads();
+                float* const ws = sm.stage + warp * (32 * 25);
+                const uint32_t ws_shared = (uint32_t)__cvta_generic_to_shared(ws);
+                char* const out_bytes = reinterpret_cast<char*>(out + off * 25ULL);
+                for (uint32_t q0 = warp * 32u; q0 < (uint32_t)HB_CHUNK_AREA; q0 += (kT / 32) * 32u) {
+                    const uint32_t L = (q0 + lane) << 5;
+                    emit_window(sm, mats, ws, ws_shared, out_bytes + q0 * 100u, 32u, L, 3u, 0u, mat(L, L >> 10, 0, (L >> 5) & 31),
+                                cx * 32, cy * 32, cz * 32);
+                }
+                continue;
+            }
+            __syncthreads();  // previous layer's readers of sm.occ / sm.rng_seed are done
+            const u64 ymask = 0x3FFFFFFFFULL & ~(iy == 0 ? 1ULL : 0ULL) & ~(iy == r.ncy - 1 ? (1ULL << 33) : 0ULL);
+            for (int i = tid; i < kTileN; i += kT) {
+                const int d = min(max(sm.hts[i] - (a - 1), 0), 34);
+                sm.occ[i] = ((1ULL << d) - 1ULL) & ymask;
+            }
+            if (tid == 32) sm.rng_seed = sm.layer_seed[iy];
+            __syncthreads();
+            mesh_tile<true>(sm, mat, FacesFromOcc{sm.occ}, cx * 32, cy * 32, cz * 32, mats, out + off * 25ULL);
+        }
+    }
+    bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
+}
+
 // ------------------------------------------------------------------------------------------------
 // counts -> offsets.  Each chunk's span is its count rounded up to 4 instances.  Three small
 // kernels (tile sums, scan of tile sums, offsets); no atomics, deterministic.
@@ -1107,6 +1346,40 @@ cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, 
         if (e != cudaSuccess) return e;
         k_count_region<<<(unsigned)std::min<size_t>(ncols, (size_t)num_sms() * 8), kT, 0, s>>>(r, d_heights, d_counts, (u64*)d_total + 3);
     }
+    return cudaGetLastError();
+}
+
+bool region_fused_supported(const WorldDev& w, const RegionDev& r) { return w.kind == HB_NOISE_FBM && r.ncy <= 32; }
+
+size_t region_fused_status_bytes(const RegionDev& r) { return (size_t)(r.ix_end - r.ix_begin) * r.ncz * sizeof(u64); }
+
+cudaError_t launch_region_fused(cudaStream_t s, const MeshTables& tb, const MaterialsDev* d_mats, const WorldDev& w,
+                                const RegionDev& r, int32_t* d_heights, uint32_t* d_counts, uint64_t* d_offsets,
+                                hb_instance3d* d_out, uint64_t capacity, uint64_t* d_total, uint64_t* d_status, bool fast,
+                                int ctas_per_sm) {
+    const size_t ncols = (size_t)(r.ix_end - r.ix_begin) * r.ncz;
+    if (ncols == 0 || r.ncy == 0) return cudaSuccess;
+    static bool attr_set[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_region_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_region_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    cudaError_t e = cudaMemsetAsync(d_total, 0, 4 * sizeof(uint64_t), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, ncols * sizeof(u64), s);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1 || ctas_per_sm > kFusedCtasPerSm) ctas_per_sm = kFusedCtasPerSm;
+    size_t grid = (size_t)num_sms() * ctas_per_sm;
+    if (grid > ncols) grid = ncols;
+    if (fast)
+        k_region_fused<true><<<(unsigned)grid, kT, sizeof(FusedSmem), s>>>(tb, d_mats, w, r, d_heights, d_counts, (u64*)d_offsets,
+                                                                           (float*)d_out, capacity, (u64*)d_total, (u64*)d_status);
+    else
+        k_region_fused<false><<<(unsigned)grid, kT, sizeof(FusedSmem), s>>>(tb, d_mats, w, r, d_heights, d_counts, (u64*)d_offsets,
+                                                                            (float*)d_out, capacity, (u64*)d_total, (u64*)d_status);
     return cudaGetLastError();
 }
 

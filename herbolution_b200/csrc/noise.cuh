@@ -46,22 +46,24 @@ __device__ __forceinline__ float2 grad2_of(int seed_lo, int hash) {
                        (lt4 ? b2 : b1) ? ym : -ym);
 }
 
-// Shared-memory tables for the 2-D path: the permutation (256 B) and, per permutation slot, the
-// gradient it selects for this seed (gx[i], gy[i] = grad2(P[i]), 2 KB).  A corner's gradient is then two
-// dependent shared loads instead of a load plus ~12 select/logic instructions.  gx and gy are separate
-// arrays so that the values of two samples land in adjacent registers (operands of the packed f32x2 ops).
+// Shared-memory tables for the 2-D path, laid out so that no index needs a mask or a shift:
+//   perm4[k] = 4 * P[k & 255]  (u16, 258 entries used: k = jj and jj + 1 with jj in 0..255)
+//   gx[k], gy[k] = grad2(P[k & 255]) for this seed, k in 0..511 (k = ii + P[..] (+1) with ii in 0..255)
+// The reference's own table is the permutation twice (512 x i32, simplex_32.rs:29-46) for the same reason.
+// A corner's gradient is two dependent shared loads instead of a load plus ~12 select/logic instructions.  gx and gy
+// are separate arrays so that the values of two samples land in adjacent registers (operands of the packed ops).
 struct NoiseTables {
-    __align__(16) uint8_t perm[256];
-    __align__(16) float gx[256];
-    __align__(16) float gy[256];
+    __align__(16) uint16_t perm4[512];
+    __align__(16) float gx[512];
+    __align__(16) float gy[512];
 };
 
 // Cooperative table setup (call from all threads, then __syncthreads()).
 __device__ __forceinline__ void load_noise_tables(NoiseTables& t, int seed_lo) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const int p = kPerm[i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        const int p = kPerm[i & 255];
         const float2 g = grad2_of(seed_lo, p);
-        t.perm[i] = (uint8_t)p;
+        t.perm4[i] = (uint16_t)(p * 4);
         t.gx[i] = g.x;
         t.gy[i] = g.y;
     }
@@ -90,34 +92,74 @@ __device__ __forceinline__ float2 sadd2(float2 a, float2 b) { return pk(__fadd_r
 // float2 (.x = sample A, .y = sample B).  The arithmetic per sample is op for op the reference's: separate
 // round-to-nearest add/mul everywhere, true FMA only at the six neg_mul_add sites
 // (_mm256_fnmadd_ps, simd/ops/f32.rs:141-145).  x and y must not be the direct result of a packed multiply.
+//
+// FAST (every lattice coordinate |floor(x + s)| < 2^20, which the launch wrapper proves from the world parameters and
+// the chunk-coordinate limit): the integer side never leaves the FP32/ALU pipes -- no F2I / I2F (quarter-rate XU pipe):
+//   * table indices come from "magic" adds: ips is integral, so ips + 1.5*2^21 is exact and its mantissa holds
+//     (2^20 + ips) << 2; `& 1020` is (i & 255) * 4, the byte offset into gx/gy.  Likewise jps + 1.5*2^22 gives
+//     (j & 255) * 2, the byte offset into perm4.
+//   * t = f32(i + j) * G2 is computed as (ips + jps) * G2: the float sum of two integral values below 2^21 is exact
+//     and equals the converted integer sum.
+//   * j1 = (y0 > x0) is taken as NOT (x0 >= y0), i.e. -1 - i1 in float: identical for every non-NaN input, and
+//     coordinates are finite by construction.
+// Bit-exactness of the result is what tests/test_gpu_parity.py::test_noise_tiles_bit_exact asserts (0 ulp).
+template <bool FAST>
 __device__ __forceinline__ float2 simplex2_pair(const NoiseTables& T, float2 x, float2 y) {
     const float2 s = smul2(bc(HB_F2), add2(x, y));  // feeds x + s, y + s
     const float2 xs = add2(x, s), ys = add2(y, s);
     const float2 ips = pk(floorf(xs.x), floorf(xs.y)), jps = pk(floorf(ys.x), floorf(ys.y));
-    const int iA = __float2int_rz(ips.x), iB = __float2int_rz(ips.y);  // exact: integral (cast_i32, simd/ops/f32.rs:716-739)
-    const int jA = __float2int_rz(jps.x), jB = __float2int_rz(jps.y);
-    const float2 t = smul2(pk(__int2float_rn(iA + jA), __int2float_rn(iB + jB)), bc(HB_G2));  // feeds ips - t, jps - t
-    const float2 x0 = sub2(x, sub2(ips, t));
-    const float2 y0 = sub2(y, sub2(jps, t));
-
-    const bool xgeA = x0.x >= y0.x, xgeB = x0.y >= y0.y;  // i1 = all-ones mask (-1) when x0 >= y0
-    const bool ygtA = y0.x > x0.x, ygtB = y0.y > x0.y;    // j1
-    const float2 x1 = add2(add2(x0, pk(xgeA ? -1.0f : 0.0f, xgeB ? -1.0f : 0.0f)), bc(HB_G2));
-    const float2 y1 = add2(add2(y0, pk(ygtA ? -1.0f : 0.0f, ygtB ? -1.0f : 0.0f)), bc(HB_G2));
+    float2 t, x0, y0, x1, y1, g0x, g0y, g1x, g1y, g2x, g2y;
+    if constexpr (FAST) {
+        const float2 mi = add2(ips, bc(3145728.0f));  // 1.5 * 2^21
+        const float2 mj = add2(jps, bc(6291456.0f));  // 1.5 * 2^22
+        t = smul2(add2(ips, jps), bc(HB_G2));         // feeds ips - t, jps - t
+        x0 = sub2(x, sub2(ips, t));
+        y0 = sub2(y, sub2(jps, t));
+        const bool xgeA = x0.x >= y0.x, xgeB = x0.y >= y0.y;  // i1 = all-ones mask (-1) when x0 >= y0
+        const float2 i1f = pk(xgeA ? -1.0f : 0.0f, xgeB ? -1.0f : 0.0f);
+        const float2 j1f = sub2(bc(-1.0f), i1f);              // -1 where y0 > x0
+        x1 = add2(add2(x0, i1f), bc(HB_G2));
+        y1 = add2(add2(y0, j1f), bc(HB_G2));
+        // gi_k = P[(ii + di) + P[jj + dj]] (simplex_32.rs:137-141) as byte offsets; k1 is k0 + 1 when i1 is set
+        // (then j1 is not: P[jj]), else P[jj + 1] without the +1
+        const char* const pb = reinterpret_cast<const char*>(T.perm4);
+        const char* const gxb = reinterpret_cast<const char*>(T.gx);
+        const char* const gyb = reinterpret_cast<const char*>(T.gy);
+        const uint32_t iiA = __float_as_uint(mi.x) & 1020u, iiB = __float_as_uint(mi.y) & 1020u;
+        const uint32_t jjA = __float_as_uint(mj.x) & 510u, jjB = __float_as_uint(mj.y) & 510u;
+        const uint32_t a0A = iiA + *reinterpret_cast<const uint16_t*>(pb + jjA);
+        const uint32_t a2A = iiA + *reinterpret_cast<const uint16_t*>(pb + jjA + 2);
+        const uint32_t a0B = iiB + *reinterpret_cast<const uint16_t*>(pb + jjB);
+        const uint32_t a2B = iiB + *reinterpret_cast<const uint16_t*>(pb + jjB + 2);
+        const uint32_t a1A = xgeA ? a0A + 4u : a2A, a1B = xgeB ? a0B + 4u : a2B;
+#define HB_G(tab, off) (*reinterpret_cast<const float*>((tab) + (off)))
+        g0x = pk(HB_G(gxb, a0A), HB_G(gxb, a0B)); g0y = pk(HB_G(gyb, a0A), HB_G(gyb, a0B));
+        g1x = pk(HB_G(gxb, a1A), HB_G(gxb, a1B)); g1y = pk(HB_G(gyb, a1A), HB_G(gyb, a1B));
+        g2x = pk(HB_G(gxb, a2A + 4u), HB_G(gxb, a2B + 4u)); g2y = pk(HB_G(gyb, a2A + 4u), HB_G(gyb, a2B + 4u));
+#undef HB_G
+    } else {
+        const int iA = __float2int_rz(ips.x), iB = __float2int_rz(ips.y);  // exact: integral (cast_i32, simd/ops/f32.rs:716-739)
+        const int jA = __float2int_rz(jps.x), jB = __float2int_rz(jps.y);
+        t = smul2(pk(__int2float_rn(iA + jA), __int2float_rn(iB + jB)), bc(HB_G2));  // feeds ips - t, jps - t
+        x0 = sub2(x, sub2(ips, t));
+        y0 = sub2(y, sub2(jps, t));
+        const bool xgeA = x0.x >= y0.x, xgeB = x0.y >= y0.y;  // i1 = all-ones mask (-1) when x0 >= y0
+        const bool ygtA = y0.x > x0.x, ygtB = y0.y > x0.y;    // j1
+        x1 = add2(add2(x0, pk(xgeA ? -1.0f : 0.0f, xgeB ? -1.0f : 0.0f)), bc(HB_G2));
+        y1 = add2(add2(y0, pk(ygtA ? -1.0f : 0.0f, ygtB ? -1.0f : 0.0f)), bc(HB_G2));
+        // indices are taken mod 256 because the reference's 512-entry table is the permutation twice
+        const int pj0A = T.perm4[jA & 255] >> 2, pj1A = T.perm4[(jA + 1) & 255] >> 2;
+        const int pj0B = T.perm4[jB & 255] >> 2, pj1B = T.perm4[(jB + 1) & 255] >> 2;
+        const int k0A = (iA + pj0A) & 255, k0B = (iB + pj0B) & 255;
+        const int k1A = (iA + (xgeA ? 1 : 0) + (ygtA ? pj1A : pj0A)) & 255;
+        const int k1B = (iB + (xgeB ? 1 : 0) + (ygtB ? pj1B : pj0B)) & 255;
+        const int k2A = (iA + 1 + pj1A) & 255, k2B = (iB + 1 + pj1B) & 255;
+        g0x = pk(T.gx[k0A], T.gx[k0B]); g0y = pk(T.gy[k0A], T.gy[k0B]);
+        g1x = pk(T.gx[k1A], T.gx[k1B]); g1y = pk(T.gy[k1A], T.gy[k1B]);
+        g2x = pk(T.gx[k2A], T.gx[k2B]); g2y = pk(T.gy[k2A], T.gy[k2B]);
+    }
     const float2 x2 = add2(add2(x0, bc(-1.0f)), bc(HB_G22));
     const float2 y2 = add2(add2(y0, bc(-1.0f)), bc(HB_G22));
-
-    // gi_k = P[(ii + di) + P[jj + dj]] (simplex_32.rs:137-141); indices are taken mod 256 because the
-    // reference's 512-entry table is the permutation twice
-    const int pj0A = T.perm[jA & 255], pj1A = T.perm[(jA + 1) & 255];
-    const int pj0B = T.perm[jB & 255], pj1B = T.perm[(jB + 1) & 255];
-    const int k0A = (iA + pj0A) & 255, k0B = (iB + pj0B) & 255;
-    const int k1A = (iA + (xgeA ? 1 : 0) + (ygtA ? pj1A : pj0A)) & 255;
-    const int k1B = (iB + (xgeB ? 1 : 0) + (ygtB ? pj1B : pj0B)) & 255;
-    const int k2A = (iA + 1 + pj1A) & 255, k2B = (iB + 1 + pj1B) & 255;
-    const float2 g0x = pk(T.gx[k0A], T.gx[k0B]), g0y = pk(T.gy[k0A], T.gy[k0B]);
-    const float2 g1x = pk(T.gx[k1A], T.gx[k1B]), g1y = pk(T.gy[k1A], T.gy[k1B]);
-    const float2 g2x = pk(T.gx[k2A], T.gx[k2B]), g2y = pk(T.gy[k2A], T.gy[k2B]);
 
     float2 t0 = fnma2(y0, y0, fnma2(x0, x0, bc(0.5f)));
     float2 t1 = fnma2(y1, y1, fnma2(x1, x1, bc(0.5f)));
@@ -139,18 +181,30 @@ __device__ __forceinline__ float2 simplex2_pair(const NoiseTables& T, float2 x, 
     return mul2(sadd2(n0, sadd2(n1, n2)), bc(45.26450774985561631259f));
 }
 
+// x * lacunarity for the next octave; the product feeds adds inside simplex2_pair, so it must not be a packed
+// multiply (see CAUTION above).  For lacunarity == 2 (the game's) x + x is the same value and packs.  LAC2 is a
+// template parameter of the octave loops so that the choice is made once, outside them.
+template <bool LAC2>
+__device__ __forceinline__ float2 next_octave(float2 v, float lac) {
+    return LAC2 ? add2(v, v) : smul2(v, bc(lac));
+}
+
 // functions/fbm_32.rs:18-31, two samples at once
-__device__ __forceinline__ float2 fbm2_pair(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
-    float2 result = simplex2_pair(T, x, y);
+template <bool FAST, bool LAC2>
+__device__ __forceinline__ float2 fbm2_octaves(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
+    float2 result = simplex2_pair<FAST>(T, x, y);
     float amp = 1.0f;
-    const float2 lac = bc(w.lacunarity);
     for (int o = 1; o < w.octaves; ++o) {
-        x = smul2(x, lac);  // scalar: x and y feed adds inside simplex2_pair
-        y = smul2(y, lac);
+        x = next_octave<LAC2>(x, w.lacunarity);
+        y = next_octave<LAC2>(y, w.lacunarity);
         amp = __fmul_rn(amp, w.gain);
-        result = sadd2(mul2(simplex2_pair(T, x, y), bc(amp)), result);
+        result = sadd2(mul2(simplex2_pair<FAST>(T, x, y), bc(amp)), result);
     }
     return result;
+}
+template <bool FAST>
+__device__ __forceinline__ float2 fbm2_pair(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
+    return w.lacunarity == 2.0f ? fbm2_octaves<FAST, true>(T, x, y, w) : fbm2_octaves<FAST, false>(T, x, y, w);
 }
 
 __device__ __forceinline__ float2 abs2(float2 a) { return pk(fabsf(a.x), fabsf(a.y)); }  // andnot(-0.0, a), simd/ops/f32.rs:307-310
@@ -160,19 +214,18 @@ __device__ __forceinline__ float2 abs2(float2 a) { return pk(fabsf(a.x), fabsf(a
 //   turbulence_2d (functions/turbulence_32.rs:18-32): r = |s0|;      r = r + |s * amp|
 //   gradient      (noise/gradient.rs:77-79):          r = s0
 // KIND is a template parameter so the FBM kernel's code is untouched by the variants.
-template <int KIND>
+template <int KIND, bool FAST>
 __device__ __forceinline__ float2 noise2_pair(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
-    if (KIND == HB_NOISE_FBM) return fbm2_pair(T, x, y, w);
-    const float2 s0 = simplex2_pair(T, x, y);
+    if (KIND == HB_NOISE_FBM) return fbm2_pair<FAST>(T, x, y, w);
+    const float2 s0 = simplex2_pair<FAST>(T, x, y);
     if (KIND == HB_NOISE_GRADIENT) return s0;
     float2 result = KIND == HB_NOISE_RIDGE ? sadd2(bc(1.0f), neg2(abs2(s0))) : abs2(s0);
     float amp = 1.0f;
-    const float2 lac = bc(w.lacunarity);
     for (int o = 1; o < w.octaves; ++o) {
-        x = smul2(x, lac);
-        y = smul2(y, lac);
+        x = next_octave<false>(x, w.lacunarity);
+        y = next_octave<false>(y, w.lacunarity);
         amp = __fmul_rn(amp, w.gain);
-        const float2 sv = simplex2_pair(T, x, y);
+        const float2 sv = simplex2_pair<FAST>(T, x, y);
         if (KIND == HB_NOISE_RIDGE) {
             const float2 a = abs2(sv);
             result = sadd2(result, pk(__fmaf_rn(-a.x, amp, 1.0f), __fmaf_rn(-a.y, amp, 1.0f)));

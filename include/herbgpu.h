@@ -223,6 +223,13 @@ HB_API int hb_generate_mesh_region_packed(hb_ctx *ctx, const hb_region *region, 
  * it concurrently on one ctx (as long as nobody changes the materials meanwhile).  Uses the ctx's palette colours. */
 HB_API int hb_expand_quads(hb_ctx *ctx, hb_chunk_pt pt, const hb_packed_quad *quads, uint32_t n, hb_instance3d *out);
 
+/* Measurement helpers: the two ceilings of the end-to-end path, measured with the ctx's own buffers and threads so
+ * that several ctxs (GPUs) can be probed at the same moment.  hb_probe_d2h: plain cudaMemcpyAsync device -> pinned
+ * host of `bytes`, `reps` times back to back (GB/s by CUDA events).  hb_probe_host_write: the expander's worker pool
+ * filling `bytes` of the expanded-slab buffer with non-temporal stores (GB/s by wall clock). */
+HB_API int hb_probe_d2h(hb_ctx *ctx, size_t bytes, int32_t reps, double *gbs);
+HB_API int hb_probe_host_write(hb_ctx *ctx, size_t bytes, int32_t reps, double *gbs);
+
 /* ---- device-resident pipeline (kernel-only measurement, chaining with other CUDA work) ----
  * A plan owns the device buffers for region chunks with ix in [ix_begin, ix_end).  Stages only
  * ENQUEUE kernels on `stream` (a cudaStream_t passed as void*; NULL = the ctx stream). */
@@ -234,6 +241,10 @@ enum {
     HB_STAGE_EMIT = 8,     /* write hb_instance3d */
     HB_STAGE_FILL = 16,    /* write u16 block ids (plan created with want_ids) */
     HB_STAGE_EMIT_PACKED = 32, /* write hb_packed_quad words at the same offsets (hb_region_plan_packed) */
+    HB_STAGE_FUSED = 64,   /* HEIGHTS + COUNT + SCAN + EMIT as ONE kernel launch (noise evaluated per column incl. its
+                              apron, offsets by a chained scan over the columns); same results, bit for bit.  The
+                              heights buffer then holds the slab's own columns only (enough for FILL).  Regions
+                              with more than 32 layers or a non-FBM noise kind run the four staged kernels instead. */
     HB_STAGE_ALL_MESH = 15
 };
 /* quad_capacity 0 = size the instance buffer by running HEIGHTS+COUNT+SCAN once (synchronous). */

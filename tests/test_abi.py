@@ -136,25 +136,44 @@ def test_noise_kernel_has_no_unintended_fma_contraction():
     """ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false; the reference's
     operator overloads never fuse (only the six neg_mul_add sites of simplex_2d do).  csrc/noise.cuh routes every
     product that feeds an add across a packed/scalar boundary; this pins the result in the shipped SASS:
-    the FBM k_heights evaluates 4 simplex pairs in its instruction stream (2 pairs x {first octave, octave loop}),
-    so it must contain exactly 4 x 6 FFMA2 and no scalar FFMA at all.  The other noise kinds (template parameter
-    KIND, HB_NOISE_*): turbulence the same, gradient 2 x 6 (no octave loop), ridge 24 plus its own neg_mul_add
-    (functions/ridge_32.rs:27, fused on AVX2) = one scalar FFMA per lane of each of the 2 packed loop bodies."""
+    the FBM k_heights evaluates 6 simplex pairs in its instruction stream (2 pairs x {first octave, octave loop for
+    lacunarity == 2, octave loop for any other lacunarity}), so it must contain exactly 6 x 6 FFMA2 and no scalar FFMA
+    at all.  The other noise kinds (template parameter KIND, HB_NOISE_*) have one octave loop: turbulence 4 x 6,
+    gradient 2 x 6 (no octave loop), ridge 24 plus its own neg_mul_add (functions/ridge_32.rs:27, fused on AVX2) = one
+    scalar FFMA per lane of each of the 2 packed loop bodies.  Every kind exists with the conversion-free index path
+    (FAST) and with the exact-conversion fallback."""
     import shutil
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
     sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
     funcs = re.split(r"\n\s*Function : ", sass)
     heights = [f for f in funcs if "k_heights" in f.split("\n", 1)[0]]
-    assert len(heights) == 8  # {ColList, ColRegion} x 4 noise kinds
-    want = {0: (24, 0), 1: (24, 4), 2: (24, 0), 3: (12, 0)}  # KIND -> (FFMA2, scalar FFMA)
+    assert len(heights) == 16  # {ColList, ColRegion} x 4 noise kinds x {FAST, exact}
+    # KIND -> scalar FFMA per simplex pair in an octave loop body (ridge only), FMUL2 besides the 16 of a simplex
+    # pair (FBM: the packed `simplex * amp` of every loop body).  How many copies of the simplex pair the compiler
+    # lays down (loop peeling, the two lacunarity variants) is its business; the per-pair mix is not.
+    want = {0: (0, 1), 1: (2, 0), 2: (0, 0), 3: (0, 0)}
+    conv = {}
     for f in heights:
-        kind = int(re.search(r"ELi(\d)EEEv", f.split("\n", 1)[0]).group(1))
+        m = re.search(r"ELi(\d)ELb([01])EEEv", f.split("\n", 1)[0])
+        kind, fast = int(m.group(1)), m.group(2) == "1"
         ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", f)
         packed = sum(o.startswith("FFMA2") for o in ops)
         scalar = sum(o.startswith("FFMA") and not o.startswith("FFMA2") for o in ops)
-        assert (packed, scalar) == want[kind], f"kind {kind}: FMA count changed, check for contraction"
+        assert packed % 6 == 0 and packed >= 12, f"kind {kind}: FFMA2 count {packed} is not 6 per simplex pair"
+        pairs, firsts = packed // 6, 2  # two first-octave evaluations (k = 0, 2) precede the loops
+        assert scalar == want[kind][0] * (pairs - firsts), f"kind {kind}: scalar FFMA count {scalar}, check for contraction"
+        fmul2 = sum(o.startswith("FMUL2") for o in ops)
+        # a contraction would turn one FMUL2 per site into an extra FFMA2: fewer than 16 FMUL2 per counted pair
+        assert 16 * pairs <= fmul2 <= 16 * pairs + want[kind][1] * (pairs - firsts), f"kind {kind}: {fmul2} FMUL2 for {pairs} simplex pairs"
         assert sum(o.startswith("FMUL2") for o in ops) > 0 and sum(o.startswith("FADD2") for o in ops) > 0  # Blackwell packed f32x2
+        conv[(f.split("\n", 1)[0].split("k_heights")[1][:16], kind, fast)] = (sum(o.startswith(("F2I", "I2F")) for o in ops), pairs)
+    # the FAST index path stays off the quarter-rate conversion pipe: each simplex pair of the exact path converts
+    # 4 floors to integers and 2 sums back (6 F2I / I2F); the FAST path has none (what is left sets up coordinates)
+    for (name, kind, fast), (n_conv, pairs) in conv.items():
+        if fast:
+            n_exact, pairs_exact = conv[(name, kind, False)]
+            assert n_exact - 6 * pairs_exact >= n_conv - 2 and n_conv <= 20, f"conversions crept back into the FAST noise path ({n_conv})"
     # the whole library is compiled without FMA contraction in the 3-D noise path too (reference: no FMAs there)
     # (reference: no FMAs there except ridge_3d's neg_mul_add, functions/ridge_32.rs:43)
     n3 = [f for f in funcs if "k_noise3d" in f.split("\n", 1)[0]]
