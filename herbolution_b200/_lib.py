@@ -86,6 +86,7 @@ PROTOTYPES = {
     "hb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "hb_destroy": (None, [C.c_void_p]),
     "hb_set_noise_kind": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hb_set_fma_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "hb_last_error": (C.c_char_p, []),
     "hb_version": (C.c_char_p, []),
     "hb_set_world": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_float, C.c_float]),
@@ -110,6 +111,19 @@ PROTOTYPES = {
     "hb_generate_mesh_region_packed": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.c_int32, C.c_int, REGION_SINK,
                                                  C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_expand_quads": (C.c_int, [C.c_void_p, ChunkPtC, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "hb_multi_create": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
+    "hb_multi_destroy": (None, [C.c_void_p]),
+    "hb_multi_device_count": (C.c_int32, [C.c_void_p]),
+    "hb_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "hb_multi_set_world": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_float, C.c_float]),
+    "hb_multi_set_noise_kind": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hb_multi_set_fma_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hb_multi_set_materials": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
+    "hb_multi_set_region_transport": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hb_multi_set_host_threads": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hb_multi_slab": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "hb_multi_generate_mesh_region": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int, REGION_SINK, C.c_void_p,
+                                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_probe_d2h": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
     "hb_probe_host_write": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
     "hb_region_plan_packed": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "herbolution_b200", "csrc")
 LIB = os.path.join(ROOT, "herbolution_b200", "libherbgpu.so")
 
-CUDA_SOURCES = ["gen.cu", "mesh.cu", "api.cu", "world.cu", "codec.cu", "expand.cu"]
+CUDA_SOURCES = ["gen.cu", "mesh.cu", "api.cu", "world.cu", "codec.cu", "expand.cu", "multi.cu"]
 CUDA_DEPS = CUDA_SOURCES + ["common.cuh", "noise.cuh", "host_common.cuh", os.path.join("..", "..", "include", "herbgpu.h")]
 
 NVCC_FLAGS = [

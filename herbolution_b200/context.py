@@ -76,6 +76,79 @@ class RegionPlan:
             pass
 
 
+def _region_sink_cb(sink):
+    """ctypes trampoline for hb_region_sink -> sink(first_chunk, offsets, counts, instances, ids or None)."""
+
+    def _cb(_user, first, n, p_off, p_cnt, p_inst, span, p_ids):
+        if sink is None:
+            return
+        off = np.frombuffer((C.c_uint64 * n).from_address(p_off), dtype=np.uint64) if n else np.zeros(0, np.uint64)
+        cnt = np.frombuffer((C.c_uint32 * n).from_address(p_cnt), dtype=np.uint32) if n else np.zeros(0, np.uint32)
+        inst = np.frombuffer((C.c_char * (span * 100)).from_address(p_inst), dtype=INSTANCE_DTYPE) if span else \
+            np.zeros(0, INSTANCE_DTYPE)
+        ids = None
+        if p_ids:
+            ids = np.frombuffer((C.c_uint16 * (n * CHUNK_VOLUME)).from_address(p_ids), dtype=np.uint16)
+            ids = ids.reshape(n, CHUNK_VOLUME)
+        sink(first, off, cnt, inst, ids)
+
+    return _lib.REGION_SINK(_cb)
+
+
+class MultiContext:
+    """hb_multi: one process driving several GPUs behind one handle (include/herbgpu.h).  devices=None takes every
+    visible device.  The region call splits the x range into one slab per device; the sink is serialised."""
+
+    def __init__(self, devices=None, seed: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        if devices is None:
+            check(self._lib.hb_multi_create(None, 0, C.byref(self._h)))
+        else:
+            arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            check(self._lib.hb_multi_create(arr, len(devices), C.byref(self._h)))
+        self.n_devices = int(self._lib.hb_multi_device_count(self._h))
+        self.set_world(seed)
+
+    def set_world(self, seed: int, freq: float = 0.001, octaves: int = 6, lacunarity: float = 2.0, gain: float = 0.6) -> None:
+        check(self._lib.hb_multi_set_world(self._h, seed, freq, octaves, lacunarity, gain))
+        self.seed = seed
+
+    def set_noise_kind(self, kind: int) -> None:
+        check(self._lib.hb_multi_set_noise_kind(self._h, int(kind)))
+
+    def set_fma_mode(self, fused: bool) -> None:
+        check(self._lib.hb_multi_set_fma_mode(self._h, 1 if fused else 0))
+
+    def set_region_transport(self, transport: int) -> None:
+        check(self._lib.hb_multi_set_region_transport(self._h, int(transport)))
+
+    def set_host_threads(self, n_per_device: int) -> None:
+        check(self._lib.hb_multi_set_host_threads(self._h, int(n_per_device)))
+
+    def slab(self, region: Region, i: int):
+        lo, hi = C.c_int32(0), C.c_int32(0)
+        check(self._lib.hb_multi_slab(self._h, C.byref(region), i, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def generate_mesh_region(self, region: Region, want_ids: bool = False, sink: Optional[Callable[..., None]] = None) -> dict:
+        cb = _region_sink_cb(sink)
+        tc, tq = C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.hb_multi_generate_mesh_region(self._h, C.byref(region), int(want_ids), cb, None, C.byref(tc), C.byref(tq)))
+        return {"chunks": tc.value, "quads": tq.value}
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.hb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 class Context:
     def __init__(self, device: int = 0, seed: int = 0):
         self._lib = _lib.load()
@@ -94,6 +167,11 @@ class Context:
     def set_noise_kind(self, kind: int) -> None:
         """_lib.NOISE_FBM (the game's, default) / NOISE_RIDGE / NOISE_TURBULENCE / NOISE_GRADIENT."""
         check(self._lib.hb_set_noise_kind(self._h, int(kind)))
+
+    def set_fma_mode(self, fused: bool) -> None:
+        """True (default): neg_mul_add fused as on AVX2+FMA / NEON hosts; False: the SSE2 / SSE4.1 / scalar column
+        (crates/simd-noise/src/simd/ops/f32.rs:141-162)."""
+        check(self._lib.hb_set_fma_mode(self._h, 1 if fused else 0))
 
     def set_materials(self, colors: list) -> None:
         """colors[m] = list of rgba tuples of material id m+1 (server/src/chunk/material.rs:27-61)."""

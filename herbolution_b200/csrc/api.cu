@@ -258,7 +258,7 @@ int hb_create(int device, hb_ctx** out) {
     if (!c) return fail(HB_ERR_NOMEM, "out of host memory");
     c->device = device;
     c->seed = 0;
-    c->world = WorldDev{0, 0.001f, 6, 2.0f, 0.6f};
+    c->world = WorldDev{0, 0.001f, 6, 2.0f, 0.6f, HB_NOISE_FBM, 1};
     for (int f = 0; f < 6; ++f) face_matrix(f, c->tables.face_mat[f]);
     for (int k = 0; k < 4; ++k) c->tables.ao_lut[k] = ao_value(k);
     default_materials(&c->mats);
@@ -302,7 +302,7 @@ int hb_set_world(hb_ctx* c, int64_t seed, float freq, int32_t octaves, float lac
     if (octaves < 1 || octaves > 255) return fail(HB_ERR_INVALID, "octaves must be in 1..255 (u8 in the reference)");
     std::lock_guard<std::mutex> lk(c->mu);
     c->seed = seed;
-    c->world = WorldDev{(int32_t)seed, freq, octaves, lacunarity, gain, c->world.kind};
+    c->world = WorldDev{(int32_t)seed, freq, octaves, lacunarity, gain, c->world.kind, c->world.fma};
     return HB_OK;
 }
 
@@ -311,6 +311,14 @@ int hb_set_noise_kind(hb_ctx* c, int32_t kind) {
     if (kind < HB_NOISE_FBM || kind > HB_NOISE_GRADIENT) return fail(HB_ERR_INVALID, "unknown noise kind %d", kind);
     std::lock_guard<std::mutex> lk(c->mu);
     c->world.kind = kind;
+    return HB_OK;
+}
+
+int hb_set_fma_mode(hb_ctx* c, int32_t fused) {
+    if (!c) return fail(HB_ERR_INVALID, "ctx is null");
+    if (fused != 0 && fused != 1) return fail(HB_ERR_INVALID, "fma mode must be 0 (unfused) or 1 (fused)");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->world.fma = fused;
     return HB_OK;
 }
 

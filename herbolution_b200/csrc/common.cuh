@@ -17,6 +17,8 @@ struct WorldDev {
     float lacunarity;
     float gain;
     int32_t kind;     // HB_NOISE_*: which of the crate's Sample32 implementations the tile walk calls
+    int32_t fma;      // 1: neg_mul_add is one fused operation (AVX2+FMA / NEON hosts); 0: product and subtraction
+                      // rounded separately (SSE2 / SSE4.1 / scalar hosts) -- simd/ops/f32.rs:141-162
 };
 
 // Constant tables built on the host with the reference's formulas (api.cu) and passed by value.

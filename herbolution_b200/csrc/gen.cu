@@ -45,7 +45,7 @@ struct ColRegion {
 // staged once per CTA and there is no barrier in the column loop.  Thread mapping: sample i has x = i >> 5,
 // z = i & 31, i.e. heights are produced directly in voxel-column order x*32 + z (coalesced stores, no transpose);
 // the optional raw noise tile keeps the crate's order x + z*32 (noise/f32.rs:95-113) with a strided store.
-template <class Cols, int KIND, bool FAST>
+template <class Cols, int KIND, bool FAST, bool FMA>
 __global__ void __launch_bounds__(kThreads, 8) k_heights(WorldDev w, Cols cols, int ncol, int32_t* __restrict__ heights,
                                                        float* __restrict__ noise) {
     __shared__ NoiseTables s_tab;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_heights(WorldDev w, Cols cols, 
             const int i0 = threadIdx.x + k * kThreads, i1 = i0 + kThreads;
             const float2 x = pk(__fadd_rn(start_x, __int2float_rn(i0 >> 5)), __fadd_rn(start_x, __int2float_rn(i1 >> 5)));
             const float2 z = pk(__fadd_rn(start_z, __int2float_rn(i0 & 31)), __fadd_rn(start_z, __int2float_rn(i1 & 31)));
-            const float2 r = noise2_pair<KIND, FAST>(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
+            const float2 r = noise2_pair<KIND, FAST, FMA>(s_tab, smul2(x, bc(w.freq)), smul2(z, bc(w.freq)), w);  // scalar muls: they feed adds
             if (noise) {
                 noise[(size_t)col * HB_CHUNK_AREA + (i0 >> 5) + (i0 & 31) * 32] = r.x;
                 noise[(size_t)col * HB_CHUNK_AREA + (i1 >> 5) + (i1 & 31) * 32] = r.y;
@@ -240,10 +240,12 @@ void launch_heights_kind(cudaStream_t s, const WorldDev& w, Cols cols, unsigned 
     const int ncol = (int)grid;
     const unsigned cap = (unsigned)num_sms() * 16u;  // two waves of the 8 resident CTAs per SM: measured best (8: +2 %, one CTA per column: +2 %)
     if (grid > cap) grid = cap;
-#define HB_LAUNCH_KIND(K)                                                                               \
-    do {                                                                                                \
-        if (fast) k_heights<Cols, K, true><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise); \
-        else k_heights<Cols, K, false><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise);    \
+    // the unfused arithmetic column (w.fma == 0) exists with the exact-conversion index path only
+#define HB_LAUNCH_KIND(K)                                                                                           \
+    do {                                                                                                            \
+        if (!w.fma) k_heights<Cols, K, false, false><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise);     \
+        else if (fast) k_heights<Cols, K, true, true><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise);    \
+        else k_heights<Cols, K, false, true><<<grid, kThreads, 0, s>>>(w, cols, ncol, d_heights, d_noise);            \
     } while (0)
     const bool fast = fast_index_ok_impl(w);
     switch (w.kind) {

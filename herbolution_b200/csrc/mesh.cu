@@ -945,19 +945,20 @@ k_mesh_region(const MeshTables tb, const MaterialsDev* __restrict__ mats, const 
 // order and a column's chunks are consecutive), so the output is bit-identical to the staged pipeline's.
 // Requires ncy <= 32 and the FBM noise kind; the launch wrapper falls back to the staged kernels otherwise.
 // ------------------------------------------------------------------------------------------------
-// Shared memory is what limits residency (5 CTAs/SM need <= 45 670 B each), so the buffers of the noise/count phase
-// live inside buffers only the emit phase uses: the noise tables (5 KB, rebuilt per column) over the occupancy tile,
-// the per-warp count accumulators over the descriptor buffer.
-constexpr int kFusedCtasPerSm = 5;
-using FusedMesh = MeshSmemT<1024>;
+// 4 CTAs/SM like the staged emit kernel.  5 CTAs/SM (48 registers; descriptor buffer halved, the noise tables and
+// count accumulators placed inside emit-only buffers to fit shared memory) measured slower: 4.32 vs 4.19 ms per
+// config-4 step -- the kernel is bound by instruction issue (profiles/r2_ncu_region_fused_5cta_summary.csv: 3.58 G
+// warp instructions, 73 % of the issue slots, top stall = barrier), not by residency.
+constexpr int kFusedCtasPerSm = 4;
+using FusedMesh = MeshSmemT<kDescCap>;
 struct FusedSmem {
     FusedMesh sm;
+    NoiseTables nt;
+    uint32_t acc[kT / 32][32];  // per warp, per layer
     uint32_t cnt[32];           // the column's quad count per layer
     u64 off[32];                // and where each layer's quads go
     int next_col;
 };
-static_assert(sizeof(NoiseTables) <= sizeof(u64) * kTileN, "noise tables alias the occupancy tile");
-static_assert(sizeof(uint32_t) * (kT / 32) * 32 <= sizeof(uint32_t) * FusedMesh::kDesc, "count accumulators alias the descriptors");
 static_assert((sizeof(FusedSmem) + 1024) * kFusedCtasPerSm <= 228 * 1024, "fused kernel: shared memory per SM");
 
 constexpr u64 kStatusAggregate = 1ULL << 62, kStatusPrefix = 2ULL << 62, kStatusValue = (1ULL << 62) - 1ULL;
@@ -979,10 +980,11 @@ k_region_fused(const MeshTables tb, const MaterialsDev* __restrict__ mats, const
     extern __shared__ __align__(16) unsigned char fused_smem_raw[];
     FusedSmem& fs = *reinterpret_cast<FusedSmem*>(fused_smem_raw);
     FusedMesh& sm = fs.sm;
-    NoiseTables& nt = *reinterpret_cast<NoiseTables*>(sm.occ);                      // noise phase only
-    uint32_t (*const acc)[32] = reinterpret_cast<uint32_t (*)[32]>(sm.desc);       // count phase only
+    NoiseTables& nt = fs.nt;
+    uint32_t (*const acc)[32] = fs.acc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     load_tables(sm, tb);
+    load_noise_tables(nt, w.seed_lo);
     const RelHeight rel{(long long)r.cy0 * 32, 32 * r.ncy + 8};
     const int ncols = (r.ix_end - r.ix_begin) * r.ncz;
     const int last = r.ncy - 1;
@@ -998,9 +1000,7 @@ k_region_fused(const MeshTables tb, const MaterialsDev* __restrict__ mats, const
         if (colw >= ncols) break;
         const int ix = r.ix_begin + colw / r.ncz, iz = colw % r.ncz;
         const int cx = r.cx0 + ix, cz = r.cz0 + iz;
-        load_noise_tables(nt, w.seed_lo);  // the previous column's occupancy tile overwrote them
         if (warp == 2 && lane < r.ncy) sm.layer_seed[lane] = siphash13_chunk(cx, r.cy0 + lane, cz);
-        __syncthreads();
 
         // ---- 1. noise: the 34 x 34 halo of heights, two samples per packed evaluation (element e = xi*34 + zi;
         //         pair = elements e and e + 578, i.e. tile rows xi and xi + 17)
@@ -1349,7 +1349,7 @@ cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, 
     return cudaGetLastError();
 }
 
-bool region_fused_supported(const WorldDev& w, const RegionDev& r) { return w.kind == HB_NOISE_FBM && r.ncy <= 32; }
+bool region_fused_supported(const WorldDev& w, const RegionDev& r) { return w.kind == HB_NOISE_FBM && w.fma && r.ncy <= 32; }
 
 size_t region_fused_status_bytes(const RegionDev& r) { return (size_t)(r.ix_end - r.ix_begin) * r.ncz * sizeof(u64); }
 

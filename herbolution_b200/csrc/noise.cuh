@@ -87,6 +87,14 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a
 __device__ __forceinline__ float2 fnma2(float2 a, float2 b, float2 c) { return __ffma2_rn(neg2(a), b, c); }  // c - a*b, fused
 __device__ __forceinline__ float2 smul2(float2 a, float2 b) { return pk(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
 __device__ __forceinline__ float2 sadd2(float2 a, float2 b) { return pk(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+// neg_mul_add(a, b, c) = c - a*b (simd/ops/f32.rs:141-162): one fused operation on AVX2+FMA and NEON hosts
+// (_mm256_fnmadd_ps / vfmsq_f32), a rounded product and a subtraction on SSE2 / SSE4.1 / scalar / wasm hosts.  FMA
+// selects which of the reference's CPU columns is reproduced (hb_set_fma_mode).
+template <bool FMA>
+__device__ __forceinline__ float2 nma2(float2 a, float2 b, float2 c) {
+    if constexpr (FMA) return fnma2(a, b, c);
+    else return sub2(c, smul2(a, b));  // scalar multiplies: a packed product feeding a packed add would be contracted
+}
 
 // functions/simplex_32.rs:103-170 (value half of simplex_2d_deriv) for TWO samples at once: every variable is a
 // float2 (.x = sample A, .y = sample B).  The arithmetic per sample is op for op the reference's: separate
@@ -103,7 +111,7 @@ __device__ __forceinline__ float2 sadd2(float2 a, float2 b) { return pk(__fadd_r
 //   * j1 = (y0 > x0) is taken as NOT (x0 >= y0), i.e. -1 - i1 in float: identical for every non-NaN input, and
 //     coordinates are finite by construction.
 // Bit-exactness of the result is what tests/test_gpu_parity.py::test_noise_tiles_bit_exact asserts (0 ulp).
-template <bool FAST>
+template <bool FAST, bool FMA = true>
 __device__ __forceinline__ float2 simplex2_pair(const NoiseTables& T, float2 x, float2 y) {
     const float2 s = smul2(bc(HB_F2), add2(x, y));  // feeds x + s, y + s
     const float2 xs = add2(x, s), ys = add2(y, s);
@@ -161,9 +169,9 @@ __device__ __forceinline__ float2 simplex2_pair(const NoiseTables& T, float2 x, 
     const float2 x2 = add2(add2(x0, bc(-1.0f)), bc(HB_G22));
     const float2 y2 = add2(add2(y0, bc(-1.0f)), bc(HB_G22));
 
-    float2 t0 = fnma2(y0, y0, fnma2(x0, x0, bc(0.5f)));
-    float2 t1 = fnma2(y1, y1, fnma2(x1, x1, bc(0.5f)));
-    float2 t2 = fnma2(y2, y2, fnma2(x2, x2, bc(0.5f)));
+    float2 t0 = nma2<FMA>(y0, y0, nma2<FMA>(x0, x0, bc(0.5f)));
+    float2 t1 = nma2<FMA>(y1, y1, nma2<FMA>(x1, x1, bc(0.5f)));
+    float2 t2 = nma2<FMA>(y2, y2, nma2<FMA>(x2, x2, bc(0.5f)));
     // t &= t.cmp_gte(0): negative -> +0.  fmaxf(t, 0) differs only for t = -0 (keeps/loses the sign
     // of zero), and t is squared next, so the result is identical.
     t0 = pk(fmaxf(t0.x, 0.0f), fmaxf(t0.y, 0.0f));
@@ -190,21 +198,21 @@ __device__ __forceinline__ float2 next_octave(float2 v, float lac) {
 }
 
 // functions/fbm_32.rs:18-31, two samples at once
-template <bool FAST, bool LAC2>
+template <bool FAST, bool LAC2, bool FMA>
 __device__ __forceinline__ float2 fbm2_octaves(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
-    float2 result = simplex2_pair<FAST>(T, x, y);
+    float2 result = simplex2_pair<FAST, FMA>(T, x, y);
     float amp = 1.0f;
     for (int o = 1; o < w.octaves; ++o) {
         x = next_octave<LAC2>(x, w.lacunarity);
         y = next_octave<LAC2>(y, w.lacunarity);
         amp = __fmul_rn(amp, w.gain);
-        result = sadd2(mul2(simplex2_pair<FAST>(T, x, y), bc(amp)), result);
+        result = sadd2(mul2(simplex2_pair<FAST, FMA>(T, x, y), bc(amp)), result);
     }
     return result;
 }
-template <bool FAST>
+template <bool FAST, bool FMA>
 __device__ __forceinline__ float2 fbm2_pair(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
-    return w.lacunarity == 2.0f ? fbm2_octaves<FAST, true>(T, x, y, w) : fbm2_octaves<FAST, false>(T, x, y, w);
+    return w.lacunarity == 2.0f ? fbm2_octaves<FAST, true, FMA>(T, x, y, w) : fbm2_octaves<FAST, false, FMA>(T, x, y, w);
 }
 
 __device__ __forceinline__ float2 abs2(float2 a) { return pk(fabsf(a.x), fabsf(a.y)); }  // andnot(-0.0, a), simd/ops/f32.rs:307-310
@@ -214,10 +222,10 @@ __device__ __forceinline__ float2 abs2(float2 a) { return pk(fabsf(a.x), fabsf(a
 //   turbulence_2d (functions/turbulence_32.rs:18-32): r = |s0|;      r = r + |s * amp|
 //   gradient      (noise/gradient.rs:77-79):          r = s0
 // KIND is a template parameter so the FBM kernel's code is untouched by the variants.
-template <int KIND, bool FAST>
+template <int KIND, bool FAST, bool FMA = true>
 __device__ __forceinline__ float2 noise2_pair(const NoiseTables& T, float2 x, float2 y, const WorldDev& w) {
-    if (KIND == HB_NOISE_FBM) return fbm2_pair<FAST>(T, x, y, w);
-    const float2 s0 = simplex2_pair<FAST>(T, x, y);
+    if (KIND == HB_NOISE_FBM) return fbm2_pair<FAST, FMA>(T, x, y, w);
+    const float2 s0 = simplex2_pair<FAST, FMA>(T, x, y);
     if (KIND == HB_NOISE_GRADIENT) return s0;
     float2 result = KIND == HB_NOISE_RIDGE ? sadd2(bc(1.0f), neg2(abs2(s0))) : abs2(s0);
     float amp = 1.0f;
@@ -225,10 +233,11 @@ __device__ __forceinline__ float2 noise2_pair(const NoiseTables& T, float2 x, fl
         x = next_octave<false>(x, w.lacunarity);
         y = next_octave<false>(y, w.lacunarity);
         amp = __fmul_rn(amp, w.gain);
-        const float2 sv = simplex2_pair<FAST>(T, x, y);
+        const float2 sv = simplex2_pair<FAST, FMA>(T, x, y);
         if (KIND == HB_NOISE_RIDGE) {
             const float2 a = abs2(sv);
-            result = sadd2(result, pk(__fmaf_rn(-a.x, amp, 1.0f), __fmaf_rn(-a.y, amp, 1.0f)));
+            if constexpr (FMA) result = sadd2(result, pk(__fmaf_rn(-a.x, amp, 1.0f), __fmaf_rn(-a.y, amp, 1.0f)));
+            else result = sadd2(result, pk(__fsub_rn(1.0f, __fmul_rn(a.x, amp)), __fsub_rn(1.0f, __fmul_rn(a.y, amp))));
         } else {
             result = sadd2(result, abs2(smul2(sv, bc(amp))));
         }
@@ -330,7 +339,7 @@ __device__ __forceinline__ float noise3(float x, float y, float z, const WorldDe
         z = __fmul_rn(z, w.lacunarity);
         amp = __fmul_rn(amp, w.gain);
         const float sv = simplex3(x, y, z, w.seed_lo);
-        if (ridge) result = __fadd_rn(result, __fmaf_rn(-fabsf(sv), amp, 1.0f));
+        if (ridge) result = __fadd_rn(result, w.fma ? __fmaf_rn(-fabsf(sv), amp, 1.0f) : __fsub_rn(1.0f, __fmul_rn(fabsf(sv), amp)));
         else result = __fadd_rn(result, fabsf(__fmul_rn(sv, amp)));
     }
     return result;

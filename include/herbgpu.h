@@ -109,6 +109,12 @@ HB_API int hb_set_world(hb_ctx *ctx, int64_t seed, float freq, int32_t octaves, 
 #define HB_NOISE_TURBULENCE 2
 #define HB_NOISE_GRADIENT 3
 HB_API int hb_set_noise_kind(hb_ctx *ctx, int32_t kind);
+/* Which arithmetic column of the reference's runtime SIMD dispatch (crates/simd-noise/src/simd/invoking.rs:169-199)
+ * the 2-D/3-D noise reproduces bit for bit.  neg_mul_add (simd/ops/f32.rs:141-162; six sites in simplex_2d, one in
+ * ridge) is ONE fused operation on AVX2+FMA and NEON hosts -- fused = 1, the default, what any x86-64 machine since 2013
+ * selects -- and a rounded product followed by a subtraction on SSE2 / SSE4.1 / scalar / wasm hosts -- fused = 0.  The
+ * two columns differ by a few ulp (inside north_star's 1e-5 relative tolerance). */
+HB_API int hb_set_fma_mode(hb_ctx *ctx, int32_t fused);
 
 /* Palette colours, Material::texture (server/src/chunk/material.rs:27-71): material id m (1-based)
  * has n_colors[m-1] colours, rgba[(m-1)*HB_MAX_COLORS + c][4].  Default = stone, dirt, grass. */
@@ -222,6 +228,37 @@ HB_API int hb_generate_mesh_region_packed(hb_ctx *ctx, const hb_region *region, 
  * for (n + 3) & ~3 records and must be 16-byte aligned).  No GPU work, no lock: any number of host threads may call
  * it concurrently on one ctx (as long as nobody changes the materials meanwhile).  Uses the ctx's palette colours. */
 HB_API int hb_expand_quads(hb_ctx *ctx, hb_chunk_pt pt, const hb_packed_quad *quads, uint32_t n, hb_instance3d *out);
+
+/* ---- one process, several GPUs (a handle owning 1..8 devices) ----
+ * The reference's host is ONE process whose chunk work fans out over a thread pool (server/src/lib.rs:42-60,
+ * lib/src/task.rs:6-25); hb_multi gives that host the same shape on a multi-GPU box: one hb_ctx per device behind one
+ * handle.  hb_multi_generate_mesh_region splits the region's chunk columns into contiguous, balanced x-slabs, one per
+ * device in the order the devices were listed (hb_multi_slab reports the split; chunks are independent, so there is
+ * no exchange: each slab recomputes its one-column apron of heights), and drives every device from its own host
+ * thread with that ctx's stream pair, pinned ring and expander threads.
+ * Sink: called once per streamed piece exactly as for hb_generate_mesh_region, from the per-device threads, but
+ * SERIALISED by the handle (never two calls at once).  Pieces of one device arrive in region order; pieces of
+ * different devices interleave.  first_chunk is the index within the whole region, so a consumer places each piece
+ * without knowing which device produced it.  The sink must not call back into the handle.
+ * devices = NULL with n_devices = 0 takes every visible device (at most HB_MAX_DEVICES).  The setters broadcast to all
+ * devices; hb_multi_ctx exposes a device's ctx for anything else (per-device worlds, probes).  Host expander threads
+ * default to min(hardware threads, 32) / n_devices per device. */
+#define HB_MAX_DEVICES 8
+typedef struct hb_multi hb_multi;
+HB_API int hb_multi_create(const int32_t *devices, int32_t n_devices, hb_multi **out);
+HB_API void hb_multi_destroy(hb_multi *multi);
+HB_API int32_t hb_multi_device_count(const hb_multi *multi);
+HB_API hb_ctx *hb_multi_ctx(hb_multi *multi, int32_t i);
+HB_API int hb_multi_set_world(hb_multi *multi, int64_t seed, float freq, int32_t octaves, float lacunarity, float gain);
+HB_API int hb_multi_set_noise_kind(hb_multi *multi, int32_t kind);
+HB_API int hb_multi_set_fma_mode(hb_multi *multi, int32_t fused);
+HB_API int hb_multi_set_materials(hb_multi *multi, int32_t n_materials, const int32_t *n_colors, const float *rgba);
+HB_API int hb_multi_set_region_transport(hb_multi *multi, int32_t transport);
+HB_API int hb_multi_set_host_threads(hb_multi *multi, int32_t n_threads_per_device);
+HB_API int hb_multi_slab(const hb_multi *multi, const hb_region *region, int32_t i, int32_t *ix_begin, int32_t *ix_end);
+HB_API int hb_multi_generate_mesh_region(hb_multi *multi, const hb_region *region, int want_ids,
+                                         hb_region_sink sink, void *user,
+                                         uint64_t *total_chunks, uint64_t *total_quads);
 
 /* Measurement helpers: the two ceilings of the end-to-end path, measured with the ctx's own buffers and threads so
  * that several ctxs (GPUs) can be probed at the same moment.  hb_probe_d2h: plain cudaMemcpyAsync device -> pinned

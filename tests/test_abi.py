@@ -148,14 +148,21 @@ def test_noise_kernel_has_no_unintended_fma_contraction():
     sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
     funcs = re.split(r"\n\s*Function : ", sass)
     heights = [f for f in funcs if "k_heights" in f.split("\n", 1)[0]]
-    assert len(heights) == 16  # {ColList, ColRegion} x 4 noise kinds x {FAST, exact}
+    # {ColList, ColRegion} x 4 noise kinds x {FAST + fused, exact + fused, exact + unfused (hb_set_fma_mode(0))}
+    assert len(heights) == 24
+    unfused = [f for f in heights if re.search(r"ELi\dELb[01]ELb0EEEv", f.split("\n", 1)[0])]
+    assert len(unfused) == 8
+    for f in unfused:  # the SSE2 / scalar column: no fused multiply-add anywhere in the noise
+        ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", f)
+        assert not any(o.startswith("FFMA") for o in ops), "FMA in the unfused noise column"
+    heights = [f for f in heights if f not in unfused]
     # KIND -> scalar FFMA per simplex pair in an octave loop body (ridge only), FMUL2 besides the 16 of a simplex
     # pair (FBM: the packed `simplex * amp` of every loop body).  How many copies of the simplex pair the compiler
     # lays down (loop peeling, the two lacunarity variants) is its business; the per-pair mix is not.
     want = {0: (0, 1), 1: (2, 0), 2: (0, 0), 3: (0, 0)}
     conv = {}
     for f in heights:
-        m = re.search(r"ELi(\d)ELb([01])EEEv", f.split("\n", 1)[0])
+        m = re.search(r"ELi(\d)ELb([01])ELb1EEEv", f.split("\n", 1)[0])
         kind, fast = int(m.group(1)), m.group(2) == "1"
         ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", f)
         packed = sum(o.startswith("FFMA2") for o in ops)

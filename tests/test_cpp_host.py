@@ -51,3 +51,30 @@ def test_header_is_plain_c():
                     f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def build_multi():
+    src = os.path.join(ROOT, "tests", "cpp", "test_multi.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_multi")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    libdir = os.path.join(ROOT, "herbolution_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-pthread", src, "-o", exe, f"-L{libdir}", "-lherbgpu",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def test_multi_driver_compiles():
+    build_multi()
+
+
+@pytest.mark.gpu
+def test_multi_gpu_single_process_cpp():
+    """hb_multi from C++: one process, all visible GPUs, byte-exact against one device.  On a 1-GPU box the same
+    program runs with a one-device handle (the >= 2 GPU run is in profiles/ and in the round-end multi-GPU tier)."""
+    import torch
+    exe = build_multi()
+    args = [exe] if torch.cuda.device_count() >= 2 else [exe, "--allow-one"]
+    out = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "byte-exact" in out.stdout

@@ -139,3 +139,31 @@ def test_expand_quads_errors(ctx):
         ctx.set_region_transport(7)
     with pytest.raises(hb.HerbGpuError):
         ctx.set_host_threads(0)
+
+
+def test_multi_context_python_one_process():
+    """hb_multi through the Python binding: all visible devices (one on the test box), serialised sink, same bytes as
+    the single-ctx call; slabs cover the region."""
+    import torch
+    reg = hb.Region(-3, 2, 11, 5, -2, 4)
+    with hb.MultiContext(devices=None, seed=5) as m:
+        assert m.n_devices == min(torch.cuda.device_count(), 8)
+        edges = [m.slab(reg, i) for i in range(m.n_devices)]
+        assert edges[0][0] == 0 and edges[-1][1] == reg.ncx and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        got = {}
+
+        def sink(first, off, cnt, inst, ids):
+            for k in range(len(cnt)):
+                got[first + k] = inst[int(off[k]):int(off[k]) + int(cnt[k])].tobytes()
+
+        tot = m.generate_mesh_region(reg, sink=sink)
+    c = hb.Context(0, seed=5)
+    want = {}
+
+    def sink1(first, off, cnt, inst, ids):
+        for k in range(len(cnt)):
+            want[first + k] = inst[int(off[k]):int(off[k]) + int(cnt[k])].tobytes()
+
+    tot1 = c.generate_mesh_region(reg, sink=sink1)
+    c.close()
+    assert tot == tot1 and got == want and len(got) == 11 * 5 * 4

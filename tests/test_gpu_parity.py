@@ -511,6 +511,54 @@ def test_noise_kinds_bit_exact(ctx, kind):
         ctx.set_world(0)
 
 
+@pytest.mark.parametrize("kind", [O.NOISE_FBM, O.NOISE_RIDGE, O.NOISE_TURBULENCE, O.NOISE_GRADIENT])
+def test_unfused_arithmetic_column_bit_exact(ctx, kind):
+    """hb_set_fma_mode(0): the SSE2 / SSE4.1 / scalar column of the reference's runtime dispatch, where neg_mul_add is a
+    rounded product and a subtraction (simd/ops/f32.rs:141-162).  Bit-exact against the oracle's unfused switch for
+    2-D tiles, heights, the 3-D tile, block ids and a meshed region; and it really is a different column (some sample
+    differs from the fused one)."""
+    try:
+        for seed in (0, 5):
+            ctx.set_world(seed)
+            ctx.set_noise_kind(kind)
+            cols = np.array([[0, 0], [-1, -1], [7, -3], [-512, 511], [262143, -262143]], dtype=np.int32)
+            fused_noise = ctx.noise_tiles(cols)
+            ctx.set_fma_mode(False)
+            w = O.world(seed, kind=kind, fused=0)
+            noise, heights = ctx.noise_tiles(cols, want_heights=True)
+            for i, (cx, cz) in enumerate(cols):
+                ref = O.noise_tile2(w, int(cx), int(cz))
+                assert noise[i].view(np.uint32).tolist() == ref.view(np.uint32).tolist(), (kind, seed, cx, cz)
+                assert (heights[i] == O.heights_from_noise(ref).reshape(32, 32).T.ravel()).all()
+            assert (noise.view(np.uint32) != fused_noise.view(np.uint32)).any()
+            # the two CPU columns differ by rounding only: 1e-5 of the noise's unit scale (values near zero lose
+            # relative, not absolute, agreement through cancellation between the octaves)
+            assert float(np.abs(noise - fused_noise).max()) <= 1e-5
+            got3 = ctx.noise_fbm3d((-5.0, 100.0, 3.0), (9, 5, 7), (0.013, 0.02, 0.011))
+            ref3 = O.noise_tile3(w, (-5.0, 100.0, 3.0), (9, 5, 7), (0.013, 0.02, 0.011))
+            assert got3.view(np.uint32).tolist() == ref3.view(np.uint32).tolist()
+            if kind == O.NOISE_FBM:
+                reg = (3, -4, 3, 2, -2, 4)
+                got = {}
+
+                def sink(first, off, cnt, inst, ids):
+                    for k in range(len(cnt)):
+                        got[first + k] = (inst[int(off[k]):int(off[k]) + int(cnt[k])].tobytes(), ids[k].copy())
+
+                ctx.generate_mesh_region(hb.Region(*reg), want_ids=True, sink=sink)
+                ref = O.region_pipeline(w, reg, literal=True, threads=2, want_ids=True)
+                off = np.concatenate([[0], np.cumsum(ref["counts"].astype(np.int64))])
+                for i in range(len(ref["counts"])):
+                    assert (got[i][1] == ref["ids"][i]).all()
+                    assert got[i][0] == ref["instances"][off[i]:off[i + 1]].tobytes()
+            ctx.set_fma_mode(True)
+    finally:
+        ctx.set_fma_mode(True)
+        ctx.set_noise_kind(O.NOISE_FBM)
+        ctx.set_world(0)
+    assert ctx._lib.hb_set_fma_mode(ctx._h, 2) == hb._lib.HB_ERR_INVALID
+
+
 def test_noise_kind_errors(ctx):
     with pytest.raises(hb.HerbGpuError) as e:
         ctx.set_noise_kind(7)
