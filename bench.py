@@ -379,7 +379,7 @@ def main():
                          "frac": noise_tflops / 74.4, "flops_per_column": flops_per_column}}
 
     # ---- end to end through the host entry point: every Instance3d reaches a host sink
-    e2e = e2e_alt = probes = None
+    e2e = e2e_alt = e2e_packed = probes = None
     stats = {"span": 0, "chunks": 0}
 
     def sink(first, off, cnt, inst, ids):
@@ -432,12 +432,38 @@ def main():
                    "d2h_gbs_per_gpu": raw_gbs, "d2h_peak_gbs_per_gpu": probes["d2h_peak_gbs_per_gpu_min"],
                    "link_frac": raw_gbs / probes["d2h_peak_gbs_per_gpu_min"], "bound": "PCIe device->host"}
         ctx.set_region_transport(hb.TRANSPORT_PACKED)
+        # and the packed SINK: the consumer takes the 4-byte quads themselves (hb_generate_mesh_region_packed) and expands
+        # only what it needs, when it needs it (hb_expand_quads) -- nothing but the link is on this path
+        pstats = {"span": 0, "chunks": 0}
+
+        def psink(first, off, cnt, quads, ids):
+            pstats["span"] += len(quads)
+            pstats["chunks"] += len(cnt)
+
+        ctx.generate_mesh_region_packed(reg, sink=psink)
+        pstats["span"] = pstats["chunks"] = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.generate_mesh_region_packed(reg, sink=psink)
+        torch.cuda.synchronize()
+        t_pk = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        pk_bytes = (pstats["span"] * 4 + pstats["chunks"] * 12) / e2e_steps
+        pk_gbs = pk_bytes / (t_pk / e2e_steps) / 1e9
+        e2e_packed = {"api": "hb_generate_mesh_region_packed (C ABI, host sink receives hb_packed_quad words, 4 B/quad; "
+                             "hb_expand_quads rebuilds Instance3d records on demand)",
+                      "value": total_chunks * e2e_steps / t_pk, "unit": UNIT, "ms_per_step": 1e3 * t_pk / e2e_steps,
+                      "d2h_bytes_per_step": int(pk_bytes), "d2h_gbs_per_gpu": pk_gbs,
+                      "d2h_peak_gbs_per_gpu": probes["d2h_peak_gbs_per_gpu_min"], "link_frac": pk_gbs / probes["d2h_peak_gbs_per_gpu_min"],
+                      "kernel_frac": (ms_total / steps) / (1e3 * t_pk / e2e_steps),
+                      "note": "kernel_frac = device step time / this step time: what is left is launch + copy latency of the streamed pieces"}
 
     # ---- config 5: 1024 x 1024 columns x 6, strong-scaled over the ranks by x-slabs
     c5 = None
     if not args.no_c5:
         c5 = run_c5(args, ctx, hb, sharding, np, torch, tstream, rank, world, barrier, max_over_ranks, min_over_ranks,
-                    sum_over_ranks, sampler, probes, host_thr)
+                    sum_over_ranks, sampler, probes, host_thr, STEP)
     clocks = sampler.stop()
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
@@ -517,7 +543,7 @@ def main():
                 "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * steps, "roofline": roofline, "cpu_baseline": cpu,
-                "e2e_instances_transport": e2e_alt, "probes": probes, "c5": c5, "kernels": kernels,
+                "e2e_instances_transport": e2e_alt, "e2e_packed_sink": e2e_packed, "probes": probes, "c5": c5, "kernels": kernels,
                 "quads_per_step_per_gpu": quads, "instance_bytes_per_step_per_gpu": span * 100, "split": split,
                 "so_sha256": so_sha256()}
         print(json.dumps(line))
@@ -528,7 +554,7 @@ def main():
 
 
 def run_c5(args, ctx, hb, sharding, np, torch, tstream, rank, world, barrier, max_over_ranks, min_over_ranks,
-           sum_over_ranks, sampler, probes, host_thr):
+           sum_over_ranks, sampler, probes, host_thr, step_stages):
     """BASELINE config 5: one fixed region, x-slabs over the ranks (strong scaling), results through the host sink.
     Parity is checked at full size on every rank, outside the timed regions: 6x6-column patches -- at the slab's west
     seam, in its middle and at its east seam, one of them on the region's z border -- all six layers (incl. layer 0 =
@@ -595,6 +621,10 @@ def run_c5(args, ctx, hb, sharding, np, torch, tstream, rank, world, barrier, ma
         stats["chunks"] += len(cnt)
 
     ctx.set_region_transport(hb.TRANSPORT_PACKED)
+    # untimed warm-up over the first part of the slab: the streamer's pieces of this region are larger than config 4's,
+    # so its pinned rings and the expanded-slab buffer grow (and are first touched) here, not in the timed pass
+    ctx.generate_mesh_region(region, sink=sink, ix_begin=lo, ix_end=min(hi, lo + 96))
+    stats.update(span=0, chunks=0)
     barrier()
     sampler.begin()
     t0 = time.perf_counter()
@@ -603,6 +633,22 @@ def run_c5(args, ctx, hb, sharding, np, torch, tstream, rank, world, barrier, ma
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     sampler.end()
     barrier()
+    # the packed sink on the same slab (4 B/quad delivered)
+    pstats = {"span": 0, "chunks": 0}
+
+    def psink(first, off, cnt, quads, ids):
+        pstats["span"] += len(quads)
+        pstats["chunks"] += len(cnt)
+
+    ctx.generate_mesh_region_packed(region, sink=psink, ix_begin=lo, ix_end=min(hi, lo + 96))
+    pstats.update(span=0, chunks=0)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.generate_mesh_region_packed(region, sink=psink, ix_begin=lo, ix_end=hi)
+    torch.cuda.synchronize()
+    t_pk = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    pk_bytes = sum_over_ranks(float(pstats["span"]) * 4 + pstats["chunks"] * 12)
     chunks = sum_over_ranks(float(tot["chunks"]))
     quads = sum_over_ranks(float(tot["quads"]))
     inst_bytes = sum_over_ranks(float(stats["span"]) * 100)
@@ -615,6 +661,11 @@ def run_c5(args, ctx, hb, sharding, np, torch, tstream, rank, world, barrier, ma
                     "link_frac": (inst_bytes / 25 + chunks * 12) / t_e2e / 1e9 / probes["d2h_peak_gbs_sum"],
                     "bound": "host memory writes; the link carries 4 B per quad"})
 
+    e2e_packed = {"value": chunks / t_pk, "unit": UNIT, "seconds": t_pk, "api": "hb_generate_mesh_region_packed (4 B/quad to the sink)",
+                  "d2h_bytes": int(pk_bytes), "d2h_gbs": pk_bytes / t_pk / 1e9}
+    if probes:
+        e2e_packed.update({"d2h_peak_gbs": probes["d2h_peak_gbs_sum"], "link_frac": pk_bytes / t_pk / 1e9 / probes["d2h_peak_gbs_sum"]})
+
     # ---- kernel-only: device-resident plans of <= 64 ix each (64 x 1024 x 6 = one config-4 sized batch), one after
     # the other; CUDA events on the launching stream around every batch, summed
     ms = 0.0
@@ -622,14 +673,14 @@ def run_c5(args, ctx, hb, sharding, np, torch, tstream, rank, world, barrier, ma
     width = max(1, min(64, (256 * 256) // max(1, region.ncz)))
     for a0 in range(lo, hi, width):
         p = ctx.region_plan(region, ix_begin=a0, ix_end=min(hi, a0 + width))
-        p.enqueue(hb.STAGE_FUSED, stream)  # warm
+        p.enqueue(step_stages, stream)  # warm
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(tstream)
-        p.enqueue(hb.STAGE_FUSED, stream)
+        p.enqueue(step_stages, stream)
         e1.record(tstream)
         tstream.synchronize()
         ms += e0.elapsed_time(e1)
-        launches += p.launches(hb.STAGE_FUSED)
+        launches += p.launches(step_stages)
         p.close()
     t_k = max_over_ranks(ms * 1e-3)
     barrier()
@@ -637,8 +688,8 @@ def run_c5(args, ctx, hb, sharding, np, torch, tstream, rank, world, barrier, ma
                         f"x-slabs over {world} GPU(s), pinned async return", "scaling": "strong", "n_gpus": world,
             "chunks": int(chunks), "quads": int(quads),
             "kernel_only": {"value": chunks / t_k, "unit": UNIT, "seconds": t_k, "launches": launches,
-                            "pipeline": "HB_STAGE_FUSED per device-resident batch"},
-            "e2e": e2e,
+                            "pipeline": ("HB_STAGE_FUSED" if step_stages == hb.STAGE_FUSED else "staged (HEIGHTS|COUNT|SCAN|EMIT)") + " per device-resident batch of <= 64 x 1024 columns"},
+            "e2e": e2e, "e2e_packed_sink": e2e_packed,
             "parity": {"ok_on_all_ranks": bool(all_ok), "chunks_compared": int(total_compared), "rank0": detail,
                        "what": "per rank 3 patches (west seam / middle / east seam of its slab; z border, random z, far z border), "
                                "all 6 layers incl. the region-bottom fast path, Instance3d bytes vs the oracle's literal pipeline"}}

@@ -76,13 +76,22 @@ struct EditRec {
     uint16_t x, y, z, material;
 };
 
-// ChunkMap::set_cube (server/src/chunk/map.rs:81-151) + CubeMesh::set (server/src/chunk/mesh.rs:125-186), one edit
-// after the other on a single warp: lane e < 6 owns direction e, the six neighbour voxels are distinct words, and
-// the centre voxel's face mask is combined with a ballot.
-__global__ void __launch_bounds__(32) k_world_edit(hb_palette_cube* __restrict__ cubes, uint32_t* __restrict__ touched,
-                                                   const EditRec* __restrict__ recs, size_t n) {
-    const int lane = threadIdx.x;
-    for (size_t i = 0; i < n; ++i) {
+// ChunkMap::set_cube (server/src/chunk/map.rs:81-151) + CubeMesh::set (server/src/chunk/mesh.rs:125-186).  One warp
+// applies the edits of one GROUP one after the other, in the caller's order: lane e < 6 owns direction e, the six
+// neighbour voxels are distinct words, and the centre voxel's face mask is combined with a ballot.  An edit reads and
+// writes only its own voxel and the six voxels next to it (in the chunk or on the adjacent chunk's border), so edits
+// whose 7-voxel stencils share no voxel commute; the host partitions a batch into the connected components of
+// "stencils intersect" (hb_world_set_cubes) and every component is a group, i.e. groups run concurrently on
+// different warps while the reference's sequential semantics are preserved inside each.
+constexpr int kEditWarps = 4;
+__global__ void __launch_bounds__(32 * kEditWarps) k_world_edit(hb_palette_cube* __restrict__ cubes, uint32_t* __restrict__ touched,
+                                                                const EditRec* __restrict__ recs,
+                                                                const uint32_t* __restrict__ group_start, uint32_t n_groups) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * kEditWarps + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const size_t i_begin = group_start[g], i_end = group_start[g + 1];
+    for (size_t i = i_begin; i < i_end; ++i) {
         __syncwarp();  // the previous edit's stores (any lane) are visible to every lane
         const EditRec r = recs[i];
         const int l[3] = {r.x, r.y, r.z};
@@ -307,6 +316,7 @@ struct hb_world {
     std::vector<uint8_t> remesh;   // received a CubeUpdate since the last remesh
     struct SyncRec { int32_t slot; uint32_t epoch; uint32_t count; };
     std::vector<SyncRec> last_sync;
+    uint32_t last_edit_groups = 0;  // conflict groups of the last hb_world_set_cubes batch (diagnostics)
     hb_world() { h_pin.pinned = true; }
     int find(int32_t x, int32_t y, int32_t z) const { return map.find(x, y, z); }
 };
@@ -614,12 +624,63 @@ int hb_world_set_cubes(hb_world* w, const int32_t* xyz, const uint16_t* material
     for (size_t i = 0; i < n; ++i)
         if (materials[i] > (uint32_t)c->mats.n_materials)
             return fail(HB_ERR_INVALID, "edit %zu: material id %u above the palette size %d", i, materials[i], c->mats.n_materials);
+    // ---- conflict groups: union-find over the edits, joined wherever two 7-voxel stencils share a voxel.  The stencil
+    // voxels go into an open-addressing table (key = world voxel, value = the first edit that touched it).
+    std::vector<uint32_t> parent(n);
+    for (size_t i = 0; i < n; ++i) parent[i] = (uint32_t)i;
+    auto root = [&](uint32_t a) {
+        while (parent[a] != a) a = parent[a] = parent[parent[a]];
+        return a;
+    };
+    {
+        struct Slot { int32_t x, y, z; uint32_t edit; };
+        size_t cap = 16;
+        while (cap < n * 14) cap <<= 1;  // 7 stencil voxels per edit, load factor <= 1/2
+        std::vector<Slot> table(cap, Slot{0, 0, 0, UINT32_MAX});
+        static const int kStencil[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+        for (size_t i = 0; i < n; ++i) {
+            for (int k = 0; k < 7; ++k) {
+                const int32_t vx = xyz[3 * i] + kStencil[k][0], vy = xyz[3 * i + 1] + kStencil[k][1], vz = xyz[3 * i + 2] + kStencil[k][2];
+                uint64_t h = (uint64_t)(uint32_t)vx * 0x9E3779B97F4A7C15ULL ^ (uint64_t)(uint32_t)vy * 0xC2B2AE3D27D4EB4FULL ^
+                             (uint64_t)(uint32_t)vz * 0x165667B19E3779F9ULL;
+                h ^= h >> 29;
+                for (size_t q = (size_t)h & (cap - 1);; q = (q + 1) & (cap - 1)) {
+                    Slot& t = table[q];
+                    if (t.edit == UINT32_MAX) {
+                        t = Slot{vx, vy, vz, (uint32_t)i};
+                        break;
+                    }
+                    if (t.x == vx && t.y == vy && t.z == vz) {
+                        const uint32_t a = root(t.edit), b = root((uint32_t)i);
+                        if (a != b) parent[a > b ? a : b] = a > b ? b : a;  // the root is the component's first edit
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    // stable grouping: groups ordered by their first edit, edits inside a group in the caller's order
+    std::vector<uint32_t> group_of(n), group_start;
+    {
+        std::vector<uint32_t> gid(n, UINT32_MAX), count;
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t r = root((uint32_t)i);
+            if (gid[r] == UINT32_MAX) { gid[r] = (uint32_t)count.size(); count.push_back(0); }
+            group_of[i] = gid[r];
+            ++count[gid[r]];
+        }
+        group_start.resize(count.size() + 1);
+        group_start[0] = 0;
+        for (size_t g = 0; g < count.size(); ++g) group_start[g + 1] = group_start[g] + count[g];
+    }
+    const uint32_t n_groups = (uint32_t)group_start.size() - 1;
+    std::vector<uint32_t> fill(group_start.begin(), group_start.end() - 1);
     std::vector<EditRec> recs(n);
     for (size_t i = 0; i < n; ++i) {
         const int32_t p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
         const int32_t ch[3] = {p[0] >> 5, p[1] >> 5, p[2] >> 5};  // lib/src/point.rs:25-32
         const int l[3] = {p[0] & 31, p[1] & 31, p[2] & 31};
-        EditRec& r = recs[i];
+        EditRec& r = recs[fill[group_of[i]]++];
         r.slot = w->find(ch[0], ch[1], ch[2]);
         r.x = (uint16_t)l[0]; r.y = (uint16_t)l[1]; r.z = (uint16_t)l[2];
         r.material = materials[i];
@@ -636,11 +697,16 @@ int hb_world_set_cubes(hb_world* w, const int32_t* xyz, const uint16_t* material
     }
     int rc = upload(c->stream, w->d_a, recs.data(), n * sizeof(EditRec));
     if (rc != HB_OK) return rc;
-    k_world_edit<<<1, 32, 0, c->stream>>>(w->d_cubes.as<hb_palette_cube>(), w->d_touched.as<uint32_t>(), w->d_a.as<EditRec>(), n);
+    if ((rc = upload(c->stream, w->d_b, group_start.data(), group_start.size() * sizeof(uint32_t))) != HB_OK) return rc;
+    k_world_edit<<<(n_groups + kEditWarps - 1) / kEditWarps, 32 * kEditWarps, 0, c->stream>>>(
+        w->d_cubes.as<hb_palette_cube>(), w->d_touched.as<uint32_t>(), w->d_a.as<EditRec>(), w->d_b.as<uint32_t>(), n_groups);
     HB_CUDA(cudaGetLastError());
+    w->last_edit_groups = n_groups;
     HB_CUDA(cudaStreamSynchronize(c->stream));
     return HB_OK;
 }
+
+uint32_t hb_world_last_edit_groups(const hb_world* w) { return w ? w->last_edit_groups : 0; }
 
 int hb_world_sync(hb_world* w, size_t* n_dirty, uint64_t* n_entries) {
     if (!w) return fail(HB_ERR_INVALID, "null argument");

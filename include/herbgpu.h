@@ -353,6 +353,10 @@ HB_API int hb_world_unload(hb_world *world, const hb_chunk_pt *pts, size_t n);
  * Includes the reference's border behaviour: the face of the adjacent chunk's border voxel is inserted
  * unconditionally, and edits to a position whose own chunk is not loaded still touch loaded neighbours. */
 HB_API int hb_world_set_cubes(hb_world *world, const int32_t *cubes_xyz, const uint16_t *materials, size_t n);
+/* How many conflict groups the last hb_world_set_cubes batch was split into (edits whose 7-voxel stencils -- the voxel
+ * and its six neighbours -- share no voxel commute and are applied concurrently, one warp per group; inside a group
+ * the caller's order is kept, so the result equals the reference's sequential ChunkMap::set_cube calls). */
+HB_API uint32_t hb_world_last_edit_groups(const hb_world *world);
 
 /* Chunk::sync_with_client (server/src/chunk/mod.rs:35-67) for every chunk: drains each chunk's
  * updated_positions.  Chunks with a non-empty set join the remesh set (they are the chunks whose client copy

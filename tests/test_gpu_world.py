@@ -366,3 +366,50 @@ def test_fetch_updates_after_unload_reports_what_it_wrote(ctx):
         assert lib.hb_world_fetch_updates(world._h, None, 0, None, None, None, 0, C.byref(nr), C.byref(ne)) == hb._lib.HB_OK
         assert nr.value == 0 and ne.value == 0
         assert lib.hb_world_fetch_updates(world._h, None, 0, None, None, None, 0, None, None) == hb._lib.HB_ERR_INVALID
+
+
+def test_world_edit_conflict_groups(ctx):
+    """One batch of 4 000 edits is split into conflict groups (edits whose 7-voxel stencils overlap stay in order on one
+    warp, the groups run concurrently): chains of adjacent digs, repeated edits of one voxel, diagonal neighbours,
+    chunk-border pairs and scattered edits -- the cubes, the CubeUpdate sets and the remeshed chunks must equal the
+    reference's strictly sequential ChunkMap::set_cube calls (server/src/chunk/map.rs:81-151)."""
+    seed = 5
+    ctx.set_world(seed)
+    w = O.world(seed)
+    ora = O.ChunkMapOracle(w)
+    pts = [(cx, cy, cz) for cx in (0, 1) for cz in (0, 1) for cy in (-2, -1, 0, 1)]
+    rng = np.random.default_rng(77)
+    edits = edit_script(rng, w, 2400)
+    # a tunnel: 200 consecutive voxels dug in order, then refilled in reverse (one long group)
+    tunnel = [((5 + i % 50, -20 - i // 50, 9), 0) for i in range(200)]
+    edits += tunnel + [(p, 2) for p, _ in reversed(tunnel)]
+    # the same voxel toggled many times, interleaved with far-away edits
+    for i in range(150):
+        edits.append(((40, -12, 40), i % 4))
+        edits.append(((int(rng.integers(0, 64)), int(rng.integers(-60, -30)), int(rng.integers(0, 64))), int(rng.integers(0, 4))))
+    # pairs across chunk borders and diagonal neighbours (L1 distance 2: they share a stencil voxel)
+    for i in range(100):
+        y = -40 + i % 20
+        edits += [((31, y, 3 + i % 25), 0), ((32, y, 3 + i % 25), 3), ((32, y + 1, 4 + i % 25), 0)]
+    edits = edits[:4000]
+    with hb.World(ctx, 32) as world:
+        world.load(pts)
+        for p in pts:
+            ora.load(p)
+        check_remesh(world, ora, check_sync(world, ora))
+        world.set_cubes([e[0] for e in edits], [e[1] for e in edits])
+        groups = int(world._lib.hb_world_last_edit_groups(world._h))
+        assert 50 < groups < len(edits), groups  # neither one serial chain nor all independent
+        for pos, mat in edits:
+            ora.set_cube(pos, mat)
+        check_cubes(world, ora)
+        check_remesh(world, ora, check_sync(world, ora))
+        # a batch that is one chain from the first edit to the last stays one group
+        line = [((10 + i, -50, 20), 0) for i in range(40)]
+        world.set_cubes([e[0] for e in line], [e[1] for e in line])
+        assert int(world._lib.hb_world_last_edit_groups(world._h)) == 1
+        for pos, mat in line:
+            ora.set_cube(pos, mat)
+        check_cubes(world, ora)
+    ora.close()
+    ctx.set_world(0)
