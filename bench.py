@@ -173,24 +173,28 @@ def measured_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
 
 
-def so_sha256() -> str:
-    from herbolution_b200 import _lib
+def src_sha256() -> str:
+    """sha256 over the CUDA sources + the header the library is built from (the .so itself is not reproducible bit
+    for bit across rebuilds, its sources are): the key that ties profiles/ncu_traffic.json to a build."""
+    from herbolution_b200 import build as b
     h = hashlib.sha256()
-    with open(_lib.LIB_PATH, "rb") as f:
-        h.update(f.read())
+    for name in sorted(b.CUDA_DEPS):
+        with open(os.path.join(b.CSRC, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    h.update(" ".join(b.NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
 def ncu_traffic(kernel_key: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
-    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py).  Only used if the capture was taken from THIS build
-    of libherbgpu.so (sha256 match); otherwise null -- a stale number is worse than none."""
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py).  Only used if the capture was taken from a build of
+    THESE sources (sha256 over csrc/ + the header + the nvcc flags); otherwise null -- a stale number is worse than none."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
-        if d.get("so_sha256") != so_sha256():
-            return None, f"profiles/ncu_traffic.json is from another build ({d.get('so_sha256', '?')[:12]}...)"
+        if d.get("src_sha256") != src_sha256():
+            return None, f"profiles/ncu_traffic.json is from other sources ({d.get('src_sha256', '?')[:12]}...)"
         k = d["kernels"].get(kernel_key)
         return (float(k["dram_bytes_per_launch"]), f"profiles/ncu_traffic.json ({k.get('source', 'ncu --set full')})") if k else (None, "kernel not in capture")
     except Exception as e:  # noqa: BLE001
@@ -210,6 +214,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (rank 0, N=1 only anyway)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-API legs (profiling runs only)")
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 record")
+    ap.add_argument("--no-c23", action="store_true", help="skip the config-2 / config-3 records")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -466,6 +471,36 @@ def main():
                     sum_over_ranks, sampler, probes, host_thr, STEP)
     clocks = sampler.stop()
 
+    # ---- the parity configs as secondary roofline records (rank 0, N=1): config 2 (noise + block fill) and config 3
+    # (meshing of pre-generated chunks incl. cross-chunk borders) through the device-pointer C ABI
+    c23 = None
+    if rank == 0 and world == 1 and not args.no_c23:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_kernels
+            c23 = {}
+            for scale, key in ((1, "4096_chunks"), (4, "65536_chunks")):
+                m = bench_kernels.measure(ctx, scale, 10)
+                c2, c3 = m["config2"], m["config3"]
+                c23[key] = {
+                    "c2": {"workload": f"BASELINE config 2: noise + block fill of {c2['chunks']} chunks (u16 ids)",
+                           "chunks_per_s": c2["chunks_per_s_ids"], "ms": c2["ms_heights_plus_fill_ids"],
+                           "roofline": {"kernel": "k_fill", "bound": "hbm", "achieved": c2["fill_ids_GBs"], "peak": peak, "unit": "GB/s",
+                                        "frac": c2["fill_ids_GBs"] / peak, "algorithmic_bytes_per_launch": c2["chunks"] * 65536,
+                                        "step_frac": c2["chunks"] * 65536 / (c2["ms_heights_plus_fill_ids"] * 1e-3) / 1e9 / peak}},
+                    "c3": {"workload": f"BASELINE config 3: meshing of {c3['chunks']} pre-generated chunks incl. cross-chunk borders",
+                           "chunks_per_s": c3["chunks_per_s"], "quads": c3["quads"], "ms": c3["ms_total"],
+                           "ms_pack_count_scan": c3["ms_pack_count_scan"], "ms_emit": c3["ms_emit"],
+                           "roofline": {"kernel": "k_pack + k_count_ids + scan + k_mesh_ids<EMIT> (whole config)", "bound": "hbm",
+                                        "achieved": c3["algorithmic_GBs"], "peak": peak, "unit": "GB/s", "frac": c3["algorithmic_GBs"] / peak,
+                                        "algorithmic_bytes": c3["algorithmic_bytes"],
+                                        "emit_gbs": c3["quads"] * 100 / (c3["ms_emit"] * 1e-3) / 1e9,
+                                        "emit_frac": c3["quads"] * 100 / (c3["ms_emit"] * 1e-3) / 1e9 / peak,
+                                        "note": "algorithmic bytes = 78 608 B read per chunk (ids + halo) + 100 B per quad written (SURVEY s8d)"}},
+                    "codec": m["codec"]}
+        except Exception as e:  # noqa: BLE001
+            c23 = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -543,9 +578,9 @@ def main():
                 "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * steps, "roofline": roofline, "cpu_baseline": cpu,
-                "e2e_instances_transport": e2e_alt, "e2e_packed_sink": e2e_packed, "probes": probes, "c5": c5, "kernels": kernels,
+                "e2e_instances_transport": e2e_alt, "e2e_packed_sink": e2e_packed, "probes": probes, "c5": c5, "c23": c23, "kernels": kernels,
                 "quads_per_step_per_gpu": quads, "instance_bytes_per_step_per_gpu": span * 100, "split": split,
-                "so_sha256": so_sha256()}
+                "src_sha256": src_sha256()}
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

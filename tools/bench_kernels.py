@@ -20,20 +20,20 @@ from herbolution_b200 import _lib  # noqa: E402
 from herbolution_b200._lib import check  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--scale", type=int, default=1)
-    a = ap.parse_args()
+def measure(ctx, scale: int = 1, reps: int = 20) -> dict:
+    """configs 2 and 3 (+ codec) on `ctx`'s device: 32*scale x 32*scale columns x 4 layers (scale 1 = BASELINE's 4096 chunks)."""
+    class A:  # noqa: D401
+        pass
+    a = A()
+    a.reps, a.scale = reps, scale
     lib = _lib.load()
-    ctx = hb.Context(0, seed=0)
     side = 32 * a.scale
     region = hb.Region(-side // 2, -side // 2, side, side, -2, 4)
     pts = region.chunk_points()
     n = len(pts)
     cols = np.stack(np.meshgrid(np.arange(side) - side // 2, np.arange(side) - side // 2, indexing="ij"), -1).reshape(-1, 2).astype(np.int32)
     col_of = (np.arange(n) // region.ncy).astype(np.int32)  # chunk index = (ix*ncz+iz)*ncy+iy
-    dev = torch.device("cuda:0")
+    dev = torch.device(f"cuda:{ctx.device}")
     st = torch.cuda.Stream(dev)
     s = C.c_void_p(st.cuda_stream)
 
@@ -103,7 +103,17 @@ def main():
     out["codec"] = {"chunks": n, "records": rspan, "encoded_MB": rspan * 3 / 1e6, "ratio": n * 65536 / (rspan * 3),
                     "ms_count_scan": t_rc, "ms_total": t_ra, "chunks_per_s": n / (t_ra * 1e-3),
                     "read_GBs": 2 * n * 65536 / (t_ra * 1e-3) / 1e9}
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--scale", type=int, default=1)
+    a = ap.parse_args()
+    ctx = hb.Context(0, seed=0)
+    print(json.dumps(measure(ctx, a.scale, a.reps)))
+    ctx.close()
 
 
 if __name__ == "__main__":

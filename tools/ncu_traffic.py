@@ -1,6 +1,6 @@
 """profiles/ncu_traffic.json from an `ncu -i X.ncu-rep --page raw --csv` export: per kernel the DRAM bytes per launch
-(dram__bytes_read.sum + dram__bytes_write.sum), tagged with the sha256 of the libherbgpu.so the capture was taken
-from, so bench.py only quotes `roofline.traffic` when it is measuring that very build.
+(dram__bytes_read.sum + dram__bytes_write.sum), tagged with the sha256 of the sources (csrc/, the header, the nvcc flags) the
+captured library was built from, so bench.py only quotes `roofline.traffic` when it is measuring a build of those sources.
 
     python tools/ncu_traffic.py <raw.csv> [<raw2.csv> ...] [--so herbolution_b200/libherbgpu.so] [--merge]"""
 import csv
@@ -21,12 +21,18 @@ def main():
     if "--so" in args:
         so = args[args.index("--so") + 1]
     files = [a for a in args if a.endswith(".csv")]
-    sha = hashlib.sha256(open(so, "rb").read()).hexdigest()
+    sys.path.insert(0, ROOT)
+    from herbolution_b200 import build as b
+    hh = hashlib.sha256()
+    for name in sorted(b.CUDA_DEPS):
+        hh.update(name.encode() + b"\0" + open(os.path.join(b.CSRC, name), "rb").read())
+    hh.update(" ".join(b.NVCC_FLAGS).encode())
+    sha = hh.hexdigest()
     out_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    out = {"so_sha256": sha, "kernels": {}}
+    out = {"src_sha256": sha, "kernels": {}}
     if merge and os.path.exists(out_path):
         old = json.load(open(out_path))
-        if old.get("so_sha256") == sha:
+        if old.get("src_sha256") == sha:
             out = old
     for fn in files:
         rows = list(csv.reader(open(fn)))
