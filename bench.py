@@ -99,7 +99,7 @@ def run_c1(threads: int):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region by an NVML polling thread (every ~2 ms), so even a
+    """SM clock / throttle reasons sampled DURING the timed region by an NVML polling thread (every ~5 ms), so even a
     40 ms timed region yields a dozen samples.  Falls back to reporting nothing if NVML is unavailable."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
@@ -141,7 +141,7 @@ class ClockSampler:
                     self.samples.append((float(sm), int(rs), pw))
                 except Exception:
                     pass
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def begin(self):
         self._on.set()
@@ -159,7 +159,7 @@ class ClockSampler:
             bits |= s[1]
         reasons = sorted(nm for b, nm in self.REASONS.items() if bits & b)
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.sm_max, "power_w_max": max(s[2] for s in self.samples),
-                "samples": len(sm), "window": "timed regions (NVML polling thread, 2 ms)", "reasons": reasons}
+                "samples": len(sm), "window": "timed regions (NVML polling thread, 5 ms)", "reasons": reasons}
 
 
 def measured_peaks():

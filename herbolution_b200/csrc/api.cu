@@ -802,9 +802,14 @@ int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t 
     const bool packed = mode != kRawInstances;
     if (mode == kPackedExpand) ensure_expander(c);
     // slab width: aim at ~384 MiB of instances per slab (about 300 KB per column on this terrain),
-    // bounded so that the optional id image (64 KiB/chunk) stays below ~1 GiB per slab
+    // bounded so that the optional id image (64 KiB/chunk) stays below ~1 GiB per slab.
+    // Packed sink: only 4 B/quad leave the device, so the same budget is counted in packed bytes (8x wider slabs):
+    // every slab costs a host synchronisation and three copies, and with 52 slabs of 14 MB that overhead kept the link
+    // at 0.66 of its rate (measured on config 4: 192 / 384 / 768 / 1536 / 3072 / 6144 MiB -> 26.7 / 19.3 / 16.7 / 15.5 /
+    // 14.9 / 14.7 ms per region; the expanding transport is host-write bound and flat between 384 and 768 MiB).
     const size_t per_col = 300 * 1024;
-    int32_t width = (int32_t)std::max<size_t>(1, ((size_t)384 << 20) / (per_col * (size_t)region->ncz));
+    const size_t slab_mib = mode == kPackedSink ? 3072 : 384;
+    int32_t width = (int32_t)std::max<size_t>(1, (slab_mib << 20) / (per_col * (size_t)region->ncz));
     if (want_ids) {
         const size_t ids_per_ix = (size_t)region->ncz * region->ncy * HB_CHUNK_VOLUME * sizeof(uint16_t);
         width = (int32_t)std::max<size_t>(1, std::min<size_t>(width, ((size_t)1 << 30) / ids_per_ix));
