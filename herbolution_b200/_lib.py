@@ -45,6 +45,11 @@ assert INSTANCE_DTYPE.itemsize == 100 and CUBE_DTYPE.itemsize == 8 and CHUNK_PT_
 assert CHUNK_CUBE_DTYPE.itemsize == 12
 
 
+class MaterialDesc(C.Structure):  # == hb_material_desc
+    _fields_ = [("group", C.c_char_p), ("key", C.c_char_p), ("cullable_faces", C.c_uint8), ("has_collider", C.c_uint8),
+                ("toughness", C.c_float)]
+
+
 class ChunkPtC(C.Structure):
     """hb_chunk_pt passed by value."""
 
@@ -124,6 +129,7 @@ PROTOTYPES = {
     "hb_multi_slab": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hb_multi_generate_mesh_region": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int, REGION_SINK, C.c_void_p,
                                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "hb_encode_palette": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "hb_probe_d2h": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
     "hb_probe_host_write": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
     "hb_region_plan_packed": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -340,6 +340,21 @@ class Context:
         check(self._lib.hb_expand_quads(self._h, _lib.ChunkPtC(x, y, z), ptr(packed), n, C.c_void_p(out.ctypes.data)))
         return out[:n]
 
+    def encode_palette(self, descs=None) -> bytes:
+        """encode_palette + Material::encode (server/src/chunk/codec.rs:70-75, material.rs:73-99) for the ctx's
+        materials; descs = [(group, key, cullable_faces, has_collider, toughness), ...] or None for the game's three."""
+        arr = None
+        if descs is not None:
+            arr = (_lib.MaterialDesc * len(descs))(*[_lib.MaterialDesc(g.encode(), k.encode(), int(cf), int(bool(hc)), float(t))
+                                                     for g, k, cf, hc, t in descs])
+        n = C.c_size_t(0)
+        rc = self._lib.hb_encode_palette(self._h, arr, None, 0, C.byref(n))
+        if rc not in (_lib.HB_OK, _lib.HB_ERR_CAPACITY):
+            check(rc)
+        out = np.zeros(max(1, n.value), dtype=np.uint8)
+        check(self._lib.hb_encode_palette(self._h, arr, ptr(out), n.value, C.byref(n)))
+        return out[:n.value].tobytes()
+
     def probe_d2h(self, nbytes: int = 1 << 30, reps: int = 4) -> float:
         """GB/s of plain device -> pinned host copies (the link ceiling of the end-to-end path)."""
         g = C.c_double(0.0)

@@ -1024,6 +1024,47 @@ int hb_probe_host_write(hb_ctx* c, size_t bytes, int32_t reps, double* gbs) {
     return HB_OK;
 }
 
+int hb_encode_palette(hb_ctx* c, const hb_material_desc* descs, uint8_t* out, size_t capacity, size_t* n_bytes) {
+    if (!c || !n_bytes) return fail(HB_ERR_INVALID, "null argument");
+    *n_bytes = 0;
+    static const hb_material_desc kGame[3] = {{"herbolution", "stone", 0x3F, 1, 10.0f},
+                                              {"herbolution", "dirt", 0x3F, 1, 0.95f},
+                                              {"herbolution", "grass", 0x3F, 1, 1.05f}};
+    std::lock_guard<std::mutex> lk(c->mu);
+    const MaterialsDev& m = c->mats;
+    if (!descs) {
+        if (m.n_materials != 3) return fail(HB_ERR_INVALID, "descs is null but the ctx holds %d materials (the default palette has 3)", m.n_materials);
+        descs = kGame;
+    }
+    std::vector<uint8_t> buf;
+    auto put = [&](const void* p, size_t n) { buf.insert(buf.end(), static_cast<const uint8_t*>(p), static_cast<const uint8_t*>(p) + n); };
+    for (int i = 0; i < m.n_materials; ++i) {
+        const hb_material_desc& d = descs[i];
+        if (!d.group || !d.key) return fail(HB_ERR_INVALID, "material %d: group/key is null", i + 1);
+        const size_t gl = strlen(d.group), kl = strlen(d.key);
+        if (gl > 255 || kl > 255) return fail(HB_ERR_INVALID, "material %d: group/key longer than 255 bytes", i + 1);
+        const uint16_t idx = (uint16_t)i;  // little-endian hosts only (as the rest of the library)
+        put(&idx, 2);
+        const uint8_t lens[2] = {(uint8_t)gl, (uint8_t)kl};
+        put(lens, 2);
+        put(d.group, gl);
+        put(d.key, kl);
+        const uint8_t e0 = (uint8_t)((uint8_t)(d.cullable_faces << 6) | (d.has_collider ? 1u : 0u));  // u8 shift, material.rs:79
+        const uint8_t tex = 0;
+        put(&e0, 1);
+        put(&tex, 1);
+        const uint16_t nc = (uint16_t)m.n_colors[i];
+        put(&nc, 2);
+        put(m.rgba[i], (size_t)m.n_colors[i] * 4 * sizeof(float));
+        put(&d.toughness, sizeof(float));
+    }
+    *n_bytes = buf.size();
+    if (buf.size() > capacity || (!out && !buf.empty()))
+        return fail(HB_ERR_CAPACITY, "palette needs %zu bytes, %zu given", buf.size(), capacity);
+    if (!buf.empty()) memcpy(out, buf.data(), buf.size());
+    return HB_OK;
+}
+
 int hb_region_plan_packed(hb_region_plan* p, const hb_packed_quad** d_packed) {
     if (!p || !d_packed) return fail(HB_ERR_INVALID, "null argument");
     *d_packed = p->d_packed.as<hb_packed_quad>();

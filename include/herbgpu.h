@@ -401,8 +401,25 @@ HB_API int hb_world_read_chunk(hb_world *world, hb_chunk_pt pt, hb_palette_cube 
  * (the 0-based index) and 0 for None, and reads back NonZeroU16::new(v + 1): None and the first material share wire
  * value 0 and come back as the first material -- the codec is lossy by construction (and unused: no writer is ever
  * called, server/src/chunk/provider.rs:48-58); it is reproduced here as it is, not repaired.  The palette half of
- * CubeGrid::encode is not produced (decode does not skip it either).
+ * CubeGrid::encode is hb_encode_palette below (CubeGrid::decode does not skip it -- another reason the reference's
+ * codec cannot round-trip; the bytes are reproduced, the defect is not repaired).
  * ---------------------------------------------------------------------------------------------- */
+/* encode_palette (codec.rs:70-75) + Material::encode (server/src/chunk/material.rs:73-99): for palette entry i
+ * (0-based, the ctx's materials in id order)
+ *   [u16 LE i][u8 len(group)][u8 len(key)][group bytes][key bytes][u8 (cullable_faces << 6) | has_collider]
+ *   [u8 0 = Texture::Colors][u16 LE n_colors][n_colors x (r, g, b, a) f32 LE][f32 LE toughness]
+ * (the shift is done in u8 as in the reference, so only the low two face bits survive).  The colours are the ctx's
+ * (hb_set_materials); everything else comes from `descs`, one per material, or -- descs = NULL, only valid while the
+ * ctx holds the default three materials -- from Material::stone / dirt / grass (material.rs:27-61).
+ * CubeGrid::encode(chunk) = these bytes followed by the chunk's hb_rle_encode stream.  Pure host code.
+ * Two-call pattern: *n_bytes is always set; HB_ERR_CAPACITY if capacity is too small. */
+typedef struct hb_material_desc {
+    const char *group, *key;   /* GroupKeyBuf, e.g. "herbolution", "stone" (each at most 255 bytes) */
+    uint8_t cullable_faces;    /* CubeFaces bits, 0x3F = all */
+    uint8_t has_collider;
+    float toughness;
+} hb_material_desc;
+HB_API int hb_encode_palette(hb_ctx *ctx, const hb_material_desc *descs, uint8_t *out, size_t capacity, size_t *n_bytes);
 /* ids: n x 32768.  Chunk i's stream is out[out_offsets[i] .. + out_sizes[i]) (bytes; starts are multiples of 12,
  * gaps zero-filled); *out_total = bytes spanned.  Two-call pattern: HB_ERR_CAPACITY reports offsets, sizes, total. */
 HB_API int hb_rle_encode(hb_ctx *ctx, const uint16_t *ids, size_t n, uint8_t *out, uint64_t out_capacity,

@@ -1153,3 +1153,38 @@ int hbo_rle_decode(const uint8_t *bytes, size_t nbytes, uint16_t *raw_ids) {
     }
     return 0;
 }
+
+/* encode_palette (codec.rs:70-75): for (i, material) in palette.materials().enumerate(): u16 LE i, then
+ * Material::encode (material.rs:73-99): u8 group.len, u8 key.len, group bytes, key bytes,
+ * u8 (cullable_faces.bits() << 6 | has_collider) -- a u8 shift, the upper four face bits fall off --,
+ * Texture::Colors: u8 0, u16 LE vec.len, r g b a as f32 LE per colour; f32 LE toughness.
+ * groups / keys / cullable / collider / toughness: one entry per material (the colours come from the palette).
+ * Returns the number of bytes the palette has; writes at most cap. */
+size_t hbo_encode_palette(const hbo_palette *pal, const char *const *groups, const char *const *keys, const uint8_t *cullable,
+                          const uint8_t *collider, const float *toughness, uint8_t *out, size_t cap) {
+    size_t n = 0;
+#define HBO_PUT(ptr, len)                                                   \
+    do {                                                                    \
+        for (size_t q_ = 0; q_ < (size_t)(len); ++q_, ++n)                  \
+            if (n < cap) out[n] = ((const uint8_t *)(ptr))[q_];             \
+    } while (0)
+    for (int32_t i = 0; i < pal->n_materials; ++i) {
+        const uint8_t idx[2] = {(uint8_t)(i & 255), (uint8_t)(i >> 8)};
+        HBO_PUT(idx, 2);
+        const uint8_t gl = (uint8_t)strlen(groups[i]), kl = (uint8_t)strlen(keys[i]);
+        HBO_PUT(&gl, 1);
+        HBO_PUT(&kl, 1);
+        HBO_PUT(groups[i], gl);
+        HBO_PUT(keys[i], kl);
+        const uint8_t e0 = (uint8_t)((uint8_t)(cullable[i] << 6) | (collider[i] ? 1 : 0));
+        HBO_PUT(&e0, 1);
+        const uint8_t tex = 0;
+        HBO_PUT(&tex, 1);
+        const uint8_t nc[2] = {(uint8_t)(pal->mat[i].n_colors & 255), (uint8_t)(pal->mat[i].n_colors >> 8)};
+        HBO_PUT(nc, 2);
+        for (int32_t c = 0; c < pal->mat[i].n_colors; ++c) HBO_PUT(pal->mat[i].rgba[c], 16);
+        HBO_PUT(&toughness[i], 4);
+    }
+#undef HBO_PUT
+    return n;
+}

@@ -180,6 +180,8 @@ void hbo_apply_updates(hbo_cube *client_cubes, const hbo_chunk_cube *entries, ui
  * raw ids: 0 = None, k = palette index k-1 (the NonZeroU16 niche the reference stores). */
 size_t hbo_rle_encode(const uint16_t *raw_ids, size_t n, uint8_t *out, size_t cap); /* codec.rs:73-101 */
 int hbo_rle_decode(const uint8_t *bytes, size_t nbytes, uint16_t *raw_ids);        /* codec.rs:52-66 */
+size_t hbo_encode_palette(const hbo_palette *pal, const char *const *groups, const char *const *keys, const uint8_t *cullable,
+                          const uint8_t *collider, const float *toughness, uint8_t *out, size_t cap); /* codec.rs:70-75, material.rs:73-99 */
 
 #ifdef __cplusplus
 }

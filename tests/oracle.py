@@ -337,6 +337,23 @@ def rle_encode(ids: np.ndarray) -> np.ndarray:
     return out
 
 
+def encode_palette(pal: Palette, descs) -> bytes:
+    """descs = [(group, key, cullable_faces, has_collider, toughness), ...], one per palette material."""
+    n = len(descs)
+    groups = (C.c_char_p * n)(*[d[0].encode() for d in descs])
+    keys = (C.c_char_p * n)(*[d[1].encode() for d in descs])
+    cull = (C.c_uint8 * n)(*[int(d[2]) for d in descs])
+    coll = (C.c_uint8 * n)(*[int(bool(d[3])) for d in descs])
+    tough = (C.c_float * n)(*[float(d[4]) for d in descs])
+    f = lib().hbo_encode_palette
+    f.restype = C.c_size_t
+    f.argtypes = [C.POINTER(Palette), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    need = f(C.byref(pal), groups, keys, cull, coll, tough, None, 0)
+    out = np.zeros(max(need, 1), dtype=np.uint8)
+    assert f(C.byref(pal), groups, keys, cull, coll, tough, out.ctypes.data, need) == need
+    return out[:need].tobytes()
+
+
 def rle_decode(data: np.ndarray):
     """CubeGrid::decode record loop -> (status, raw ids)."""
     data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)

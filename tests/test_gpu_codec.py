@@ -71,3 +71,32 @@ def test_decode_edges_and_errors(ctx):
         ctx.rle_decode(data, [4], [data.shape[0]])  # stream runs past the input
     assert e.value.code == hb._lib.HB_ERR_INVALID
     assert ctx.rle_encode(np.zeros((0, hb.CHUNK_VOLUME), dtype=np.uint16))["bytes"].shape[0] == 0
+
+
+def test_encode_palette_matches_oracle(ctx):
+    """hb_encode_palette = encode_palette + Material::encode (codec.rs:70-75, material.rs:73-99): the game's three
+    materials by default, custom palettes with their own group keys; together with the RLE stream it is the byte
+    string CubeGrid::encode produces."""
+    from test_oracle_codec import GAME_DESCS, py_encode_palette
+    got = ctx.encode_palette()
+    assert got == O.encode_palette(O.default_palette(), GAME_DESCS)
+    custom = [[(0.25, 0.5, 0.75, 1.0)], [(0.0, 0.0, 0.0, 1.0), (1.0, 1.0, 1.0, 0.5)], [(0.1 * k, 0.2, 0.3, 1.0) for k in range(8)],
+              [(0.9, 0.9, 0.1, 1.0)]]
+    descs = [("a", "", 0x15, False, -2.5), ("grp", "k" * 200, 0x02, True, 0.0), ("herbolution", "sand", 0x3F, True, 0.5),
+             ("x" * 255, "y", 0x00, False, 1e9)]
+    try:
+        ctx.set_materials(custom)
+        want = O.encode_palette(O.make_palette(custom), descs)
+        assert ctx.encode_palette(descs) == want == py_encode_palette(custom, descs)
+        with pytest.raises(hb.HerbGpuError):  # no default descriptions for a 4-material palette
+            ctx.encode_palette()
+        # CubeGrid::encode of one chunk = palette bytes + its record stream
+        ids = np.zeros((1, 32768), dtype=np.uint16)
+        ids[0, :5000] = 2
+        enc = ctx.rle_encode(ids)
+        stream = bytes(enc["bytes"][int(enc["offsets"][0]):int(enc["offsets"][0]) + int(enc["sizes"][0])])
+        assert want + stream == want + O.rle_encode(ids[0]).tobytes()
+    finally:
+        ctx.set_materials([[(0.5, 0.5, 0.5, 1.0), (0.6, 0.6, 0.6, 1.0), (0.7, 0.7, 0.7, 1.0)],
+                           [(0.4, 0.3, 0.2, 1.0), (0.5, 0.4, 0.3, 1.0), (0.6, 0.5, 0.4, 1.0)],
+                           [(0.1, 0.8, 0.1, 1.0), (0.2, 0.9, 0.2, 1.0), (0.3, 1.0, 0.3, 1.0)]])

@@ -74,3 +74,35 @@ def test_decode_edges():
     assert rc == 0
     rc, _ = O.rle_decode(np.r_[full, np.array([129, 0, 0], dtype=np.uint8)])
     assert rc == -1
+
+
+GAME_DESCS = [("herbolution", "stone", 0x3F, True, 10.0), ("herbolution", "dirt", 0x3F, True, 0.95),
+              ("herbolution", "grass", 0x3F, True, 1.05)]  # Material::stone / dirt / grass, material.rs:27-61
+
+
+def py_encode_palette(colors, descs) -> bytes:
+    """encode_palette + Material::encode transcribed from codec.rs:70-75 / material.rs:73-99 (independent of the C oracle)."""
+    import struct
+    buf = bytearray()
+    for i, (cols, (group, key, cull, coll, tough)) in enumerate(zip(colors, descs)):
+        buf += struct.pack("<H", i)
+        buf += bytes([len(group.encode()), len(key.encode())]) + group.encode() + key.encode()
+        buf.append(((cull << 6) & 0xFF) | int(bool(coll)))  # u8 arithmetic
+        buf.append(0)
+        buf += struct.pack("<H", len(cols))
+        for rgba in cols:
+            buf += struct.pack("<4f", *rgba)
+        buf += struct.pack("<f", tough)
+    return bytes(buf)
+
+
+def test_palette_bytes_oracle_vs_python_restatement():
+    game = [[(0.5, 0.5, 0.5, 1.0), (0.6, 0.6, 0.6, 1.0), (0.7, 0.7, 0.7, 1.0)],
+            [(0.4, 0.3, 0.2, 1.0), (0.5, 0.4, 0.3, 1.0), (0.6, 0.5, 0.4, 1.0)],
+            [(0.1, 0.8, 0.1, 1.0), (0.2, 0.9, 0.2, 1.0), (0.3, 1.0, 0.3, 1.0)]]
+    got = O.encode_palette(O.default_palette(), GAME_DESCS)
+    assert got == py_encode_palette(game, GAME_DESCS)
+    assert got[:2] == b"\x00\x00" and got[2:4] == bytes([11, 5]) and got[4:20] == b"herbolutionstone" and got[20] == 0xC1
+    custom = [[(0.25, 0.5, 0.75, 1.0)], [(0.0, 0.0, 0.0, 1.0), (1.0, 1.0, 1.0, 0.5)]]
+    descs = [("a", "", 0x15, False, -2.5), ("grp", "k" * 200, 0x02, True, 0.0)]
+    assert O.encode_palette(O.make_palette(custom), descs) == py_encode_palette(custom, descs)
