@@ -591,20 +591,39 @@ def test_region_config4_full_size(ctx):
     assert (ctx.download(res2["d_counts"], np.uint32, n) == counts).all() and res2["quads"] == res["quads"]
     rng = np.random.default_rng(2024)
     w = O.world(0)
-    for _ in range(3):
-        px, pz = int(rng.integers(0, 250)), int(rng.integers(0, 250))
+    # 6x6-column patches meshed by the oracle as regions of their own, ALL six layers (layer 0 = the region-bottom fast
+    # path with 39 % of the benchmark's quads, layer 5 = the region top): three random interior patches, the region's
+    # corner, and one patch on each of two borders.  A column is comparable iff every one of its 8 neighbour columns is
+    # inside the patch (the oracle saw it) or outside the region (absent for both).
+    spots = [(int(rng.integers(1, 249)), int(rng.integers(1, 249))) for _ in range(3)]
+    spots += [(0, 0), (250, int(rng.integers(1, 249))), (int(rng.integers(1, 249)), 250)]
+    compared = slab_chunks = top_chunks = 0
+    for px, pz in spots:
         patch = (reg[0] + px, reg[1] + pz, 6, 6, reg[4], reg[5])
         ref = O.region_pipeline(w, patch, literal=True, threads=8)
         roff = np.concatenate([[0], np.cumsum(ref["counts"].astype(np.int64))])
-        for ix in range(1, 5):
-            for iz in range(1, 5):
-                for iy in range(1, 5):  # layers 0 and 5 touch the region's bottom / top on both sides alike, but keep to the interior
+        for ix in range(6):
+            for iz in range(6):
+                ok = True
+                for dx in (-1, 0, 1):
+                    for dz in (-1, 0, 1):
+                        ax, az = px + ix + dx, pz + iz + dz
+                        in_patch = 0 <= ix + dx < 6 and 0 <= iz + dz < 6
+                        in_region = 0 <= ax < 256 and 0 <= az < 256
+                        ok = ok and (in_patch or not in_region)
+                if not ok:
+                    continue
+                for iy in range(6):
                     g = ((px + ix) * 256 + (pz + iz)) * 6 + iy
                     k = (ix * 6 + iz) * 6 + iy
                     assert counts[g] == ref["counts"][k], (px, pz, ix, iz, iy)
+                    compared += 1
                     if counts[g]:
+                        slab_chunks += iy == 0
+                        top_chunks += iy == 5
                         inst = ctx.download(res2["d_instances"] + int(offsets[g]) * 100, hb.INSTANCE_DTYPE, int(counts[g]))
                         assert_instances_equal(inst, ref["instances"][roff[k]:roff[k + 1]], f"patch {px},{pz} chunk {ix},{iz},{iy}")
+    assert compared >= 6 * 16 * 6 and slab_chunks >= 96  # every compared column has a bottom chunk with >= 1024 quads
     plan.close()
 
 
