@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-API legs (profiling runs only)")
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 record")
     ap.add_argument("--no-c23", action="store_true", help="skip the config-2 / config-3 records")
+    ap.add_argument("--host-threads", type=int, default=0, help="expander threads per GPU (0 = host cores / GPUs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -283,7 +284,7 @@ def main():
         return sharding.reduce_sum(x, device="cuda")
 
     ctx = hb.Context(device=local_rank, seed=SEED)
-    host_thr = max(1, host_threads() // max(1, world))
+    host_thr = args.host_threads if args.host_threads > 0 else max(1, host_threads() // max(1, world))
     ctx.set_host_threads(host_thr)
     reg = hb.Region(*region_for_rank(cols, rank, world))
     plan = ctx.region_plan(reg)  # sizes the instance buffer with one synchronous count pass
