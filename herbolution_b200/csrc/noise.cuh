@@ -96,6 +96,19 @@ __device__ __forceinline__ float2 nma2(float2 a, float2 b, float2 c) {
     else return sub2(c, smul2(a, b));  // scalar multiplies: a packed product feeding a packed add would be contracted
 }
 
+// c - a*a, clamped to [0, 1] (callers guarantee c <= 0.5): the clamp rides on the producing instruction
+template <bool FMA>
+__device__ __forceinline__ float2 nma_sat(float2 a, float2 c) {
+    if constexpr (FMA) return pk(__saturatef(__fmaf_rn(-a.x, a.x, c.x)), __saturatef(__fmaf_rn(-a.y, a.y, c.y)));
+    else return pk(__saturatef(__fsub_rn(c.x, __fmul_rn(a.x, a.x))), __saturatef(__fsub_rn(c.y, __fmul_rn(a.y, a.y))));
+}
+// gx*x + gy*y for gradient components in {+-1, +-2}
+template <bool FMA>
+__device__ __forceinline__ float2 gdot(float2 gx, float2 x, float2 gy, float2 y) {
+    if constexpr (FMA) return __ffma2_rn(gx, x, mul2(gy, y));
+    else return sadd2(mul2(gx, x), mul2(gy, y));
+}
+
 // functions/simplex_32.rs:103-170 (value half of simplex_2d_deriv) for TWO samples at once: every variable is a
 // float2 (.x = sample A, .y = sample B).  The arithmetic per sample is op for op the reference's: separate
 // round-to-nearest add/mul everywhere, true FMA only at the six neg_mul_add sites
@@ -169,23 +182,24 @@ __device__ __forceinline__ float2 simplex2_pair(const NoiseTables& T, float2 x, 
     const float2 x2 = add2(add2(x0, bc(-1.0f)), bc(HB_G22));
     const float2 y2 = add2(add2(y0, bc(-1.0f)), bc(HB_G22));
 
-    float2 t0 = nma2<FMA>(y0, y0, nma2<FMA>(x0, x0, bc(0.5f)));
-    float2 t1 = nma2<FMA>(y1, y1, nma2<FMA>(x1, x1, bc(0.5f)));
-    float2 t2 = nma2<FMA>(y2, y2, nma2<FMA>(x2, x2, bc(0.5f)));
-    // t &= t.cmp_gte(0): negative -> +0.  fmaxf(t, 0) differs only for t = -0 (keeps/loses the sign
-    // of zero), and t is squared next, so the result is identical.
-    t0 = pk(fmaxf(t0.x, 0.0f), fmaxf(t0.y, 0.0f));
-    t1 = pk(fmaxf(t1.x, 0.0f), fmaxf(t1.y, 0.0f));
-    t2 = pk(fmaxf(t2.x, 0.0f), fmaxf(t2.y, 0.0f));
+    // t = (0.5 - x*x) - y*y, then t &= t.cmp_gte(0): negative -> +0.  t never exceeds 0.5, so the clamp is the
+    // saturation modifier of the instruction that produces t (FFMA.SAT / FADD.SAT: [0, 1]) instead of a separate
+    // FMNMX per value; it differs from the mask only for t = -0 (sign of zero), and t is squared next.
+    float2 t0 = nma_sat<FMA>(y0, nma2<FMA>(x0, x0, bc(0.5f)));
+    float2 t1 = nma_sat<FMA>(y1, nma2<FMA>(x1, x1, bc(0.5f)));
+    float2 t2 = nma_sat<FMA>(y2, nma2<FMA>(x2, x2, bc(0.5f)));
     const float2 t20 = mul2(t0, t0), t40 = mul2(t20, t20);
     const float2 t21 = mul2(t1, t1), t41 = mul2(t21, t21);
     const float2 t22 = mul2(t2, t2), t42 = mul2(t22, t22);
 
-    // g = gx*x + gy*y: two multiplies and one add, as the operator overloads do (never fused):
-    // packed products, scalar sums
-    const float2 n0 = mul2(t40, sadd2(mul2(g0x, x0), mul2(g0y, y0)));
-    const float2 n1 = mul2(t41, sadd2(mul2(g1x, x1), mul2(g1y, y1)));
-    const float2 n2 = mul2(t42, sadd2(mul2(g2x, x2), mul2(g2y, y2)));
+    // g = gx*x + gy*y: two multiplies and one add in the reference (operator overloads, never fused).  The gradient
+    // components are +-1 and +-2 (gradient_32.rs:13-30), so both products are EXACT, and a fused multiply-add of exact
+    // terms rounds exactly once like the reference's add does: fma(gx, x, gy*y) is bit-identical (signed zeros
+    // included) and one packed instruction shorter.  Used in the fused column only, so that the SSE2 / scalar column's
+    // kernels stay free of any FMA (tests/test_abi.py).
+    const float2 n0 = mul2(t40, gdot<FMA>(g0x, x0, g0y, y0));
+    const float2 n1 = mul2(t41, gdot<FMA>(g1x, x1, g1y, y1));
+    const float2 n2 = mul2(t42, gdot<FMA>(g2x, x2, g2y, y2));
     return mul2(sadd2(n0, sadd2(n1, n2)), bc(45.26450774985561631259f));
 }
 

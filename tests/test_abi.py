@@ -135,13 +135,16 @@ def test_host_mirror_api_surface():
 def test_noise_kernel_has_no_unintended_fma_contraction():
     """ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false; the reference's
     operator overloads never fuse (only the six neg_mul_add sites of simplex_2d do).  csrc/noise.cuh routes every
-    product that feeds an add across a packed/scalar boundary; this pins the result in the shipped SASS:
-    the FBM k_heights evaluates 6 simplex pairs in its instruction stream (2 pairs x {first octave, octave loop for
-    lacunarity == 2, octave loop for any other lacunarity}), so it must contain exactly 6 x 6 FFMA2 and no scalar FFMA
-    at all.  The other noise kinds (template parameter KIND, HB_NOISE_*) have one octave loop: turbulence 4 x 6,
-    gradient 2 x 6 (no octave loop), ridge 24 plus its own neg_mul_add (functions/ridge_32.rs:27, fused on AVX2) = one
-    scalar FFMA per lane of each of the 2 packed loop bodies.  Every kind exists with the conversion-free index path
-    (FAST) and with the exact-conversion fallback."""
+    product that feeds an add across a packed/scalar boundary; this pins the result in the shipped SASS.  Per simplex
+    pair of the fused column (hb_set_fma_mode(1)) there are exactly
+      * 6 FFMA2: the three inner neg_mul_add (0.5 - x*x) and the three gradient dot products gx*x + gy*y, whose
+        products are exact (components +-1 / +-2), so the fused form is bit-identical to the reference's mul, mul, add;
+      * 6 scalar FFMA.SAT: the three outer neg_mul_add (t - y*y) for both samples, carrying the t >= 0 clamp;
+      * 13 FMUL2 (16 multiplies of the reference minus the three folded into the dot products);
+    plus, per octave-loop pair, ridge's own neg_mul_add (functions/ridge_32.rs:27: one scalar FFMA per lane) and FBM's
+    packed `simplex * amp`.  How many copies of the pair the compiler lays down (loop peeling, the two lacunarity
+    variants) is its business.  The unfused column (SSE2 / scalar hosts) contains no FMA of any kind.  Every kind exists
+    with the conversion-free index path (FAST) and with the exact-conversion fallback."""
     import shutil
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
@@ -156,9 +159,7 @@ def test_noise_kernel_has_no_unintended_fma_contraction():
         ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", f)
         assert not any(o.startswith("FFMA") for o in ops), "FMA in the unfused noise column"
     heights = [f for f in heights if f not in unfused]
-    # KIND -> scalar FFMA per simplex pair in an octave loop body (ridge only), FMUL2 besides the 16 of a simplex
-    # pair (FBM: the packed `simplex * amp` of every loop body).  How many copies of the simplex pair the compiler
-    # lays down (loop peeling, the two lacunarity variants) is its business; the per-pair mix is not.
+    # KIND -> (extra scalar FFMA per octave-loop pair: ridge only, extra FMUL2 per octave-loop pair: FBM's `* amp`)
     want = {0: (0, 1), 1: (2, 0), 2: (0, 0), 3: (0, 0)}
     conv = {}
     for f in heights:
@@ -166,13 +167,15 @@ def test_noise_kernel_has_no_unintended_fma_contraction():
         kind, fast = int(m.group(1)), m.group(2) == "1"
         ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", f)
         packed = sum(o.startswith("FFMA2") for o in ops)
-        scalar = sum(o.startswith("FFMA") and not o.startswith("FFMA2") for o in ops)
+        sat = sum(o.startswith("FFMA.SAT") for o in ops)
+        scalar = sum(o.startswith("FFMA") and not o.startswith("FFMA2") for o in ops) - sat
         assert packed % 6 == 0 and packed >= 12, f"kind {kind}: FFMA2 count {packed} is not 6 per simplex pair"
         pairs, firsts = packed // 6, 2  # two first-octave evaluations (k = 0, 2) precede the loops
+        assert sat == 6 * pairs, f"kind {kind}: {sat} FFMA.SAT for {pairs} simplex pairs"
         assert scalar == want[kind][0] * (pairs - firsts), f"kind {kind}: scalar FFMA count {scalar}, check for contraction"
         fmul2 = sum(o.startswith("FMUL2") for o in ops)
-        # a contraction would turn one FMUL2 per site into an extra FFMA2: fewer than 16 FMUL2 per counted pair
-        assert 16 * pairs <= fmul2 <= 16 * pairs + want[kind][1] * (pairs - firsts), f"kind {kind}: {fmul2} FMUL2 for {pairs} simplex pairs"
+        # a contraction would turn one FMUL2 per site into an extra FFMA2: fewer than 13 FMUL2 per counted pair
+        assert 13 * pairs <= fmul2 <= 13 * pairs + want[kind][1] * (pairs - firsts), f"kind {kind}: {fmul2} FMUL2 for {pairs} simplex pairs"
         assert sum(o.startswith("FMUL2") for o in ops) > 0 and sum(o.startswith("FADD2") for o in ops) > 0  # Blackwell packed f32x2
         conv[(f.split("\n", 1)[0].split("k_heights")[1][:16], kind, fast)] = (sum(o.startswith(("F2I", "I2F")) for o in ops), pairs)
     # the FAST index path stays off the quarter-rate conversion pipe: each simplex pair of the exact path converts
