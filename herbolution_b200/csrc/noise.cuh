@@ -121,8 +121,8 @@ __device__ __forceinline__ float2 gdot(float2 gx, float2 x, float2 gy, float2 y)
 //     (j & 255) * 2, the byte offset into perm4.
 //   * t = f32(i + j) * G2 is computed as (ips + jps) * G2: the float sum of two integral values below 2^21 is exact
 //     and equals the converted integer sum.
-//   * j1 = (y0 > x0) is taken as NOT (x0 >= y0), i.e. -1 - i1 in float: identical for every non-NaN input, and
-//     coordinates are finite by construction.
+//   * j1 = (y0 > x0) is taken as NOT (x0 >= y0): identical for every non-NaN input, and coordinates are finite by
+//     construction.
 // Bit-exactness of the result is what tests/test_gpu_parity.py::test_noise_tiles_bit_exact asserts (0 ulp).
 template <bool FAST, bool FMA = true>
 __device__ __forceinline__ float2 simplex2_pair(const NoiseTables& T, float2 x, float2 y) {
@@ -137,10 +137,11 @@ __device__ __forceinline__ float2 simplex2_pair(const NoiseTables& T, float2 x, 
         x0 = sub2(x, sub2(ips, t));
         y0 = sub2(y, sub2(jps, t));
         const bool xgeA = x0.x >= y0.x, xgeB = x0.y >= y0.y;  // i1 = all-ones mask (-1) when x0 >= y0
-        const float2 i1f = pk(xgeA ? -1.0f : 0.0f, xgeB ? -1.0f : 0.0f);
-        const float2 j1f = sub2(bc(-1.0f), i1f);              // -1 where y0 > x0
-        x1 = add2(add2(x0, i1f), bc(HB_G2));
-        y1 = add2(add2(y0, j1f), bc(HB_G2));
+        // x1 = (x0 + f32(i1)) + G2 with i1 = -1 / 0: x0 - 1 is needed for x2 anyway and x0 + 0 is x0 (a -0 would
+        // only differ before the + G2), so the masks select between values that exist already; j1 = NOT i1
+        const float2 xm = add2(x0, bc(-1.0f)), ym = add2(y0, bc(-1.0f));
+        x1 = add2(pk(xgeA ? xm.x : x0.x, xgeB ? xm.y : x0.y), bc(HB_G2));
+        y1 = add2(pk(xgeA ? y0.x : ym.x, xgeB ? y0.y : ym.y), bc(HB_G2));
         // gi_k = P[(ii + di) + P[jj + dj]] (simplex_32.rs:137-141) as byte offsets; k1 is k0 + 1 when i1 is set
         // (then j1 is not: P[jj]), else P[jj + 1] without the +1
         const char* const pb = reinterpret_cast<const char*>(T.perm4);
