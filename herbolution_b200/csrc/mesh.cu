@@ -693,23 +693,29 @@ struct TileRegs {
 // global -> registers half of the tile staging (raw heights; ABSENT for columns outside the region)
 __device__ __forceinline__ TileRegs fetch_heights_tile(const RegionDev& r, const int32_t* __restrict__ heights, int ix, int iz) {
     const int tid = threadIdx.x;
-    auto tile_of = [&](int cix, int ciz) -> const int32_t* {
-        if (cix < 0 || cix >= r.ncx || ciz < 0 || ciz >= r.ncz) return nullptr;
-        return heights + ((size_t)(cix - r.hx_begin) * r.ncz + ciz) * HB_CHUNK_AREA;
-    };
+    // the eight neighbour tiles lie at fixed strides from the column's own tile: one 64-bit address per column, the
+    // rest is 32-bit offsets (ncz * 1024 < 2^31 within the coordinate limit)
+    const int32_t* const c0 = heights + ((size_t)(ix - r.hx_begin) * r.ncz + iz) * HB_CHUNK_AREA;
+    const int dxs = r.ncz * HB_CHUNK_AREA;  // elements between the tiles of ix and ix + 1 (iz + 1: HB_CHUNK_AREA)
     TileRegs t;
-    t.centre = __ldg(reinterpret_cast<const int4*>(tile_of(ix, iz)) + tid);  // element e = x*32 + z
+    t.centre = __ldg(reinterpret_cast<const int4*>(c0) + tid);  // element e = x*32 + z
     t.edge = kHeightAbsent;
-    if (tid < 128) {  // edges: west (x = -1), east (x = 32), south (z = -1), north (z = 32); 32 values each
-        const int side = tid >> 5, j = tid & 31;
-        const int32_t* p = side == 0 ? tile_of(ix - 1, iz) : side == 1 ? tile_of(ix + 1, iz)
-                         : side == 2 ? tile_of(ix, iz - 1) : tile_of(ix, iz + 1);
-        const int src = side == 0 ? 31 * 32 + j : side == 1 ? j : side == 2 ? j * 32 + 31 : j * 32;
-        if (p) t.edge = __ldg(p + src);
-    } else if (tid < 132) {  // corners
-        const int c = tid - 128, dx = (c & 1) ? 1 : -1, dz = (c & 2) ? 1 : -1;
-        const int32_t* p = tile_of(ix + dx, iz + dz);
-        if (p) t.edge = __ldg(p + (dx < 0 ? 31 : 0) * 32 + (dz < 0 ? 31 : 0));
+    if (tid < 132) {
+        int dx, dz, src;
+        if (tid < 128) {  // edges: west (x = -1), east (x = 32), south (z = -1), north (z = 32); 32 values each
+            const int side = tid >> 5, j = tid & 31;
+            dx = side == 0 ? -1 : (side == 1 ? 1 : 0);
+            dz = side == 2 ? -1 : (side == 3 ? 1 : 0);
+            src = side == 0 ? 31 * 32 + j : side == 1 ? j : side == 2 ? j * 32 + 31 : j * 32;
+        } else {  // corners
+            const int c = tid - 128;
+            dx = (c & 1) ? 1 : -1;
+            dz = (c & 2) ? 1 : -1;
+            src = (dx < 0 ? 31 : 0) * 32 + (dz < 0 ? 31 : 0);
+        }
+        // columns outside the region are ABSENT
+        if ((unsigned)(ix + dx) < (unsigned)r.ncx && (unsigned)(iz + dz) < (unsigned)r.ncz)
+            t.edge = __ldg(c0 + (dx * dxs + dz * HB_CHUNK_AREA + src));
     }
     return t;
 }
@@ -776,6 +782,7 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
     __syncthreads();  // previous column's readers of s_h / s_next are done
     // columns are drawn from a ticket counter (`ticket`, zeroed by the launch wrapper): the per-column cost follows
     // the terrain (how many layers a column's surface spans), and a static stride left a tail of late CTAs
+    // (drawing the ticket two columns ahead, to hide the atomic's round trip, changes nothing: 0.353 vs 0.350 ms)
     if (tid == 0) s_next = (int)gridDim.x + (int)atomicAdd(ticket, 1ULL);
     store_heights_tile(next, s_h, cmax, hmin, emin, rel);
     __syncthreads();
