@@ -792,36 +792,58 @@ __global__ void __launch_bounds__(kT) k_count_region(const RegionDev r, const in
         const int nl = min(32, r.ncy - iy0);
         s_acc[warp][lane] = 0;
         __syncwarp();
-        for (int k = 0; k < 4; ++k) {
-            const int* o = s_h + (k * 8 + warp + 1) * kTile + (lane + 1);
-            const int hc = o[0], hE = o[kTile], hW = o[-kTile], hN = o[1], hS = o[-1];
-            // Layers below `lo` see this column and its four neighbours completely solid; layers above `hi`
-            // see the column empty.  Only the warp-wide union [wlo, whi] needs the full formula; outside it
-            // the only faces are the region's bottom (layer 0, Down) and top (last layer, Up) boundary faces.
-            int lo = min(min(hc - 1, hE), min(min(hW, hN), hS));
-            lo = hc > 0 ? (lo < 0 ? 0 : lo >> 5) : INT32_MAX;
-            const int hi = hc > 0 ? (hc - 1) >> 5 : -1;
-            const int wlo = __reduce_min_sync(0xffffffffu, lo);
-            const int whi = __reduce_max_sync(0xffffffffu, hi);
-            const int nsolid = __popc(__ballot_sync(0xffffffffu, hc > 0));
-            const int j1 = min(min(whi, last), iy0 + nl - 1);
-            for (int j = max(wlo, iy0); j <= j1; ++j) {  // warp-uniform bounds
-                const int a = j * 32;
-                const int rc = min(max(hc - a, 0), 32);
-                uint32_t v = 0;
-                if (rc > 0) {
-                    v = max(0, rc - min(max(hE - a, 0), 32)) + max(0, rc - min(max(hW - a, 0), 32)) +
-                        max(0, rc - min(max(hN - a, 0), 32)) + max(0, rc - min(max(hS - a, 0), 32));
-                    v += (hc - a <= 32 || j == last) ? 1u : 0u;  // up: real top, or the chunk above is absent
-                    v += (j == 0) ? 1u : 0u;                     // down: only where the chunk below is absent
+        // Each thread holds four cells ADJACENT in x (rows 4*warp + k, column z = lane): their east/west neighbours
+        // are each other, so per layer every clamped height is computed once and the three inner x-pairs cost one
+        // |difference| each (max(0, a - b) + max(0, b - a) = |a - b|: the pair's two facing side counts together).
+        // Layers below `lo` see a cell and its four neighbours completely solid; layers above `hi` see it empty.  Only
+        // the union [wlo, whi] over the warp's 128 cells needs the formula (which is valid for every layer); outside
+        // it the only faces are the region's bottom (layer 0, Down) and top (last layer, Up) boundary faces.  One pair
+        // of range reductions and one sum reduction per layer serve all four rows.
+        int hc[4], hN[4], hS[4], hWest, hEast;
+        int lo = INT32_MAX, hi = -1, solid = 0;
+        {
+            const int* o = s_h + (4 * warp + 1) * kTile + (lane + 1);
+            hWest = o[-kTile];
+            hEast = o[4 * kTile];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { hc[k] = o[k * kTile]; hN[k] = o[k * kTile + 1]; hS[k] = o[k * kTile - 1]; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (hc[k] > 0) {
+                    const int hW = k ? hc[k - 1] : hWest, hE = k < 3 ? hc[k + 1] : hEast;
+                    const int l = min(min(hc[k] - 1, hE), min(min(hW, hN[k]), hS[k]));
+                    lo = min(lo, l < 0 ? 0 : l >> 5);
+                    hi = max(hi, (hc[k] - 1) >> 5);
+                    ++solid;
                 }
-                v = __reduce_add_sync(0xffffffffu, v);
-                if (lane == 0) s_acc[warp][j - iy0] += v;
             }
-            if (lane == 0 && nsolid) {
-                if (wlo > 0 && iy0 == 0) s_acc[warp][0] += nsolid * (last == 0 ? 2 : 1);             // bottom faces (+ top if 1 layer)
-                if (last > 0 && last < wlo && last >= iy0 && last < iy0 + nl) s_acc[warp][last - iy0] += nsolid;  // top faces
+        }
+        const int wlo = __reduce_min_sync(0xffffffffu, lo);
+        const int whi = __reduce_max_sync(0xffffffffu, hi);
+        const int nsolid = __reduce_add_sync(0xffffffffu, solid);
+        const int j1 = min(min(whi, last), iy0 + nl - 1);
+        for (int j = max(wlo, iy0); j <= j1; ++j) {  // warp-uniform bounds
+            const int a = j * 32;
+            int rc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rc[k] = min(max(hc[k] - a, 0), 32);
+            // x direction: west of cell 0, the three inner pairs, east of cell 3
+            uint32_t v = max(0, rc[0] - min(max(hWest - a, 0), 32)) + abs(rc[0] - rc[1]) + abs(rc[1] - rc[2]) + abs(rc[2] - rc[3]) +
+                         max(0, rc[3] - min(max(hEast - a, 0), 32));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (rc[k] > 0) {
+                    v += max(0, rc[k] - min(max(hN[k] - a, 0), 32)) + max(0, rc[k] - min(max(hS[k] - a, 0), 32));
+                    v += (hc[k] - a <= 32 || j == last) ? 1u : 0u;  // up: real top, or the chunk above is absent
+                    v += (j == 0) ? 1u : 0u;                        // down: only where the chunk below is absent
+                }
             }
+            v = __reduce_add_sync(0xffffffffu, v);
+            if (lane == 0) s_acc[warp][j - iy0] = v;  // the only writer of this slot (zeroed above)
+        }
+        if (lane == 0 && nsolid) {
+            if (wlo > 0 && iy0 == 0) s_acc[warp][0] += nsolid * (last == 0 ? 2 : 1);             // bottom faces (+ top if 1 layer)
+            if (last > 0 && last < wlo && last >= iy0 && last < iy0 + nl) s_acc[warp][last - iy0] += nsolid;  // top faces
         }
         __syncthreads();
         if (tid < nl) {
