@@ -615,15 +615,10 @@ int hb_world_unload(hb_world* w, const hb_chunk_pt* pts, size_t n) {
     return HB_OK;
 }
 
-int hb_world_set_cubes(hb_world* w, const int32_t* xyz, const uint16_t* materials, size_t n) {
-    if (!w || (n && (!xyz || !materials))) return fail(HB_ERR_INVALID, "null argument");
-    if (n == 0) return HB_OK;
+namespace {
+// one sub-batch of hb_world_set_cubes (c->mu held, device current): group, upload, launch, wait
+int apply_edits(hb_world* w, const int32_t* xyz, const uint16_t* materials, size_t n, uint32_t* groups_out) {
     hb_ctx* c = w->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
-    HB_CUDA(cudaSetDevice(c->device));
-    for (size_t i = 0; i < n; ++i)
-        if (materials[i] > (uint32_t)c->mats.n_materials)
-            return fail(HB_ERR_INVALID, "edit %zu: material id %u above the palette size %d", i, materials[i], c->mats.n_materials);
     // ---- conflict groups: union-find over the edits, joined wherever two 7-voxel stencils share a voxel.  The stencil
     // voxels go into an open-addressing table (key = world voxel, value = the first edit that touched it).
     std::vector<uint32_t> parent(n);
@@ -701,8 +696,31 @@ int hb_world_set_cubes(hb_world* w, const int32_t* xyz, const uint16_t* material
     k_world_edit<<<(n_groups + kEditWarps - 1) / kEditWarps, 32 * kEditWarps, 0, c->stream>>>(
         w->d_cubes.as<hb_palette_cube>(), w->d_touched.as<uint32_t>(), w->d_a.as<EditRec>(), w->d_b.as<uint32_t>(), n_groups);
     HB_CUDA(cudaGetLastError());
-    w->last_edit_groups = n_groups;
+    *groups_out = n_groups;
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
+}
+}  // namespace
+
+int hb_world_set_cubes(hb_world* w, const int32_t* xyz, const uint16_t* materials, size_t n) {
+    if (!w || (n && (!xyz || !materials))) return fail(HB_ERR_INVALID, "null argument");
+    if (n == 0) return HB_OK;
+    hb_ctx* c = w->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    HB_CUDA(cudaSetDevice(c->device));
+    for (size_t i = 0; i < n; ++i)
+        if (materials[i] > (uint32_t)c->mats.n_materials)
+            return fail(HB_ERR_INVALID, "edit %zu: material id %u above the palette size %d", i, materials[i], c->mats.n_materials);
+    // sub-batches bound the host-side grouping tables (224 bytes per edit); they run one after the other, so the order
+    // between them is kept like the order inside a group
+    const size_t kSub = 65536;
+    w->last_edit_groups = 0;
+    for (size_t first = 0; first < n; first += kSub) {
+        uint32_t groups = 0;
+        const int rc = apply_edits(w, xyz + 3 * first, materials + first, std::min(kSub, n - first), &groups);
+        if (rc != HB_OK) return rc;
+        w->last_edit_groups += groups;
+    }
     return HB_OK;
 }
 

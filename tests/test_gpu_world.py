@@ -413,3 +413,28 @@ def test_world_edit_conflict_groups(ctx):
         check_cubes(world, ora)
     ora.close()
     ctx.set_world(0)
+
+
+def test_world_edit_batch_larger_than_a_sub_batch(ctx):
+    """70 000 edits in one call: the library groups and applies them in sub-batches of 65 536, one after the other;
+    the cubes equal the reference's sequential result."""
+    ctx.set_world(0)
+    w = O.world(0)
+    ora = O.ChunkMapOracle(w)
+    pts = [(cx, cy, cz) for cx in (0, 1) for cz in (0, 1) for cy in (-1, 0)]
+    rng = np.random.default_rng(9)
+    n = 70000
+    xyz = np.stack([rng.integers(-2, 66, n), rng.integers(-34, 34, n), rng.integers(-2, 66, n)], axis=1).astype(np.int32)
+    xyz[65000:] = xyz[:5000]  # the tail re-edits voxels of the first sub-batch: order across sub-batches matters
+    mats = rng.integers(0, 4, n).astype(np.uint16)
+    with hb.World(ctx, 16) as world:
+        world.load(pts)
+        for p in pts:
+            ora.load(p)
+        world.set_cubes(xyz, mats)
+        assert int(world._lib.hb_world_last_edit_groups(world._h)) > 1000
+        for p, m in zip(xyz.tolist(), mats.tolist()):
+            ora.set_cube(tuple(p), m)
+        check_cubes(world, ora)
+        check_remesh(world, ora, check_sync(world, ora))
+    ora.close()
