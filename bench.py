@@ -173,12 +173,16 @@ def measured_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
 
 
+KERNEL_SOURCES = ["common.cuh", "gen.cu", "mesh.cu", "noise.cuh"]  # what the region kernels are compiled from
+
+
 def src_sha256() -> str:
-    """sha256 over the CUDA sources + the header the library is built from (the .so itself is not reproducible bit
-    for bit across rebuilds, its sources are): the key that ties profiles/ncu_traffic.json to a build."""
+    """sha256 over the sources of the region kernels + the nvcc flags (the .so itself is not reproducible bit for bit
+    across rebuilds, its sources are; host-side files do not change a kernel): the key that ties
+    profiles/ncu_traffic.json to a build."""
     from herbolution_b200 import build as b
     h = hashlib.sha256()
-    for name in sorted(b.CUDA_DEPS):
+    for name in KERNEL_SOURCES:
         with open(os.path.join(b.CSRC, name), "rb") as f:
             h.update(name.encode() + b"\0" + f.read())
     h.update(" ".join(b.NVCC_FLAGS).encode())

@@ -811,10 +811,8 @@ int hb_world_remesh(hb_world* w, hb_chunk_pt* out_pts, size_t pts_capacity, hb_i
     HB_CUDA(cudaSetDevice(c->device));
     int rc = remesh_impl(w, out_pts, pts_capacity, out ? out_capacity : 0, true, out_offsets, out_counts, n_chunks, out_total, nullptr);
     if (rc != HB_OK) return rc;
-    if (*out_total) {
-        HB_CUDA(cudaMemcpyAsync(out, w->d_out.p, *out_total * sizeof(hb_instance3d), cudaMemcpyDeviceToHost, c->stream));
-        HB_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    // pinned destination: one DMA at link speed; pageable: streamed through the pinned bounce buffers
+    if (*out_total) return copy_to_host(c, c->stream, out, w->d_out.p, *out_total * sizeof(hb_instance3d));
     return HB_OK;
 }
 

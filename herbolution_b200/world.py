@@ -82,19 +82,34 @@ class World:
         return {"pts": pts[:k], "offsets": offsets[:k], "counts": counts[:k], "entries": entries[:ne.value]}
 
     def remesh(self) -> dict:
-        """{"pts", "offsets", "counts", "instances"} for every chunk that received a CubeUpdate since the last remesh."""
+        """{"pts", "offsets", "counts", "instances"} for every chunk that received a CubeUpdate since the last remesh.
+        The instances land in a pinned buffer the World keeps (grow-only), so the arrays are views that stay valid until
+        the next remesh(); with enough room the meshes are produced and copied in ONE pass (the two-call sizing pattern
+        of hb_world_remesh is only taken when the buffer has to grow)."""
+        cap = self.capacity
+        pts = np.zeros(cap, dtype=CHUNK_PT_DTYPE)
+        offsets = np.zeros(cap, dtype=np.uint64)
+        counts = np.zeros(cap, dtype=np.uint32)
+        buf = getattr(self, "_pinned_inst", None)
+        if buf is None:
+            self._pinned_inst = buf = self.ctx.pinned_empty(1 << 18, INSTANCE_DTYPE)  # 26 MB to start with
         n, total = C.c_size_t(0), C.c_uint64(0)
-        rc = self._lib.hb_world_remesh(self._h, None, 0, None, 0, None, None, C.byref(n), C.byref(total))
-        if rc not in (_lib.HB_OK, _lib.HB_ERR_CAPACITY):
-            check(rc)
-        pts = np.zeros(n.value, dtype=CHUNK_PT_DTYPE)
-        offsets = np.zeros(n.value, dtype=np.uint64)
-        counts = np.zeros(n.value, dtype=np.uint32)
-        inst = np.zeros(total.value, dtype=INSTANCE_DTYPE)
+        rc = self._lib.hb_world_remesh(self._h, ptr(pts), cap, ptr(buf), buf.shape[0], ptr(offsets), ptr(counts),
+                                       C.byref(n), C.byref(total))
         if rc == _lib.HB_ERR_CAPACITY:
-            check(self._lib.hb_world_remesh(self._h, ptr(pts), n.value, ptr(inst), total.value, ptr(offsets), ptr(counts),
-                                            C.byref(n), C.byref(total)))
-        return {"pts": pts, "offsets": offsets, "counts": counts, "instances": inst}
+            self._pinned_inst = buf = self.ctx.pinned_empty(int(total.value) + int(total.value) // 2 + 4, INSTANCE_DTYPE)
+            rc = self._lib.hb_world_remesh(self._h, ptr(pts), cap, ptr(buf), buf.shape[0], ptr(offsets), ptr(counts),
+                                           C.byref(n), C.byref(total))
+        check(rc)
+        k = n.value
+        return {"pts": pts[:k], "offsets": offsets[:k], "counts": counts[:k], "instances": buf[:total.value]}
+
+    def reserve_remesh(self, quads: int) -> None:
+        """Size the pinned instance buffer of remesh() up front (pinning memory costs milliseconds per MB; a host sizes
+        it once at start-up instead of on the first large remesh)."""
+        buf = getattr(self, "_pinned_inst", None)
+        if buf is None or buf.shape[0] < quads:
+            self._pinned_inst = self.ctx.pinned_empty(int(quads) + 4, INSTANCE_DTYPE)
 
     def remesh_dev(self) -> dict:
         """Like remesh() but the instances stay in HBM: adds "d_instances" (raw device pointer) and "span"."""

@@ -23,8 +23,9 @@ def main():
     files = [a for a in args if a.endswith(".csv")]
     sys.path.insert(0, ROOT)
     from herbolution_b200 import build as b
+    from bench import KERNEL_SOURCES
     hh = hashlib.sha256()
-    for name in sorted(b.CUDA_DEPS):
+    for name in KERNEL_SOURCES:
         hh.update(name.encode() + b"\0" + open(os.path.join(b.CSRC, name), "rb").read())
     hh.update(" ".join(b.NVCC_FLAGS).encode())
     sha = hh.hexdigest()
