@@ -281,7 +281,7 @@ void hb_destroy(hb_ctx* c) {
     Buf* bufs[] = {&c->d_pts, &c->d_cols, &c->d_colidx, &c->d_heights, &c->d_noise, &c->d_ids, &c->d_cubes, &c->d_nbr,
                    &c->d_bitmaps, &c->d_summary, &c->d_counts, &c->d_offsets, &c->d_scan, &c->d_total, &c->d_out,
                    &c->h_total, &c->h_inst[0], &c->h_inst[1], &c->h_off[0], &c->h_off[1], &c->h_cnt[0], &c->h_cnt[1],
-                   &c->h_ids[0], &c->h_ids[1], &c->h_bounce[0], &c->h_bounce[1], &c->h_packed[0], &c->h_packed[1]};
+                   &c->h_ids[0], &c->h_ids[1], &c->h_heights[0], &c->h_heights[1], &c->h_bounce[0], &c->h_bounce[1], &c->h_packed[0], &c->h_packed[1]};
     for (Buf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         if (c->stream_plan[i]) hb_region_plan_destroy(c->stream_plan[i]);
@@ -291,6 +291,7 @@ void hb_destroy(hb_ctx* c) {
     }
     c->pool.resize(0);
     free(c->h_expanded);
+    free(c->h_ids_plain);
     if (c->d_mats) cudaFree(c->d_mats);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy) cudaStreamDestroy(c->copy);
@@ -750,19 +751,20 @@ enum StreamMode { kRawInstances = 0, kPackedExpand = 1, kPackedSink = 2 };
 
 // plain host memory for the expanded slab: grow-only, 2 MiB aligned and huge-page advised so that the expander's
 // stores do not pay a TLB miss every 4 KiB; the pages are touched once (first call of a given shape)
-int reserve_expanded(hb_ctx* c, size_t bytes) {
-    if (bytes <= c->h_expanded_cap) return HB_OK;
-    free(c->h_expanded);
-    c->h_expanded = nullptr;
-    c->h_expanded_cap = 0;
+int reserve_plain(void** buf, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return HB_OK;
+    free(*buf);
+    *buf = nullptr;
+    *cap = 0;
     const size_t want = ((bytes + bytes / 8) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
     void* p = aligned_alloc((size_t)2 << 20, want);
-    if (!p) return fail(HB_ERR_NOMEM, "out of host memory for the expanded slab (%zu bytes)", want);
+    if (!p) return fail(HB_ERR_NOMEM, "out of host memory for a slab buffer (%zu bytes)", want);
     madvise(p, want, MADV_HUGEPAGE);
-    c->h_expanded = p;
-    c->h_expanded_cap = want;
+    *buf = p;
+    *cap = want;
     return HB_OK;
 }
+int reserve_expanded(hb_ctx* c, size_t bytes) { return reserve_plain(&c->h_expanded, &c->h_expanded_cap, bytes); }
 
 void ensure_expander(hb_ctx* c) {
     if (!c->xt_valid) {
@@ -800,7 +802,11 @@ int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t 
     std::lock_guard<std::mutex> lk(c->mu);
     HB_CUDA(cudaSetDevice(c->device));
     const bool packed = mode != kRawInstances;
-    if (mode == kPackedExpand) ensure_expander(c);
+    // packed transports: the block ids are rebuilt on the host from the slab's heights tiles (fill_chunk_ids), so only
+    // 4 KiB per chunk COLUMN cross the link instead of 64 KiB per chunk, and the device skips the FILL stage
+    const bool host_ids = want_ids && packed;
+    const int dev_ids = want_ids && !packed;
+    if (mode == kPackedExpand || host_ids) ensure_expander(c);
     // slab width: aim at ~384 MiB of instances per slab (about 300 KB per column on this terrain),
     // bounded so that the optional id image (64 KiB/chunk) stays below ~1 GiB per slab.
     // Packed sink: only 4 B/quad leave the device, so the same budget is counted in packed bytes (8x wider slabs):
@@ -830,7 +836,7 @@ int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t 
         }
         plan[b] = c->stream_plan[b];
         plan[b]->region = *region;
-        plan[b]->want_ids = want_ids;
+        plan[b]->want_ids = dev_ids;
         plan_target(plan[b], ix_begin, ix_begin + width);
         rc = plan_alloc(plan[b], width);
         if (rc != HB_OK) return rc;
@@ -846,7 +852,18 @@ int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t 
         HB_CUDA(cudaEventSynchronize(ev_copied[b]));
         const uint64_t* off = c->h_off[b].as<uint64_t>();
         const uint32_t* cnt = c->h_cnt[b].as<uint32_t>();
-        const uint16_t* ids = want_ids ? c->h_ids[b].as<uint16_t>() : nullptr;
+        const uint16_t* ids = dev_ids ? c->h_ids[b].as<uint16_t>() : nullptr;
+        if (host_ids && (sink || psink)) {
+            const int rc2 = reserve_plain(&c->h_ids_plain, &c->h_ids_plain_cap, pend[b].n * HB_CHUNK_VOLUME * sizeof(uint16_t));
+            if (rc2 != HB_OK) return rc2;
+            uint16_t* out_ids = static_cast<uint16_t*>(c->h_ids_plain);
+            const int32_t* hts = c->h_heights[b].as<int32_t>();
+            const int32_t ncy = region->ncy, cy0 = region->cy0;
+            c->pool.run(pend[b].n, 4, [&](size_t i) {  // slab-relative chunk i = column i / ncy, layer i % ncy
+                fill_chunk_ids(hts + (i / ncy) * HB_CHUNK_AREA, cy0 + (int32_t)(i % ncy), out_ids + i * HB_CHUNK_VOLUME);
+            });
+            ids = out_ids;
+        }
         if (mode == kPackedSink) {
             if (psink) psink(user, pend[b].first, pend[b].n, off, cnt, c->h_packed[b].as<hb_packed_quad>(), pend[b].span, ids);
         } else if (mode == kPackedExpand) {
@@ -884,9 +901,11 @@ int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t 
         }
         if (e == cudaSuccess) e = c->h_off[b].reserve(nch * sizeof(uint64_t));
         if (e == cudaSuccess) e = c->h_cnt[b].reserve(nch * sizeof(uint32_t));
-        if (e == cudaSuccess && want_ids) e = c->h_ids[b].reserve(nch * HB_CHUNK_VOLUME * sizeof(uint16_t));
+        if (e == cudaSuccess && dev_ids) e = c->h_ids[b].reserve(nch * HB_CHUNK_VOLUME * sizeof(uint16_t));
+        const size_t slab_cols = (size_t)(p->dev.ix_end - p->dev.ix_begin) * region->ncz;
+        if (e == cudaSuccess && host_ids) e = c->h_heights[b].reserve(slab_cols * HB_CHUNK_AREA * sizeof(int32_t));
         if (e != cudaSuccess) { rc = fail(HB_ERR_CUDA, "slab buffer allocation failed: %s", cudaGetErrorString(e)); break; }
-        rc = plan_enqueue(p, (packed ? HB_STAGE_EMIT_PACKED : HB_STAGE_EMIT) | (want_ids ? HB_STAGE_FILL : 0), c->stream);
+        rc = plan_enqueue(p, (packed ? HB_STAGE_EMIT_PACKED : HB_STAGE_EMIT) | (dev_ids ? HB_STAGE_FILL : 0), c->stream);
         if (rc != HB_OK) break;
         cudaEventRecord(ev_kernels[b], c->stream);
         cudaStreamWaitEvent(c->copy, ev_kernels[b], 0);
@@ -898,8 +917,12 @@ int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t 
             else
                 cudaMemcpyAsync(c->h_inst[b].p, p->d_out.p, tot[0] * sizeof(hb_instance3d), cudaMemcpyDeviceToHost, c->copy);
         }
-        if (want_ids)
+        if (dev_ids)
             cudaMemcpyAsync(c->h_ids[b].p, p->d_ids.p, nch * HB_CHUNK_VOLUME * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->copy);
+        if (host_ids)  // the slab's own columns inside the heights buffer (which also holds the one-column apron)
+            cudaMemcpyAsync(c->h_heights[b].p,
+                            p->d_heights.as<int32_t>() + (size_t)(p->dev.ix_begin - p->dev.hx_begin) * region->ncz * HB_CHUNK_AREA,
+                            slab_cols * HB_CHUNK_AREA * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy);
         cudaError_t ce = cudaEventRecord(ev_copied[b], c->copy);
         if (ce != cudaSuccess) { rc = fail(HB_ERR_CUDA, "slab copy failed: %s", cudaGetErrorString(ce)); break; }
         pend[b] = Pending{true, (uint64_t)ix0 * region->ncz * region->ncy, nch, tot[0]};

@@ -99,6 +99,38 @@ void expand_chunk(const ExpandTables& T, hb_chunk_pt pt, const uint32_t* __restr
     _mm_sfence();  // non-temporal stores are weakly ordered: make them visible before the job is reported done
 }
 
+// Host half of the block-id transport (want_ids): the generator's block ids are a function of the column's heights
+// alone (GenerationParams::generate, server/src/generator/mod.rs:85-91: with d = h - y, stone for d > 6, dirt for d > 1,
+// grass for d > 0, else air), and a chunk column shares one 4 KiB heights tile between all its layers.  So the heights
+// cross the link (4 KiB per column instead of 64 KiB per chunk) and the ids are written here, one 64-byte voxel column
+// per table row: row d = clamp(h - 32*cy, 0, 38) holds the 32 ids of a column whose surface is d voxels above the chunk's
+// floor (d >= 38: all stone).  Same ids as k_fill writes on the device (tests compare both transports).
+void fill_chunk_ids(const int32_t* __restrict__ heights, int32_t cy, uint16_t* __restrict__ out) {
+    struct Lut {
+        alignas(64) uint16_t row[39][32];
+        Lut() {
+            for (int d = 0; d < 39; ++d)
+                for (int y = 0; y < 32; ++y) {
+                    const int k = d - y;
+                    row[d][y] = (uint16_t)(k > 6 ? 1 : (k > 1 ? 2 : (k > 0 ? 3 : 0)));
+                }
+        }
+    };
+    static const Lut lut;
+    const long long wy0 = (long long)cy * 32;
+    for (int c = 0; c < HB_CHUNK_AREA; ++c) {
+        const long long dl = (long long)heights[c] - wy0;
+        const int d = (int)(dl < 0 ? 0 : (dl > 38 ? 38 : dl));
+        const __m128i* src = reinterpret_cast<const __m128i*>(lut.row[d]);
+        __m128i* dst = reinterpret_cast<__m128i*>(out + c * 32);
+        _mm_stream_si128(dst, _mm_load_si128(src));
+        _mm_stream_si128(dst + 1, _mm_load_si128(src + 1));
+        _mm_stream_si128(dst + 2, _mm_load_si128(src + 2));
+        _mm_stream_si128(dst + 3, _mm_load_si128(src + 3));
+    }
+    _mm_sfence();
+}
+
 // ---- a small persistent worker pool: run(n_items, fn) calls fn(item) for every item on all workers + the caller ----
 struct HostPool::Impl {
     std::vector<std::thread> workers;

@@ -80,6 +80,8 @@ struct ExpandTables {
 };
 uint64_t chunk_color_seed(int32_t x, int32_t y, int32_t z);
 void expand_chunk(const ExpandTables& T, hb_chunk_pt pt, const uint32_t* packed, uint32_t n, hb_instance3d* out);
+// heights tile of the chunk's column (int32[1024], index x*32 + z) -> the chunk's 32 768 block ids (out 16-byte aligned)
+void fill_chunk_ids(const int32_t* heights, int32_t cy, uint16_t* out);
 
 // Persistent host worker pool (the caller participates): run() returns when fn(i) ran for every i in [0, n_items).
 class HostPool {
@@ -120,6 +122,9 @@ struct hb_ctx {
     int transport = 0;              // HB_TRANSPORT_*
     void* h_expanded = nullptr;     // plain (pageable, huge-page advised) host memory: the sink's Instance3d view
     size_t h_expanded_cap = 0;
+    void* h_ids_plain = nullptr;    // same kind of memory for the block ids rebuilt from heights (want_ids, packed transports)
+    size_t h_ids_plain_cap = 0;
+    hb::Buf h_heights[2];           // pinned landing buffers of the slab's heights tiles
     hb::Buf h_packed[2];            // pinned landing buffers of the packed words
     hb::Buf h_bounce[2];            // pinned bounce buffers of copy_to_host (pageable destinations)
     cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
@@ -132,6 +137,7 @@ struct hb_ctx {
         h_total.pinned = true;
         h_bounce[0].pinned = h_bounce[1].pinned = true;
         h_packed[0].pinned = h_packed[1].pinned = true;
+        h_heights[0].pinned = h_heights[1].pinned = true;
         for (int i = 0; i < 2; ++i) h_inst[i].pinned = h_off[i].pinned = h_cnt[i].pinned = h_ids[i].pinned = true;
     }
 };

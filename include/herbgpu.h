@@ -200,7 +200,11 @@ HB_API int hb_generate_mesh_region(hb_ctx *ctx, const hb_region *region, int wan
  *     library's host threads (hb_set_host_threads; default min(hardware threads, 32) or $HB_HOST_THREADS) rebuild the
  *     100-byte records with non-temporal stores into a library-owned host buffer -- 25x less link traffic;
  *   HB_TRANSPORT_INSTANCES: the device writes the 100-byte records and they are copied as they are (pinned buffers).
- * The sink sees byte-identical data either way. */
+ * The sink sees byte-identical data either way.
+ * want_ids follows the transport: with the packed one the slab's heights tiles cross the link (4 KiB per chunk COLUMN)
+ * and the host threads write the u16 block ids from them -- the generator's ids are a function of the column's heights
+ * alone (server/src/generator/mod.rs:85-91) --; with HB_TRANSPORT_INSTANCES the device's FILL stage writes them and
+ * 64 KiB per chunk are copied.  Same ids either way (hb_generate_mesh_region_packed always rebuilds them on the host). */
 #define HB_TRANSPORT_PACKED 0
 #define HB_TRANSPORT_INSTANCES 1
 HB_API int hb_set_region_transport(hb_ctx *ctx, int32_t transport);

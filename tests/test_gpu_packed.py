@@ -167,3 +167,40 @@ def test_multi_context_python_one_process():
     tot1 = c.generate_mesh_region(reg, sink=sink1)
     c.close()
     assert tot == tot1 and got == want and len(got) == 11 * 5 * 4
+
+
+@pytest.mark.parametrize("seed,reg,kind", [(0, (-20, -6, 40, 12, -3, 6), 0), (5, (3, 3, 2, 2, -40, 80), 0), (5, (100, -100, 3, 3, 2, 3), 1),
+                                           (0, (262140, -262143, 3, 2, -2, 4), 0)])
+def test_block_ids_rebuilt_on_the_host_equal_the_device_fill(ctx, transports, seed, reg, kind):
+    """want_ids with the packed transports: the heights tiles cross the link (4 KiB per column) and the host threads
+    write the ids (csrc/expand.cu: fill_chunk_ids); with the instance transport k_fill writes them on the device and
+    they are copied (64 KiB per chunk).  Same bytes, and the oracle's generate() agrees -- several slabs, 80 layers,
+    another noise kind, the coordinate limit."""
+    try:
+        ctx.set_world(seed)
+        ctx.set_noise_kind(kind)
+        region = hb.Region(*reg)
+        ctx.set_region_transport(hb.TRANSPORT_INSTANCES)
+        _, dev, _ = collect(ctx, region, want_ids=True)
+        ctx.set_region_transport(hb.TRANSPORT_PACKED)
+        _, host, _ = collect(ctx, region, want_ids=True)
+        got = {}
+
+        def psink(first, off, cnt, packed, ids):
+            for k in range(len(cnt)):
+                got[first + k] = ids[k].copy()
+
+        ctx.generate_mesh_region_packed(region, want_ids=True, sink=psink)
+        assert len(dev) == len(host) == len(got) == region.n_chunks
+        for i in range(region.n_chunks):
+            assert (host[i][1] == dev[i][1]).all(), f"chunk {i}: host-rebuilt ids differ from the device fill"
+            assert (got[i] == dev[i][1]).all(), f"chunk {i}: packed sink ids differ"
+        pts = region.chunk_points()
+        step = max(1, region.n_chunks // 40)
+        w = O.world(seed, kind=kind)
+        sel = list(range(0, region.n_chunks, step))
+        ref = O.generate_ids(w, [(int(pts["x"][i]), int(pts["y"][i]), int(pts["z"][i])) for i in sel])
+        for k, i in enumerate(sel):
+            assert (host[i][1] == ref[k]).all(), f"chunk {i} vs oracle"
+    finally:
+        ctx.set_noise_kind(0)
