@@ -434,6 +434,27 @@ def main():
                "host_frac": hw_gbs / probes["host_write_peak_gbs_sum"],
                "bound": "host memory writes (100 B per quad into the sink's buffer)",
                "note": "input is the 24-byte region descriptor; the sink receives every Instance3d (100 B/quad) + offsets/counts"}
+        # like for like with the reference's generate() + generate_mesh(): the u16 block arrays (64 KiB per chunk) are
+        # delivered to the host sink as well (heights tiles over the link, ids written by the host threads)
+        ids_stats = {"chunks": 0, "bytes": 0}
+
+        def ids_sink(first, off, cnt, inst, ids):
+            ids_stats["chunks"] += len(cnt)
+            ids_stats["bytes"] += ids.nbytes + len(inst) * 100
+
+        ctx.generate_mesh_region(reg, want_ids=True, sink=ids_sink)
+        ids_stats.update(chunks=0, bytes=0)
+        barrier()
+        t0 = time.perf_counter()
+        ctx.generate_mesh_region(reg, want_ids=True, sink=ids_sink)
+        torch.cuda.synchronize()
+        t_ids = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        ids_gbs = sum_over_ranks(float(ids_stats["bytes"])) / t_ids / 1e9
+        e2e["with_block_ids"] = {"value": total_chunks / t_ids, "unit": UNIT, "ms_per_step": 1e3 * t_ids,
+                                 "host_bytes_delivered_per_step": int(ids_stats["bytes"]), "host_write_gbs": ids_gbs,
+                                 "host_frac": ids_gbs / probes["host_write_peak_gbs_sum"],
+                                 "note": "same call with want_ids: every chunk's 32 768 u16 block ids reach the sink too"}
         # the round-1 path beside it: the device writes the 100-byte records and they cross the link as they are
         t_raw, span_r, chunks_r = run_e2e(hb.TRANSPORT_INSTANCES)
         raw_gbs = (span_r * 100 + chunks_r * 12) / (t_raw / e2e_steps) / 1e9
