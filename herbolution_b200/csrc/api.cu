@@ -230,6 +230,8 @@ int plan_enqueue(hb_region_plan* p, int stages, cudaStream_t s) {
     return HB_OK;
 }
 
+void ensure_expander(hb_ctx* c);  // defined with the region streamer below
+
 int plan_totals(hb_region_plan* p, cudaStream_t s, uint64_t tot[4]) {
     HB_CUDA(cudaMemcpyAsync(p->h_total.p, p->d_total.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     HB_CUDA(cudaStreamSynchronize(s));
@@ -421,6 +423,12 @@ int hb_generate(hb_ctx* c, const hb_chunk_pt* pts, size_t n, uint16_t* out_ids, 
     std::lock_guard<std::mutex> lk(c->mu);
     HB_CUDA(cudaSetDevice(c->device));
     const size_t batch = out_cubes ? 2048 : 8192;
+    // Block ids follow the region transport (hb_set_region_transport): with the packed one (default) the heights tiles
+    // come back (4 KiB per distinct column) and the host threads write the ids straight into the caller's array
+    // (fill_chunk_ids: the ids are a function of the column's heights); with HB_TRANSPORT_INSTANCES k_fill writes them
+    // on the device and 64 KiB per chunk are copied.
+    const bool host_ids = out_ids && c->transport == HB_TRANSPORT_PACKED && ((uintptr_t)out_ids & 15u) == 0;
+    if (host_ids) ensure_expander(c);
     std::vector<int32_t> cols, colidx;
     std::unordered_map<KeyXZ, int32_t, KeyXZHash> map;
     for (size_t b0 = 0; b0 < n; b0 += batch) {
@@ -442,23 +450,34 @@ int hb_generate(hb_ctx* c, const hb_chunk_pt* pts, size_t n, uint16_t* out_ids, 
         HB_CUDA(c->d_pts.reserve(nb * sizeof(hb_chunk_pt)));
         HB_CUDA(c->d_heights.reserve(ncol * HB_CHUNK_AREA * sizeof(int32_t)));
         if (out_noise) HB_CUDA(c->d_noise.reserve(ncol * HB_CHUNK_AREA * sizeof(float)));
-        if (out_ids) HB_CUDA(c->d_ids.reserve(nb * HB_CHUNK_VOLUME * sizeof(uint16_t)));
+        if (out_ids && !host_ids) HB_CUDA(c->d_ids.reserve(nb * HB_CHUNK_VOLUME * sizeof(uint16_t)));
+        if (host_ids) HB_CUDA(c->h_heights[0].reserve(ncol * HB_CHUNK_AREA * sizeof(int32_t)));
         if (out_cubes) HB_CUDA(c->d_cubes.reserve(nb * HB_CHUNK_VOLUME * sizeof(hb_palette_cube)));
         HB_CUDA(cudaMemcpyAsync(c->d_cols.p, cols.data(), ncol * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         HB_CUDA(cudaMemcpyAsync(c->d_colidx.p, colidx.data(), nb * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         HB_CUDA(cudaMemcpyAsync(c->d_pts.p, pts + b0, nb * sizeof(hb_chunk_pt), cudaMemcpyHostToDevice, c->stream));
         int rc = hb_dev_generate(c, c->stream, c->d_cols.as<int32_t>(), ncol, c->d_pts.as<hb_chunk_pt>(),
                                  c->d_colidx.as<int32_t>(), nb, c->d_heights.as<int32_t>(),
-                                 out_noise ? c->d_noise.as<float>() : nullptr, out_ids ? c->d_ids.as<uint16_t>() : nullptr,
+                                 out_noise ? c->d_noise.as<float>() : nullptr,
+                                 out_ids && !host_ids ? c->d_ids.as<uint16_t>() : nullptr,
                                  out_cubes ? c->d_cubes.as<hb_palette_cube>() : nullptr);
         if (rc != HB_OK) return rc;
-        if (out_ids)
+        if (host_ids)
+            HB_CUDA(cudaMemcpyAsync(c->h_heights[0].p, c->d_heights.p, ncol * HB_CHUNK_AREA * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                    c->stream));
+        else if (out_ids)
             HB_CUDA(cudaMemcpyAsync(out_ids + b0 * HB_CHUNK_VOLUME, c->d_ids.p, nb * HB_CHUNK_VOLUME * sizeof(uint16_t),
                                     cudaMemcpyDeviceToHost, c->stream));
         if (out_cubes)
             HB_CUDA(cudaMemcpyAsync(out_cubes + b0 * HB_CHUNK_VOLUME, c->d_cubes.p,
                                     nb * HB_CHUNK_VOLUME * sizeof(hb_palette_cube), cudaMemcpyDeviceToHost, c->stream));
         HB_CUDA(cudaStreamSynchronize(c->stream));
+        if (host_ids) {
+            const int32_t* hts = c->h_heights[0].as<int32_t>();
+            c->pool.run(nb, 4, [&](size_t i) {
+                fill_chunk_ids(hts + (size_t)colidx[i] * HB_CHUNK_AREA, pts[b0 + i].y, out_ids + (b0 + i) * HB_CHUNK_VOLUME);
+            });
+        }
         if (out_noise) {
             // per-chunk tiles in the caller's order (a column's tile is repeated for each of its chunks)
             std::vector<float> tiles(ncol * HB_CHUNK_AREA);

@@ -204,3 +204,26 @@ def test_block_ids_rebuilt_on_the_host_equal_the_device_fill(ctx, transports, se
             assert (host[i][1] == ref[k]).all(), f"chunk {i} vs oracle"
     finally:
         ctx.set_noise_kind(0)
+
+
+def test_generate_ids_host_fill_equals_device_fill(ctx, transports):
+    """hb_generate's block ids follow the transport too: heights tiles + host fill (default) vs k_fill + 64 KiB copies;
+    duplicated points, several layers per column, an unaligned destination (falls back to the device fill)."""
+    ctx.set_world(5)
+    pts = hb.Region(-5, 7, 6, 5, -3, 6).chunk_points()
+    pts = np.concatenate([pts, pts[:7]])
+    ctx.set_region_transport(hb.TRANSPORT_INSTANCES)
+    dev = ctx.generate(pts)["ids"]
+    ctx.set_region_transport(hb.TRANSPORT_PACKED)
+    host = ctx.generate(pts)["ids"]
+    assert (dev == host).all()
+    ref = O.generate_ids(O.world(5), [(int(p["x"]), int(p["y"]), int(p["z"])) for p in pts[::9]])
+    assert (host[::9] == ref).all()
+    # unaligned output pointer through the raw ABI
+    import ctypes as C
+    raw = np.zeros(len(pts) * 32768 + 8, dtype=np.uint16)
+    view = raw[1:1 + len(pts) * 32768]
+    assert view.ctypes.data % 16 != 0
+    p2 = np.ascontiguousarray(pts)
+    rc = ctx._lib.hb_generate(ctx._h, C.c_void_p(p2.ctypes.data), len(pts), C.c_void_p(view.ctypes.data), None, None)
+    assert rc == 0 and (view.reshape(-1, 32768) == dev).all()
