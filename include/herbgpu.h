@@ -142,7 +142,8 @@ HB_API int hb_noise_fbm3d(hb_ctx *ctx, float sx, float sy, float sz, int32_t nx,
  * (server/src/generator/mod.rs:32-48,63-95) for a batch of n chunks.
  * out_ids: n x 32768 u16.  out_cubes (nullable): n x 32768 hb_palette_cube = CubeMesh::data right
  * after generate() (in-chunk face flags as CubeMesh::set leaves them, server/src/chunk/mesh.rs:125-232;
- * cross-chunk culling not yet applied).  out_noise (nullable): n x 1024 f32 as hb_noise_tiles. * out_ids follow the region transport (hb_set_region_transport): with the packed one (default) the heights tiles come
+ * cross-chunk culling not yet applied).  out_noise (nullable): n x 1024 f32 as hb_noise_tiles.
+ * out_ids follow the region transport (hb_set_region_transport): with the packed one (default) the heights tiles come
  * back and the host threads write the ids into out_ids (which should then be 16-byte aligned; otherwise, and with
  * HB_TRANSPORT_INSTANCES, the device writes them and 64 KiB per chunk are copied).  Same ids either way. */
 HB_API int hb_generate(hb_ctx *ctx, const hb_chunk_pt *pts, size_t n, uint16_t *out_ids,
