@@ -130,6 +130,8 @@ PROTOTYPES = {
     "hb_multi_generate_mesh_region": (C.c_int, [C.c_void_p, C.POINTER(Region), C.c_int, REGION_SINK, C.c_void_p,
                                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_encode_palette": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "hb_host_expand_quads": (C.c_int, [ChunkPtC, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_host_fill_ids": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "hb_probe_d2h": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
     "hb_probe_host_write": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
     "hb_region_plan_packed": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

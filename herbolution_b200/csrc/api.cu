@@ -1066,6 +1066,41 @@ int hb_probe_host_write(hb_ctx* c, size_t bytes, int32_t reps, double* gbs) {
     return HB_OK;
 }
 
+// ---- the host half of the packed transports without a context (no CUDA call is made: usable, and tested, on a
+// machine without a GPU) ----
+int hb_host_expand_quads(hb_chunk_pt pt, const hb_packed_quad* quads, uint32_t n, int32_t n_materials, const int32_t* n_colors,
+                         const float* rgba, hb_instance3d* out) {
+    if (n && (!quads || !out)) return fail(HB_ERR_INVALID, "null argument");
+    if ((uintptr_t)out & 15u) return fail(HB_ERR_INVALID, "out must be 16-byte aligned");
+    MaterialsDev m;
+    if (!n_colors || !rgba) {
+        default_materials(&m);
+    } else {
+        if (n_materials < 1 || n_materials > HB_MAX_MATERIALS) return fail(HB_ERR_INVALID, "n_materials must be in 1..%d", HB_MAX_MATERIALS);
+        memset(&m, 0, sizeof(m));
+        m.n_materials = n_materials;
+        for (int i = 0; i < n_materials; ++i) {
+            if (n_colors[i] < 1 || n_colors[i] > HB_MAX_COLORS) return fail(HB_ERR_INVALID, "material %d: n_colors must be in 1..%d", i + 1, HB_MAX_COLORS);
+            m.n_colors[i] = n_colors[i];
+            memcpy(m.rgba[i], rgba + (size_t)i * HB_MAX_COLORS * 4, sizeof(float) * HB_MAX_COLORS * 4);
+        }
+    }
+    MeshTables tb;
+    for (int f = 0; f < 6; ++f) face_matrix(f, tb.face_mat[f]);
+    for (int k = 0; k < 4; ++k) tb.ao_lut[k] = ao_value(k);
+    ExpandTables T;
+    T.build(tb, m);
+    expand_chunk(T, pt, quads, n, out);
+    return HB_OK;
+}
+
+int hb_host_fill_ids(const int32_t* heights, int32_t cy, uint16_t* out_ids) {
+    if (!heights || !out_ids) return fail(HB_ERR_INVALID, "null argument");
+    if ((uintptr_t)out_ids & 15u) return fail(HB_ERR_INVALID, "out_ids must be 16-byte aligned");
+    fill_chunk_ids(heights, cy, out_ids);
+    return HB_OK;
+}
+
 int hb_encode_palette(hb_ctx* c, const hb_material_desc* descs, uint8_t* out, size_t capacity, size_t* n_bytes) {
     if (!c || !n_bytes) return fail(HB_ERR_INVALID, "null argument");
     *n_bytes = 0;

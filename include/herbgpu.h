@@ -267,6 +267,17 @@ HB_API int hb_multi_generate_mesh_region(hb_multi *multi, const hb_region *regio
                                          hb_region_sink sink, void *user,
                                          uint64_t *total_chunks, uint64_t *total_quads);
 
+/* The host half of the packed transports without a context: no CUDA call is made, so a consumer on another machine
+ * (or a test on a machine without a GPU) can rebuild the records and the block ids.
+ * hb_host_expand_quads = hb_expand_quads with the palette passed in (n_colors / rgba as for hb_set_materials; NULL = the
+ * game's stone, dirt, grass); the tables are rebuilt per call, so pass whole chunks.
+ * hb_host_fill_ids: the 32 768 block ids of the chunk at layer cy of a column from the column's heights tile
+ * (int32[1024], index x*32 + z, as hb_noise_tiles returns it): GenerationParams::generate's threshold rule
+ * (server/src/generator/mod.rs:85-91).  Both outputs 16-byte aligned. */
+HB_API int hb_host_expand_quads(hb_chunk_pt pt, const hb_packed_quad *quads, uint32_t n, int32_t n_materials,
+                                const int32_t *n_colors, const float *rgba, hb_instance3d *out);
+HB_API int hb_host_fill_ids(const int32_t *heights, int32_t cy, uint16_t *out_ids);
+
 /* Measurement helpers: the two ceilings of the end-to-end path, measured with the ctx's own buffers and threads so
  * that several ctxs (GPUs) can be probed at the same moment.  hb_probe_d2h: plain cudaMemcpyAsync device -> pinned
  * host of `bytes`, `reps` times back to back (GB/s by CUDA events).  hb_probe_host_write: the expander's worker pool

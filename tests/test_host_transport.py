@@ -1,0 +1,92 @@
+"""The host half of the packed transports, on the CPU (no GPU, no context): hb_host_fill_ids and hb_host_expand_quads are
+product code (csrc/expand.cu) that rebuilds block ids from heights tiles and Instance3d records from 4-byte quads.
+Checked against the oracle: ids vs generate(), records vs generate_mesh() byte for byte."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle as O
+from herbolution_b200 import _lib
+
+STONE = [(0.5, 0.5, 0.5, 1.0), (0.6, 0.6, 0.6, 1.0), (0.7, 0.7, 0.7, 1.0)]
+
+
+def aligned(n, dtype):
+    raw = np.zeros(n * np.dtype(dtype).itemsize + 64, dtype=np.uint8)
+    o = (-raw.ctypes.data) & 63
+    return raw[o:o + n * np.dtype(dtype).itemsize].view(dtype)
+
+
+@pytest.mark.parametrize("seed", [0, 5])
+def test_host_fill_ids_equals_generate(seed):
+    L = _lib.load()
+    w = O.world(seed)
+    for (cx, cz) in [(0, 0), (-3, 7), (100, -100)]:
+        noise = O.noise_tile2(w, cx, cz)                       # index x + z*32
+        h = O.heights_from_noise(noise).reshape(32, 32).T       # -> [x][z]
+        heights = np.ascontiguousarray(h, dtype=np.int32).reshape(-1)
+        top = int(heights.max()) // 32
+        for cy in (top - 2, top - 1, top, top + 1, -40, 40):
+            out = aligned(32768, np.uint16)
+            assert L.hb_host_fill_ids(C.c_void_p(heights.ctypes.data), cy, C.c_void_p(out.ctypes.data)) == 0
+            ref = O.generate_ids(w, [(cx, cy, cz)])[0]
+            assert (out == ref).all(), (seed, cx, cy, cz)
+    # extreme heights do not overflow the layer arithmetic
+    heights = np.full(1024, 2**31 - 1, dtype=np.int32)
+    out = aligned(32768, np.uint16)
+    assert L.hb_host_fill_ids(C.c_void_p(heights.ctypes.data), -67108864, C.c_void_p(out.ctypes.data)) == 0 and (out == 1).all()
+    heights[:] = -2**31
+    assert L.hb_host_fill_ids(C.c_void_p(heights.ctypes.data), 67108863, C.c_void_p(out.ctypes.data)) == 0 and (out == 0).all()
+    assert L.hb_host_fill_ids(None, 0, C.c_void_p(out.ctypes.data)) == _lib.HB_ERR_INVALID
+
+
+def pack_from_instances(inst, ids, pos):
+    """Derive the 4-byte quads (L | face << 15 | ao << 18 | (material - 1) << 26) from an Instance3d stream."""
+    mats = np.zeros((6, 12), dtype=np.float32)
+    for f in range(6):
+        O.lib().hbo_face_matrix(f, mats[f].ctypes.data)
+    ao_vals = [np.float32(O.lib().hbo_ao_value(k)) for k in range(4)]
+    out = np.zeros(len(inst), dtype=np.uint32)
+    for q, rec in enumerate(inst):
+        model = rec["model"]
+        face = next(f for f in range(6) if model[:12].tobytes() == mats[f].tobytes())
+        x, y, z = (int(model[12 + k]) - 32 * int(pos[k]) for k in range(3))
+        L = x * 1024 + z * 32 + y
+        ao = 0
+        for v in range(4):
+            ao |= ao_vals.index(np.float32(rec["ao"][v])) << (2 * v)
+        out[q] = L | (face << 15) | (ao << 18) | ((int(ids[L]) - 1) << 26)
+    return out
+
+
+@pytest.mark.parametrize("palette", [None, [STONE, [(0.25, 0.5, 0.75, 1.0)], [(0.1 * k, 0.2, 0.3, 1.0) for k in range(8)]]])
+def test_host_expand_quads_equals_generate_mesh(palette):
+    L = _lib.load()
+    rng = np.random.default_rng(4)
+    pos = (5, -2, -7)
+    shell = []
+    for i in range(27):
+        a = np.zeros(32768, dtype=np.uint16)
+        sel = rng.choice(32768, size=900 if i == 13 else 6000, replace=False)
+        a[sel] = rng.integers(1, 4, size=len(sel))
+        shell.append(None if i in (1, 25) else a)
+    pal = O.make_palette(palette) if palette else None
+    want = O.mesh_ids(shell, pos, pal)
+    assert len(want) > 3000
+    quads = pack_from_instances(want, shell[13], pos)
+    n = len(quads)
+    out = aligned(((n + 3) & ~3), O.INSTANCE_DTYPE)
+    if palette:
+        ncol = np.array([len(c) for c in palette], dtype=np.int32)
+        rgba = np.zeros((len(palette), 8, 4), dtype=np.float32)
+        for i, cs in enumerate(palette):
+            rgba[i, :len(cs)] = cs
+        rc = L.hb_host_expand_quads(_lib.ChunkPtC(*pos), C.c_void_p(quads.ctypes.data), n, len(palette), C.c_void_p(ncol.ctypes.data),
+                                    C.c_void_p(rgba.ctypes.data), C.c_void_p(out.ctypes.data))
+    else:
+        rc = L.hb_host_expand_quads(_lib.ChunkPtC(*pos), C.c_void_p(quads.ctypes.data), n, 0, None, None, C.c_void_p(out.ctypes.data))
+    assert rc == 0
+    assert out[:n].tobytes() == want.tobytes(), "expanded records differ from the oracle's generate_mesh"
+    assert not out[n:].tobytes().strip(b"\0"), "gap after the last quad must be zero"
+    assert L.hb_host_expand_quads(_lib.ChunkPtC(*pos), None, 4, 0, None, None, C.c_void_p(out.ctypes.data)) == _lib.HB_ERR_INVALID
