@@ -155,6 +155,7 @@ PROTOTYPES = {
     "hb_world_unload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "hb_world_set_cubes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "hb_world_last_edit_groups": (C.c_uint32, [C.c_void_p]),
+    "hb_host_group_edits": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint32)]),
     "hb_world_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),
     "hb_world_fetch_updates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint64, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]),

@@ -616,9 +616,10 @@ int hb_world_unload(hb_world* w, const hb_chunk_pt* pts, size_t n) {
 }
 
 namespace {
-// one sub-batch of hb_world_set_cubes (c->mu held, device current): group, upload, launch, wait
-int apply_edits(hb_world* w, const int32_t* xyz, const uint16_t* materials, size_t n, uint32_t* groups_out) {
-    hb_ctx* c = w->ctx;
+// Conflict groups of an edit batch: the connected components of "the two edits' 7-voxel stencils (the voxel and its six
+// neighbours) share a voxel".  group_of[i] = group of edit i; groups are numbered by their first edit; group_start is the
+// exclusive prefix of the group sizes (n_groups + 1 entries).  Pure host code (hb_host_group_edits exposes it to tests).
+void group_edits(const int32_t* xyz, size_t n, std::vector<uint32_t>& group_of, std::vector<uint32_t>& group_start) {
     // ---- conflict groups: union-find over the edits, joined wherever two 7-voxel stencils share a voxel.  The stencil
     // voxels go into an open-addressing table (key = world voxel, value = the first edit that touched it).
     std::vector<uint32_t> parent(n);
@@ -655,7 +656,8 @@ int apply_edits(hb_world* w, const int32_t* xyz, const uint16_t* materials, size
         }
     }
     // stable grouping: groups ordered by their first edit, edits inside a group in the caller's order
-    std::vector<uint32_t> group_of(n), group_start;
+    group_of.assign(n, 0);
+    group_start.clear();
     {
         std::vector<uint32_t> gid(n, UINT32_MAX), count;
         for (size_t i = 0; i < n; ++i) {
@@ -668,6 +670,13 @@ int apply_edits(hb_world* w, const int32_t* xyz, const uint16_t* materials, size
         group_start[0] = 0;
         for (size_t g = 0; g < count.size(); ++g) group_start[g + 1] = group_start[g] + count[g];
     }
+}
+
+// one sub-batch of hb_world_set_cubes (c->mu held, device current): group, upload, launch, wait
+int apply_edits(hb_world* w, const int32_t* xyz, const uint16_t* materials, size_t n, uint32_t* groups_out) {
+    hb_ctx* c = w->ctx;
+    std::vector<uint32_t> group_of, group_start;
+    group_edits(xyz, n, group_of, group_start);
     const uint32_t n_groups = (uint32_t)group_start.size() - 1;
     std::vector<uint32_t> fill(group_start.begin(), group_start.end() - 1);
     std::vector<EditRec> recs(n);
@@ -725,6 +734,15 @@ int hb_world_set_cubes(hb_world* w, const int32_t* xyz, const uint16_t* material
 }
 
 uint32_t hb_world_last_edit_groups(const hb_world* w) { return w ? w->last_edit_groups : 0; }
+
+int hb_host_group_edits(const int32_t* cubes_xyz, size_t n, uint32_t* group_of, uint32_t* n_groups) {
+    if ((n && (!cubes_xyz || !group_of)) || !n_groups) return fail(HB_ERR_INVALID, "null argument");
+    std::vector<uint32_t> g, start;
+    if (n) group_edits(cubes_xyz, n, g, start);
+    for (size_t i = 0; i < n; ++i) group_of[i] = g[i];
+    *n_groups = n ? (uint32_t)start.size() - 1 : 0;
+    return HB_OK;
+}
 
 int hb_world_sync(hb_world* w, size_t* n_dirty, uint64_t* n_entries) {
     if (!w) return fail(HB_ERR_INVALID, "null argument");

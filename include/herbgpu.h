@@ -375,6 +375,10 @@ HB_API int hb_world_set_cubes(hb_world *world, const int32_t *cubes_xyz, const u
  * and its six neighbours -- share no voxel commute and are applied concurrently, one warp per group; inside a group
  * the caller's order is kept, so the result equals the reference's sequential ChunkMap::set_cube calls). */
 HB_API uint32_t hb_world_last_edit_groups(const hb_world *world);
+/* The grouping itself, without a world or a GPU (host code; what the CPU tests check against a brute-force graph):
+ * group_of[i] = conflict group of edit i of the batch (one sub-batch: hb_world_set_cubes groups every 65 536 edits
+ * separately), groups numbered by their first edit. */
+HB_API int hb_host_group_edits(const int32_t *cubes_xyz, size_t n, uint32_t *group_of, uint32_t *n_groups);
 
 /* Chunk::sync_with_client (server/src/chunk/mod.rs:35-67) for every chunk: drains each chunk's
  * updated_positions.  Chunks with a non-empty set join the remesh set (they are the chunks whose client copy

@@ -90,3 +90,36 @@ def test_host_expand_quads_equals_generate_mesh(palette):
     assert out[:n].tobytes() == want.tobytes(), "expanded records differ from the oracle's generate_mesh"
     assert not out[n:].tobytes().strip(b"\0"), "gap after the last quad must be zero"
     assert L.hb_host_expand_quads(_lib.ChunkPtC(*pos), None, 4, 0, None, None, C.c_void_p(out.ctypes.data)) == _lib.HB_ERR_INVALID
+
+
+def test_edit_conflict_groups_are_the_stencil_components():
+    """hb_host_group_edits (the grouping hb_world_set_cubes uses): two edits belong to one group iff they are connected
+    through overlapping 7-voxel stencils, i.e. through pairs at L1 distance <= 2; groups are numbered by their first
+    edit.  Checked against a brute-force graph (scipy connected components) on scattered, clustered, duplicated and
+    chained edits."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    L = _lib.load()
+    rng = np.random.default_rng(12)
+    cases = [rng.integers(-40, 40, size=(600, 3)),                                   # sparse: mostly singletons
+             rng.integers(0, 9, size=(500, 3)),                                      # dense: few big components
+             np.concatenate([np.stack([np.arange(50) * 2, np.zeros(50), np.zeros(50)], 1),  # a chain at distance 2
+                             np.array([[200, 0, 0], [203, 0, 0], [200, 0, 0]]),             # distance 3 apart, one repeat
+                             np.array([[31, 5, 5], [32, 5, 5], [32, 6, 6]])]),              # across a chunk border, diagonal
+             np.array([[2**31 - 3, 0, -2**31 + 2]])]                                 # near the int32 ends
+    for xyz in cases:
+        xyz = np.ascontiguousarray(xyz, dtype=np.int32)
+        n = len(xyz)
+        got = np.zeros(n, dtype=np.uint32)
+        ng = C.c_uint32(0)
+        assert L.hb_host_group_edits(C.c_void_p(xyz.ctypes.data), n, C.c_void_p(got.ctypes.data), C.byref(ng)) == 0
+        d = np.abs(xyz[:, None, :].astype(np.int64) - xyz[None, :, :].astype(np.int64)).sum(-1)
+        i, j = np.nonzero(d <= 2)
+        ncomp, lab = connected_components(coo_matrix((np.ones(len(i)), (i, j)), shape=(n, n)), directed=False)
+        assert ng.value == ncomp
+        # same partition, and groups numbered in order of first appearance
+        seen = {}
+        for k in range(n):
+            seen.setdefault(int(lab[k]), len(seen))
+            assert got[k] == seen[int(lab[k])], (k, got[k], lab[k])
+    assert L.hb_host_group_edits(None, 0, None, C.byref(ng)) == 0 and ng.value == 0
