@@ -192,8 +192,8 @@ class ServerChunkMap:
                 for p, o, c in zip(u["pts"], u["offsets"], u["counts"])}
 
     def remesh(self) -> dict:
-        out = self.world.remesh()
-        return {(int(p["x"]), int(p["y"]), int(p["z"])): out["instances"][int(o):int(o) + int(c)]
+        out = self.world.remesh()  # views of the World's pinned buffer: copied, the mirror hands out owned meshes
+        return {(int(p["x"]), int(p["y"]), int(p["z"])): out["instances"][int(o):int(o) + int(c)].copy()
                 for p, o, c in zip(out["pts"], out["offsets"], out["counts"])}
 
     def close(self) -> None:
