@@ -725,7 +725,7 @@ int hb_region_plan_launches(const hb_region_plan* p, int stages) {
     }
     if (stages & HB_STAGE_HEIGHTS) n += 1;
     if (stages & HB_STAGE_COUNT) n += 1;
-    if (stages & HB_STAGE_SCAN) n += 3;
+    if (stages & HB_STAGE_SCAN) n += scan_launch_count(p->n_chunks());
     if (stages & HB_STAGE_EMIT) n += 1;
     if (stages & HB_STAGE_EMIT_PACKED) n += 1;
     if (stages & HB_STAGE_FILL) n += 1;

@@ -90,6 +90,7 @@ bool noise_fast_index_ok(const WorldDev& w);
 // counts -> offsets (each chunk's start rounded up to 4 instances); d_total[0]=span, d_total[1]=quads.
 // accumulate: offsets start at the current d_total[0] and the totals are advanced (slab chaining).
 size_t scan_workspace_bytes(size_t n);
+int scan_launch_count(size_t n);  // kernels launch_scan enqueues for n chunks (1 up to 16 384 chunks, else 3)
 cudaError_t launch_scan(cudaStream_t s, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* d_ws,
                         uint64_t* d_total, bool accumulate);
 int num_sms();
