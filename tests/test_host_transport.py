@@ -123,3 +123,17 @@ def test_edit_conflict_groups_are_the_stencil_components():
             seen.setdefault(int(lab[k]), len(seen))
             assert got[k] == seen[int(lab[k])], (k, got[k], lab[k])
     assert L.hb_host_group_edits(None, 0, None, C.byref(ng)) == 0 and ng.value == 0
+
+
+def test_host_fill_ids_against_the_threshold_rule_in_numpy():
+    """generator/mod.rs:85-91 written out in numpy (independent of the C oracle): with d = h - world_y, stone (1) for
+    d > 6, dirt (2) for d > 1, grass (3) for d > 0, else air."""
+    L = _lib.load()
+    rng = np.random.default_rng(21)
+    for cy in (-3, 0, 2):
+        heights = rng.integers(cy * 32 - 12, cy * 32 + 44, size=1024).astype(np.int32)  # straddles the chunk and its thresholds
+        out = aligned(32768, np.uint16)
+        assert L.hb_host_fill_ids(C.c_void_p(heights.ctypes.data), cy, C.c_void_p(out.ctypes.data)) == 0
+        d = heights.astype(np.int64)[:, None] - (cy * 32 + np.arange(32))[None, :]        # [column x*32+z][y]
+        want = np.where(d > 6, 1, np.where(d > 1, 2, np.where(d > 0, 3, 0))).astype(np.uint16)
+        assert (out.reshape(1024, 32) == want).all()
