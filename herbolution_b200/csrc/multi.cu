@@ -160,8 +160,16 @@ int hb_multi_generate_mesh_region(hb_multi* m, const hb_region* region, int want
     };
     // device 0 runs on the calling thread (a single-device handle spawns nothing)
     std::vector<std::thread> th;
-    for (int i = 1; i < n; ++i) th.emplace_back(work, i);
+    std::vector<int> inline_later;
+    for (int i = 1; i < n; ++i) {
+        try {
+            th.emplace_back(work, i);
+        } catch (...) {  // no thread to be had: this device's slab runs on the calling thread after device 0's
+            inline_later.push_back(i);
+        }
+    }
     work(0);
+    for (int i : inline_later) work(i);
     for (auto& t : th) t.join();
     uint64_t tc = 0, tq = 0;
     for (int i = 0; i < n; ++i) {

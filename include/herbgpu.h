@@ -255,7 +255,7 @@ typedef struct hb_multi hb_multi;
 HB_API int hb_multi_create(const int32_t *devices, int32_t n_devices, hb_multi **out);
 HB_API void hb_multi_destroy(hb_multi *multi);
 HB_API int32_t hb_multi_device_count(const hb_multi *multi);
-HB_API hb_ctx *hb_multi_ctx(hb_multi *multi, int32_t i);
+HB_API hb_ctx *hb_multi_ctx(hb_multi *multi, int32_t i);   /* owned by the handle: never pass it to hb_destroy */
 HB_API int hb_multi_set_world(hb_multi *multi, int64_t seed, float freq, int32_t octaves, float lacunarity, float gain);
 HB_API int hb_multi_set_noise_kind(hb_multi *multi, int32_t kind);
 HB_API int hb_multi_set_fma_mode(hb_multi *multi, int32_t fused);
