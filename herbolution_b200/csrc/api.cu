@@ -796,19 +796,6 @@ void ensure_expander(hb_ctx* c) {
     }
 }
 
-// packed words of the chunks [0, n) of one slab -> Instance3d at the same offsets, on all host threads
-void expand_slab(hb_ctx* c, const hb_region& r, uint64_t first_chunk, size_t n, const uint64_t* off, const uint32_t* cnt,
-                 const uint32_t* packed, hb_instance3d* out) {
-    const ExpandTables& T = c->xt;
-    const uint64_t per_ix = (uint64_t)r.ncz * r.ncy;
-    c->pool.run(n, 8, [&](size_t i) {
-        if (cnt[i] == 0) return;
-        const uint64_t g = first_chunk + i;
-        const hb_chunk_pt pt{r.cx0 + (int32_t)(g / per_ix), r.cy0 + (int32_t)(g % r.ncy), r.cz0 + (int32_t)((g / r.ncy) % r.ncz)};
-        expand_chunk(T, pt, packed + off[i], cnt[i], out + off[i]);
-    });
-}
-
 int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t ix_end, int want_ids, StreamMode mode,
                   hb_region_sink sink, hb_region_packed_sink psink, void* user, uint64_t* total_chunks, uint64_t* total_quads) {
     if (!c) return fail(HB_ERR_INVALID, "ctx is null");
@@ -865,43 +852,71 @@ int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t 
     struct Pending { bool live; uint64_t first, n, span; } pend[2] = {{false, 0, 0, 0}, {false, 0, 0, 0}};
     uint64_t sum_chunks = 0, sum_quads = 0;
     // hand slab `b` to the sink: wait for its copies; packed+expand writes the Instance3d records on the host threads
-    auto drain = [&](int b) -> int {
+    // Handing slab `b` to the sink has two halves so that the host threads rebuild its records (and block ids) WHILE the
+    // calling thread enqueues and sizes the next slab on the device: drain_begin waits for the slab's copies and starts
+    // the workers, drain_end waits for them and calls the sink.
+    uint16_t* host_ids_out = nullptr;
+    auto drain_begin = [&](int b) -> int {
         if (!pend[b].live) return HB_OK;
-        pend[b].live = false;
         HB_CUDA(cudaEventSynchronize(ev_copied[b]));
-        const uint64_t* off = c->h_off[b].as<uint64_t>();
-        const uint32_t* cnt = c->h_cnt[b].as<uint32_t>();
-        const uint16_t* ids = dev_ids ? c->h_ids[b].as<uint16_t>() : nullptr;
-        if (host_ids && (sink || psink)) {
+        const bool want_expand = mode == kPackedExpand && sink;
+        const bool want_fill = host_ids && (sink || psink);
+        if (!want_expand && !want_fill) return HB_OK;
+        if (want_fill) {
             const int rc2 = reserve_plain(&c->h_ids_plain, &c->h_ids_plain_cap, pend[b].n * HB_CHUNK_VOLUME * sizeof(uint16_t));
             if (rc2 != HB_OK) return rc2;
-            uint16_t* out_ids = static_cast<uint16_t*>(c->h_ids_plain);
-            const int32_t* hts = c->h_heights[b].as<int32_t>();
-            const int32_t ncy = region->ncy, cy0 = region->cy0;
-            c->pool.run(pend[b].n, 4, [&](size_t i) {  // slab-relative chunk i = column i / ncy, layer i % ncy
-                fill_chunk_ids(hts + (i / ncy) * HB_CHUNK_AREA, cy0 + (int32_t)(i % ncy), out_ids + i * HB_CHUNK_VOLUME);
-            });
-            ids = out_ids;
         }
+        if (want_expand) {
+            const int rc2 = reserve_expanded(c, std::max<uint64_t>(pend[b].span, 4) * sizeof(hb_instance3d));
+            if (rc2 != HB_OK) return rc2;
+        }
+        host_ids_out = want_fill ? static_cast<uint16_t*>(c->h_ids_plain) : nullptr;
+        const uint64_t* off = c->h_off[b].as<uint64_t>();
+        const uint32_t* cnt = c->h_cnt[b].as<uint32_t>();
+        const uint32_t* packed_words = c->h_packed[b].as<uint32_t>();
+        hb_instance3d* inst = static_cast<hb_instance3d*>(c->h_expanded);
+        uint16_t* out_ids = host_ids_out;
+        const int32_t* hts = c->h_heights[b].as<int32_t>();
+        const hb_region r = *region;
+        const uint64_t first = pend[b].first, per_ix = (uint64_t)r.ncz * r.ncy;
+        const ExpandTables* T = &c->xt;
+        c->pool.start(pend[b].n, 8, [=](size_t i) {  // slab-relative chunk i = column i / ncy, layer i % ncy
+            if (want_expand && cnt[i]) {
+                const uint64_t g = first + i;
+                const hb_chunk_pt pt{r.cx0 + (int32_t)(g / per_ix), r.cy0 + (int32_t)(g % r.ncy), r.cz0 + (int32_t)((g / r.ncy) % r.ncz)};
+                expand_chunk(*T, pt, packed_words + off[i], cnt[i], inst + off[i]);
+            }
+            if (want_fill) fill_chunk_ids(hts + (i / r.ncy) * HB_CHUNK_AREA, r.cy0 + (int32_t)(i % r.ncy), out_ids + i * HB_CHUNK_VOLUME);
+        });
+        return HB_OK;
+    };
+    auto drain_end = [&](int b) -> int {
+        if (!pend[b].live) return HB_OK;
+        pend[b].live = false;
+        c->pool.wait();
+        const uint64_t* off = c->h_off[b].as<uint64_t>();
+        const uint32_t* cnt = c->h_cnt[b].as<uint32_t>();
+        const uint16_t* ids = dev_ids ? c->h_ids[b].as<uint16_t>() : (host_ids && (sink || psink) ? host_ids_out : nullptr);
         if (mode == kPackedSink) {
             if (psink) psink(user, pend[b].first, pend[b].n, off, cnt, c->h_packed[b].as<hb_packed_quad>(), pend[b].span, ids);
         } else if (mode == kPackedExpand) {
-            if (!sink) return HB_OK;  // nobody looks at the records
-            const int rc2 = reserve_expanded(c, std::max<uint64_t>(pend[b].span, 4) * sizeof(hb_instance3d));
-            if (rc2 != HB_OK) return rc2;
-            hb_instance3d* inst = static_cast<hb_instance3d*>(c->h_expanded);
-            expand_slab(c, *region, pend[b].first, pend[b].n, off, cnt, c->h_packed[b].as<uint32_t>(), inst);
-            sink(user, pend[b].first, pend[b].n, off, cnt, inst, pend[b].span, ids);
+            if (sink) sink(user, pend[b].first, pend[b].n, off, cnt, static_cast<hb_instance3d*>(c->h_expanded), pend[b].span, ids);
         } else if (sink) {
             sink(user, pend[b].first, pend[b].n, off, cnt, c->h_inst[b].as<hb_instance3d>(), pend[b].span, ids);
         }
         return HB_OK;
+    };
+    auto drain = [&](int b) -> int {
+        const int rc2 = drain_begin(b);
+        return rc2 != HB_OK ? rc2 : drain_end(b);
     };
     int slab = 0;
     for (int32_t ix0 = ix_begin; ix0 < ix_end && rc == HB_OK; ix0 += width, ++slab) {
         const int b = slab & 1;
         hb_region_plan* p = plan[b];
         rc = drain(b);  // buffers of parity b are free again (device out + pinned)
+        if (rc != HB_OK) break;
+        rc = drain_begin(b ^ 1);  // the previous slab's records are rebuilt by the workers during the device calls below
         if (rc != HB_OK) break;
         plan_target(p, ix0, std::min(ix_end, ix0 + width));
         const size_t nch = p->n_chunks();
@@ -948,8 +963,9 @@ int stream_region(hb_ctx* c, const hb_region* region, int32_t ix_begin, int32_t 
         sum_chunks += nch;
         sum_quads += tot[1];
         // hand the previous slab to the sink while this one is computed and copied
-        rc = drain(b ^ 1);
+        rc = drain_end(b ^ 1);
     }
+    c->pool.wait();  // an error path may have left the loop between drain_begin and drain_end
     if (rc == HB_OK) rc = drain((slab & 1));
     if (rc == HB_OK) rc = drain((slab & 1) ^ 1);
     cudaStreamSynchronize(c->copy);

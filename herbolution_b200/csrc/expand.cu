@@ -208,6 +208,30 @@ void HostPool::run(size_t n_items, size_t grain, const std::function<void(size_t
     impl_->cv_done.wait(lk, [&] { return impl_->active == 0; });
 }
 
+void HostPool::start(size_t n_items, size_t grain, const std::function<void(size_t)>& fn) {
+    if (n_items == 0) return;
+    if (!impl_) {
+        for (size_t i = 0; i < n_items; ++i) fn(i);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->fn = fn;
+        impl_->n_items = n_items;
+        impl_->grain = grain ? grain : 1;
+        impl_->next.store(0, std::memory_order_relaxed);
+        impl_->active = (int)impl_->workers.size();
+        ++impl_->generation;
+    }
+    impl_->cv_work.notify_all();
+}
+
+void HostPool::wait() {
+    if (!impl_) return;
+    std::unique_lock<std::mutex> lk(impl_->mu);
+    impl_->cv_done.wait(lk, [&] { return impl_->active == 0; });
+}
+
 int default_host_threads() {
     unsigned hw = std::thread::hardware_concurrency();
     if (const char* e = getenv("HB_HOST_THREADS")) {

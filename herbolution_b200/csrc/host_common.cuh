@@ -91,6 +91,10 @@ class HostPool {
     void resize(int n_threads);  // total threads incl. the caller; <= 1 = run inline
     int threads() const;
     void run(size_t n_items, size_t grain, const std::function<void(size_t)>& fn);
+    // The same on the workers alone: start() returns at once (with a single thread it runs the items inline), wait()
+    // returns when they are done.  Nothing else may use the pool between the two.
+    void start(size_t n_items, size_t grain, const std::function<void(size_t)>& fn);
+    void wait();
 
    private:
     struct Impl;
