@@ -528,18 +528,20 @@ int hb_build_neighbor_index(const hb_chunk_pt* pts, size_t n, int32_t* out) {
 size_t hb_dev_mesh_workspace_bytes(size_t n) {
     const size_t a = n * HB_CHUNK_AREA * sizeof(uint32_t);  // bitmaps
     const size_t b = (n * sizeof(uint32_t) + 255) & ~(size_t)255;  // summary
-    return a + b + scan_workspace_bytes(n) + 256;
+    const size_t d = n * 6 * 32 * sizeof(uint32_t) + (((n + 1) * sizeof(uint32_t) + 255) & ~(size_t)255);  // border records, work list
+    return a + b + scan_workspace_bytes(n) + 256 + d;
 }
 
 }  // extern "C"
 
 namespace {
 
-// workspace layout shared by the ids and the PaletteCube (flags) paths: bitmaps | summary | scan | [face planes]
+// workspace layout shared by the ids and the PaletteCube (flags) paths: bitmaps | summary | scan | borders | [face planes]
 struct MeshWs {
     uint32_t* bitmaps;
     uint32_t* summary;
     void* scan;
+    uint32_t* borders;  // ids path: six 32-word planes per chunk (k_pack)
     uint32_t* planes;  // only in flags mode
 };
 size_t mesh_ws_bytes(size_t n, bool flags) {
@@ -554,6 +556,8 @@ MeshWs mesh_ws(void* d_workspace, size_t n, bool flags) {
     ws += (n * sizeof(uint32_t) + 255) & ~(size_t)255;
     w.scan = ws;
     ws += (scan_workspace_bytes(n) + 255) & ~(size_t)255;
+    w.borders = reinterpret_cast<uint32_t*>(ws);
+    ws += n * 6 * 32 * sizeof(uint32_t) + (((n + 1) * sizeof(uint32_t) + 255) & ~(size_t)255);  // + the emit work list
     w.planes = flags ? reinterpret_cast<uint32_t*>(ws) : nullptr;
     return w;
 }
@@ -569,13 +573,14 @@ int dev_mesh_impl(hb_ctx* c, cudaStream_t s, bool flags, const hb_chunk_pt* d_pt
         HB_CUDA(launch_pack_cubes(s, static_cast<const hb_palette_cube*>(d_blocks), n, c->mats.n_materials, w.bitmaps, w.summary,
                                   w.planes, d_total));
     else
-        HB_CUDA(launch_pack(s, static_cast<const uint16_t*>(d_blocks), n, c->mats.n_materials, w.bitmaps, w.summary, d_total));
+        HB_CUDA(launch_pack(s, static_cast<const uint16_t*>(d_blocks), n, c->mats.n_materials, w.bitmaps, w.summary, w.borders,
+                            d_counts, d_total));
     HB_CUDA(launch_mesh_ids(s, false, c->tables, c->d_mats, d_pts, n, d_blocks, d_nbr, w.bitmaps, w.summary, w.planes, d_counts,
-                            nullptr, nullptr, 0, d_total));
+                            nullptr, nullptr, 0, d_total, nullptr, w.borders));
     HB_CUDA(launch_scan(s, d_counts, n, d_offsets, w.scan, d_total, false));
     if (d_out)
         HB_CUDA(launch_mesh_ids(s, true, c->tables, c->d_mats, d_pts, n, d_blocks, d_nbr, w.bitmaps, w.summary, w.planes,
-                                d_counts, d_offsets, d_out, out_capacity, d_total));
+                                d_counts, d_offsets, d_out, out_capacity, d_total, nullptr, w.borders));
     return HB_OK;
 }
 
@@ -629,7 +634,7 @@ int mesh_host_impl(hb_ctx* c, bool flags, const hb_chunk_pt* pts, size_t n, cons
         const MeshWs w = mesh_ws(c->d_bitmaps.p, n, flags);
         HB_CUDA(launch_mesh_ids(s, true, c->tables, c->d_mats, c->d_pts.as<hb_chunk_pt>(), n, c->d_ids.p, c->d_nbr.as<int32_t>(),
                                 w.bitmaps, w.summary, w.planes, c->d_counts.as<uint32_t>(), c->d_offsets.as<uint64_t>(),
-                                c->d_out.as<hb_instance3d>(), tot[0], c->d_total.as<uint64_t>()));
+                                c->d_out.as<hb_instance3d>(), tot[0], c->d_total.as<uint64_t>(), nullptr, w.borders));
         HB_CUDA(cudaMemcpyAsync(out, c->d_out.p, tot[0] * sizeof(hb_instance3d), cudaMemcpyDeviceToHost, s));
     }
     HB_CUDA(cudaStreamSynchronize(s));

@@ -60,8 +60,9 @@ cudaError_t launch_fill_region(cudaStream_t s, const RegionDev& r, const int32_t
 cudaError_t launch_noise3d(cudaStream_t s, const WorldDev& w, float sx, float sy, float sz, int nx, int ny, int nz,
                            float fx, float fy, float fz, float* d_out);
 
+// d_borders: [n][6][32] border records, d_counts: the chunk-local face counts (launch_mesh_ids(emit = false) adds the hull)
 cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_materials, uint32_t* d_bitmaps,
-                        uint32_t* d_summary, uint64_t* d_total);
+                        uint32_t* d_summary, uint32_t* d_borders, uint32_t* d_counts, uint64_t* d_total);
 cudaError_t launch_pack_cubes(cudaStream_t s, const hb_palette_cube* d_cubes, size_t n, int n_materials,
                               uint32_t* d_bitmaps, uint32_t* d_summary, uint32_t* d_planes, uint64_t* d_total,
                               const int32_t* d_list = nullptr);
@@ -72,7 +73,7 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
                             const hb_chunk_pt* d_pts, size_t n, const void* d_blocks, const int32_t* d_nbr,
                             const uint32_t* d_bitmaps, const uint32_t* d_summary, const uint32_t* d_planes,
                             uint32_t* d_counts, const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
-                            uint64_t* d_total, const int32_t* d_list = nullptr);
+                            uint64_t* d_total, const int32_t* d_list = nullptr, const uint32_t* d_borders = nullptr);
 cudaError_t launch_mesh_region(cudaStream_t s, bool emit, const MeshTables& tb, const MaterialsDev* d_mats,
                                const RegionDev& r, const int32_t* d_heights, uint32_t* d_counts,
                                const uint64_t* d_offsets, void* d_out, uint64_t capacity,

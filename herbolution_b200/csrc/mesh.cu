@@ -365,39 +365,45 @@ __device__ __forceinline__ void load_tables(SM& sm, const MeshTables& tb) {
 // K3a: u16 ids -> 1 bit per voxel (bitmap[c] for column c = x*32+z, bit y) + a per-chunk summary
 // word: bit0 any solid, bit1 all solid, bit(2+f) boundary slab at face f entirely solid.
 // One 128-bit streaming load per thread per 8 voxels; the chunk's 64 KiB are read exactly once.
+//
+// While the words are still on chip the kernel also does the chunk-local half of the COUNT stage: the faces between
+// two voxels of this chunk (`counts[chunk]`), and a 768-byte border record (six 32-word planes, face order
+// E W U D N S: the x = 31 / x = 0 rows by z, the y = 31 / y = 0 bits as bit z of word x, the z = 31 / z = 0 words
+// by x) from which k_count_border adds the faces on the chunk's hull without touching the bitmaps again.
+constexpr int kBorderWords = 6 * 32;
 __global__ void __launch_bounds__(kT, 3) k_pack(const uint16_t* __restrict__ ids, size_t n, int n_materials,
                                              uint32_t* __restrict__ bitmaps, uint32_t* __restrict__ summary,
+                                             uint32_t* __restrict__ borders, uint32_t* __restrict__ counts,
                                              u64* __restrict__ total) {
     __shared__ uint32_t s_red[8][8];
+    __shared__ uint32_t s_bm[HB_CHUNK_AREA];
+    __shared__ uint32_t s_cnt[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (size_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         const uint4* src = reinterpret_cast<const uint4*>(ids + chunk * HB_CHUNK_VOLUME);
-        uint32_t any = 0, all = ~0u, fE = ~0u, fW = ~0u, fN = ~0u, fS = ~0u, bad = 0;
-        // Two ids per 32-bit word, tested with plain integer SWAR (the __v*2 video intrinsics are emulated with long
-        // sequences on this architecture).  With guard = 0x8000 in both halfwords:
-        //   nonzero:  ((w & 0x7FFF7FFF) + 0x7FFF7FFF) | w   has the halfword's top bit set iff the id is non-zero
-        //   in range: (n_materials | guard) - w             keeps the halfword's top bit iff id <= n_materials (ids with
-        //             their own top bit set are flagged separately; a borrow can only start in a halfword that is
-        //             already out of range)
-        const uint32_t guard = 0x80008000u, nmg = ((uint32_t)n_materials * 0x10001u) | guard;
+        uint32_t any = 0, all = ~0u, fE = ~0u, fW = ~0u, fN = ~0u, fS = ~0u, mx = 0;
+        // Two ids per 32-bit word, tested with the packed 16-bit min/max of the DPX unit (VIMNMX3.U16x2):
+        //   min(id, 1) is the "non-zero" bit of each halfword, the running max is compared with the palette size once
+        //   per chunk.
+        const uint32_t one = 0x00010001u;
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
             const int u = it * kT + tid;
             const uint4 v = __ldg(src + u);
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            uint32_t t = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t y = (((w4[k] & 0x7FFF7FFFu) + 0x7FFF7FFFu) | w4[k]) & guard;
-                t |= y >> (15 - 2 * k);  // low id -> bit 2k, high id -> bit 16 + 2k
-                bad |= (~(nmg - w4[k]) | w4[k]) & guard;
-            }
+            const uint32_t y0 = __vimin3_u16x2(v.x, one, one), y1 = __vimin3_u16x2(v.y, one, one);
+            const uint32_t y2 = __vimin3_u16x2(v.z, one, one), y3 = __vimin3_u16x2(v.w, one, one);
+            const uint32_t t = y0 + y1 * 4u + y2 * 16u + y3 * 64u;  // low id of word k -> bit 2k, high id -> bit 16 + 2k
+            mx = __vimax3_u16x2(mx, v.x, v.y);
+            mx = __vimax3_u16x2(mx, v.z, v.w);
             const uint32_t m8 = (t & 0x55u) | ((t >> 15) & 0xAAu);  // bit j = id j of this 8-id unit is non-zero
             uint32_t w = m8 << ((u & 3) * 8);
             w |= __shfl_xor_sync(0xffffffffu, w, 1);
             w |= __shfl_xor_sync(0xffffffffu, w, 2);
             const int c = u >> 2, x = c >> 5, z = c & 31;
-            if ((lane & 3) == 0) bitmaps[chunk * HB_CHUNK_AREA + c] = w;
+            if ((lane & 3) == 0) {
+                bitmaps[chunk * HB_CHUNK_AREA + c] = w;
+                s_bm[c] = w;
+            }
             any |= w;
             all &= w;
             if (x == 31) fE &= w;
@@ -411,7 +417,8 @@ __global__ void __launch_bounds__(kT, 3) k_pack(const uint16_t* __restrict__ ids
         fW = __reduce_and_sync(0xffffffffu, fW);
         fN = __reduce_and_sync(0xffffffffu, fN);
         fS = __reduce_and_sync(0xffffffffu, fS);
-        bad = __reduce_or_sync(0xffffffffu, bad);
+        const uint32_t bad =
+            __reduce_or_sync(0xffffffffu, (uint32_t)((mx & 0xFFFFu) > (uint32_t)n_materials || (mx >> 16) > (uint32_t)n_materials));
         if (lane == 0) {
             s_red[warp][0] = any; s_red[warp][1] = all; s_red[warp][2] = fE; s_red[warp][3] = fW;
             s_red[warp][4] = fN; s_red[warp][5] = fS; s_red[warp][6] = bad;
@@ -433,7 +440,79 @@ __global__ void __launch_bounds__(kT, 3) k_pack(const uint16_t* __restrict__ ids
             summary[chunk] = sw;
             if (b) atomicOr(total + 2, 2ULL);         // error path only: unknown material id
         }
+        // chunk-local faces: a voxel's face is visible when the voxel behind it is empty; on the hull that voxel
+        // belongs to another chunk, so it is treated as solid here and k_count_border settles it
+        uint32_t* rec = borders + chunk * kBorderWords;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = k * 8 + warp, z = lane, col = x * 32 + z;
+            const uint32_t cen = s_bm[col];
+            const uint32_t e = x < 31 ? s_bm[col + 32] : ~0u;
+            const uint32_t w = x > 0 ? s_bm[col - 32] : ~0u;
+            const uint32_t nn = z < 31 ? s_bm[col + 1] : ~0u;
+            const uint32_t ss = z > 0 ? s_bm[col - 1] : ~0u;
+            const uint32_t up = (cen >> 1) | 0x80000000u, dn = (cen << 1) | 1u;
+            cnt += __popc(cen & ~e) + __popc(cen & ~w) + __popc(cen & ~up) + __popc(cen & ~dn) + __popc(cen & ~nn) +
+                   __popc(cen & ~ss);
+            const uint32_t top = __ballot_sync(0xffffffffu, cen >> 31), bot = __ballot_sync(0xffffffffu, cen & 1u);
+            if (lane == 0) {
+                rec[2 * 32 + x] = top;
+                rec[3 * 32 + x] = bot;
+            }
+        }
+        if (tid < 32) rec[tid] = s_bm[31 * 32 + tid];                         // E: x = 31, by z
+        else if (tid < 64) rec[tid] = s_bm[tid - 32];                         // W: x = 0, by z
+        else if (tid >= 128 && tid < 160) rec[tid] = s_bm[(tid - 128) * 32 + 31];  // N: z = 31, by x
+        else if (tid >= 160 && tid < 192) rec[tid] = s_bm[(tid - 160) * 32];       // S: z = 0, by x
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) s_cnt[warp] = cnt;
         __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += s_cnt[i];
+            counts[chunk] = t;
+        }
+    }
+}
+
+// COUNT, second half (ids path): the faces on the hull of every chunk, from the border records of the chunk and of its six
+// face neighbours (shell index (dx+1)*9 + (dy+1)*3 + (dz+1), client/src/world/chunk.rs:158-174); a missing
+// neighbour is empty space.  One warp per chunk, 12 coalesced 128-byte loads.  Also appends the chunks that have
+// quads to nz[1..] (nz[0] = how many; zeroed by the launch wrapper): the work list of k_emit_ids.  The list's order
+// depends on CTA arrival; it only decides which CTA emits a chunk, never where the quads go.
+__global__ void __launch_bounds__(kT) k_count_border(size_t n, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ borders,
+                                                      uint32_t* __restrict__ counts, uint32_t* __restrict__ nz) {
+    __shared__ uint32_t s_tot[kT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t chunk = (size_t)blockIdx.x * (kT / 32) + warp;
+    uint32_t tot = 0;
+    if (chunk < n) {
+        const int32_t* nb = nbr + chunk * 27;
+        const int shell[6] = {22, 4, 16, 10, 14, 12};  // E W U D N S
+        const uint32_t* rec = borders + chunk * kBorderWords;
+        uint32_t c = 0;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+            const int o = __ldg(nb + shell[f]);
+            const uint32_t own = __ldg(rec + f * 32 + lane);
+            const uint32_t other = o >= 0 ? __ldg(borders + (size_t)o * kBorderWords + (f ^ 1) * 32 + lane) : 0u;
+            c += __popc(own & ~other);
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        tot = counts[chunk] + c;  // k_pack's chunk-local faces + the hull
+        if (lane == 0 && c) counts[chunk] = tot;
+    }
+    if (lane == 0) s_tot[warp] = tot;
+    __syncthreads();
+    if (warp == 0) {
+        const bool has = lane < kT / 32 && s_tot[lane] != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, has);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(nz, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (has) nz[1 + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(blockIdx.x * (kT / 32) + lane);
     }
 }
 
@@ -503,62 +582,23 @@ struct MatCubes {
     __device__ __forceinline__ uint32_t operator()(uint32_t L, int, int, int) const { return __ldg(&cubes[L].material); }
 };
 
-// K3b (COUNT) for the general mesher: no occupancy tile.  Every thread takes four columns and builds their six
-// face masks straight from the L2-resident bitmaps (own word, four lateral words -- from the neighbour chunk at the
-// chunk border -- and one bit each from the chunks above and below), or reads the face planes in FLAGS mode.
-// One barrier per chunk; equals what mesh_tile<EMIT> emits (same masks), which the parity tests pin down.
-template <bool FLAGS>
-__global__ void __launch_bounds__(kT) k_count_ids(size_t n, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
-                                                   const uint32_t* __restrict__ summary, const uint32_t* __restrict__ planes,
+// K3b (COUNT) for PaletteCube input: the visible faces are the bits of the six planes k_pack_cubes wrote.
+__global__ void __launch_bounds__(kT) k_count_ids(size_t n, const uint32_t* __restrict__ summary, const uint32_t* __restrict__ planes,
                                                    uint32_t* __restrict__ counts, const int32_t* __restrict__ list) {
     __shared__ uint32_t s_part[kT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (size_t item = blockIdx.x; item < n; item += gridDim.x) {
         const size_t chunk = list ? (size_t)list[item] : item;  // counts[] is indexed by work item
-        const uint32_t s = summary[chunk];
-        if (!(s & 1u)) {  // no solid voxel
+        if (!(summary[chunk] & 1u)) {  // no solid voxel
             if (tid == 0) counts[item] = 0;
             continue;
         }
         uint32_t c = 0;
-        if (FLAGS) {
-            const uint32_t* p = planes + chunk * 6 * HB_CHUNK_AREA;
+        const uint32_t* p = planes + chunk * 6 * HB_CHUNK_AREA;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int f = 0; f < 6; ++f) c += __popc(__ldg(p + f * HB_CHUNK_AREA + (k * 8 + warp) * 32 + lane));
-        } else {
-            const int32_t* nb = nbr + chunk * 27;
-            // shell index (dx+1)*9 + (dy+1)*3 + (dz+1) of the six face neighbours (client/src/world/chunk.rs:158-174)
-            const int nE = nb[22], nW = nb[4], nU = nb[16], nD = nb[10], nN = nb[14], nS = nb[12];
-            if (s & 2u) {  // completely solid: nothing to count if the six facing slabs are solid too
-                bool buried = true;
-                const int nf[6] = {nE, nW, nU, nD, nN, nS};
-#pragma unroll
-                for (int f = 0; f < 6; ++f)
-                    if (nf[f] < 0 || !((summary[nf[f]] >> (2 + (f ^ 1))) & 1u)) buried = false;
-                if (buried) {
-                    if (tid == 0) counts[item] = 0;
-                    continue;
-                }
-            }
-            const uint32_t* bm = bitmaps + chunk * HB_CHUNK_AREA;
-            auto word = [&](int nbc, int col) -> uint32_t { return nbc >= 0 ? __ldg(bitmaps + (size_t)nbc * HB_CHUNK_AREA + col) : 0u; };
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int x = k * 8 + warp, z = lane, col = x * 32 + z;
-                const uint32_t cen = __ldg(bm + col);
-                if (!cen) continue;
-                const uint32_t e = x < 31 ? __ldg(bm + col + 32) : word(nE, z);
-                const uint32_t w = x > 0 ? __ldg(bm + col - 32) : word(nW, 31 * 32 + z);
-                const uint32_t nn = z < 31 ? __ldg(bm + col + 1) : word(nN, x * 32);
-                const uint32_t ss = z > 0 ? __ldg(bm + col - 1) : word(nS, x * 32 + 31);
-                const uint32_t up = (cen >> 1) | ((word(nU, col) & 1u) << 31);   // voxel above: y+1, or y = 0 of the chunk above
-                const uint32_t dn = (cen << 1) | (word(nD, col) >> 31);          // voxel below
-                c += __popc(cen & ~e) + __popc(cen & ~w) + __popc(cen & ~up) + __popc(cen & ~dn) + __popc(cen & ~nn) +
-                     __popc(cen & ~ss);
-            }
-        }
+            for (int f = 0; f < 6; ++f) c += __popc(__ldg(p + f * HB_CHUNK_AREA + (k * 8 + warp) * 32 + lane));
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0) s_part[warp] = c;
         __syncthreads();
@@ -654,6 +694,175 @@ k_mesh_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
     }
     }  // ticket loop
     if (EMIT) bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
+}
+
+// ---- EMIT for the ids path, software-pipelined across chunks --------------------------------------------------------
+// A chunk's EMIT starts with a chain of dependent loads (which chunk -> its neighbour row -> 1156 + 576 occupancy
+// words) before the first quad can be written; in k_mesh_ids that chain is paid in full by every chunk (23 % of the
+// kernel's stall samples sit on the first use of the tile words, profiles/r2_ncu_c3emit_summary.csv).  Here the
+// chain of chunk i+1 runs underneath the emission of chunk i:
+//   * COUNT leaves a compacted list of the chunks that have quads (k_count_border), so one ticket = one chunk;
+//   * warp 0 keeps the control pipeline in registers: the ticket of chunk i+2 is drawn and the neighbour row, count,
+//     offset and position of chunk i+1 are loaded while the CTA still waits for chunk i's tile;
+//   * the tile of chunk i+1 is fetched with cp.async (no registers, no scoreboard) into a raw buffer as soon as the
+//     occupancy tile of chunk i has been built from it, and lands during chunk i's emission.
+// The words above and below the tile come from the 128-byte U/D planes of the border records instead of one full
+// bitmap word per column.  Which CTA meshes a chunk is decided by tickets; where its quads go is fixed by the scanned
+// offsets, so the output is deterministic.
+struct IdsItem {
+    u64 off;
+    uint32_t count;
+    int32_t chunk;  // < 0: no such item
+    hb_chunk_pt pt;
+    int32_t nbr[27];
+};
+struct IdsPipe {
+    uint32_t pl[2][9][32];  // [0]: U planes (y = 31) of the 9 chunks below, [1]: D planes (y = 0) of the 9 chunks above
+    IdsItem item[2];
+};
+
+struct EmitIdsSmem {
+    MeshSmem sm;
+    IdsPipe pp;
+};
+static_assert((sizeof(EmitIdsSmem) + 1024) * kCtasPerSm <= 228 * 1024, "k_emit_ids: shared memory per SM");
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// tile cell i of a 34x34 halo tile -> (shell index of the lateral neighbour at dy = -1, 3x3 index, column in that chunk)
+__device__ __forceinline__ void tile_cell(int i, int& sb, int& nb9, int& x, int& z) {
+    const int xi = i / kTile, zi = i - xi * kTile;
+    const int dx = (xi == 0) ? -1 : (xi == kTile - 1 ? 1 : 0);
+    const int dz = (zi == 0) ? -1 : (zi == kTile - 1 ? 1 : 0);
+    x = (xi - 1) & 31;
+    z = (zi - 1) & 31;
+    sb = (dx + 1) * 9 + (dz + 1);
+    nb9 = (dx + 1) * 3 + (dz + 1);
+}
+
+__global__ void __launch_bounds__(kT, kCtasPerSm)
+k_emit_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_chunk_pt* __restrict__ pts,
+           const uint16_t* __restrict__ ids, const int32_t* __restrict__ nbr, const uint32_t* __restrict__ bitmaps,
+           const uint32_t* __restrict__ borders, const uint32_t* __restrict__ nz, const uint32_t* __restrict__ counts,
+           const u64* __restrict__ offsets, float* __restrict__ out, u64 capacity, u64* __restrict__ total) {
+    extern __shared__ __align__(16) unsigned char emit_ids_smem_raw[];
+    EmitIdsSmem& es = *reinterpret_cast<EmitIdsSmem*>(emit_ids_smem_raw);
+    MeshSmem& sm = es.sm;
+    IdsPipe& pp = es.pp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* const raw = reinterpret_cast<uint32_t*>(sm.hts);  // dy = 0 words of the tile being fetched (region kernels keep heights here)
+    load_tables(sm, tb);
+    const uint32_t n_nz = __ldg(nz);
+    const uint32_t* const list = nz + 1;
+
+    // warp 0: this lane's part of item `chunk` (27 neighbour entries, count, offset, position)
+    struct Piece { u64 off; int32_t v; };
+    auto load_piece = [&](int32_t chunk) -> Piece {
+        Piece p{0, 0};
+        if (chunk < 0) return p;
+        if (lane < 27) p.v = __ldg(nbr + (size_t)chunk * 27 + lane);
+        else if (lane == 27) p.v = (int32_t)__ldg(counts + chunk);
+        else if (lane == 28) p.off = __ldg(offsets + chunk);
+        else p.v = __ldg(reinterpret_cast<const int32_t*>(pts + chunk) + (lane - 29));
+        return p;
+    };
+    auto store_piece = [&](IdsItem& it, int32_t chunk, const Piece& p) {
+        if (lane == 0) it.chunk = chunk;
+        if (chunk < 0) return;
+        if (lane < 27) it.nbr[lane] = p.v;
+        else if (lane == 27) it.count = (uint32_t)p.v;
+        else if (lane == 28) it.off = p.off;
+        else (&it.pt.x)[lane - 29] = p.v;
+    };
+    // all threads: start fetching the tile of item `it` (block-uniform; it.nbr is visible)
+    auto fetch_tile = [&](const IdsItem& it) {
+        constexpr int kIter = (kTileN + kT - 1) / kT;
+#pragma unroll
+        for (int k = 0; k < kIter; ++k) {
+            const int i = tid + k * kT;
+            if (i < kTileN) {
+                int sb, nb9, x, z;
+                tile_cell(i, sb, nb9, x, z);
+                const int n0 = it.nbr[sb + 3];  // dy = 0
+                if (n0 >= 0) cp_async4(raw + i, bitmaps + (size_t)n0 * HB_CHUNK_AREA + x * 32 + z);
+                else raw[i] = 0u;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int e = tid + k * kT;
+            if (e < 2 * 9 * 32) {
+                const int v = e / 288, r = e - v * 288, nb9 = r >> 5, w = r & 31;
+                const int nbc = it.nbr[(nb9 / 3) * 9 + (nb9 % 3) + (v ? 6 : 0)];
+                // the chunk above shows its y = 0 bits (D plane, 3), the chunk below its y = 31 bits (U plane, 2)
+                if (nbc >= 0) cp_async4(&pp.pl[v][nb9][w], borders + (size_t)nbc * kBorderWords + (v ? 3 : 2) * 32 + w);
+                else pp.pl[v][nb9][w] = 0u;
+            }
+        }
+    };
+
+    // prologue: the first two tickets; the first item's record and tile
+    int32_t next_chunk = -1;  // warp 0 (uniform): the item after the current one, not yet loaded
+    if (warp == 0) {
+        u64 t = 0;
+        if (lane == 0) t = atomicAdd(total + 3, 2ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        const int32_t first = t < n_nz ? (int32_t)__ldg(list + t) : -1;
+        next_chunk = t + 1 < n_nz ? (int32_t)__ldg(list + t + 1) : -1;
+        store_piece(pp.item[0], first, load_piece(first));
+    }
+    __syncthreads();
+    int cur = 0;
+    if (pp.item[0].chunk >= 0) fetch_tile(pp.item[0]);
+    while (pp.item[cur].chunk >= 0) {
+        // (1) warp 0: the next item's record and the ticket after it go out while this item's tile is still in flight
+        Piece piece{0, 0};
+        u64 ticket = 0;
+        if (warp == 0) {
+            piece = load_piece(next_chunk);
+            if (lane == 0) ticket = atomicAdd(total + 3, 1ULL);
+        }
+        // (2) this item's tile has landed
+        cp_async_wait_all();
+        __syncthreads();
+        const IdsItem& it = pp.item[cur];
+        constexpr int kIter = (kTileN + kT - 1) / kT;
+#pragma unroll
+        for (int k = 0; k < kIter; ++k) {
+            const int i = tid + k * kT;
+            if (i < kTileN) {
+                int sb, nb9, x, z;
+                tile_cell(i, sb, nb9, x, z);
+                const u64 below = (pp.pl[0][nb9][x] >> z) & 1u, above = (pp.pl[1][nb9][x] >> z) & 1u;
+                sm.occ[i] = ((u64)raw[i] << 1) | below | (above << 33);
+            }
+        }
+        if (warp == 0) store_piece(pp.item[cur ^ 1], next_chunk, piece);
+        if (tid == 32) sm.rng_seed = siphash13_chunk(it.pt.x, it.pt.y, it.pt.z);
+        __syncthreads();  // occupancy tile complete, raw buffers free, next record visible
+        // (3) the next item's tile is fetched underneath this item's emission
+        if (pp.item[cur ^ 1].chunk >= 0) fetch_tile(pp.item[cur ^ 1]);
+        if (warp == 0) {  // identity of the item after the next (consumed at the top of the next iteration)
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            next_chunk = ticket < n_nz ? (int32_t)__ldg(list + ticket) : -1;
+        }
+        // (4) mesh
+        const u64 off = it.off;
+        if (off + (((u64)it.count + 3ULL) & ~3ULL) > capacity) {
+            if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
+        } else {
+            const hb_chunk_pt pt = it.pt;
+            mesh_tile<true>(sm, MatIds{ids + (size_t)it.chunk * HB_CHUNK_VOLUME}, FacesFromOcc{sm.occ}, pt.x * 32, pt.y * 32,
+                            pt.z * 32, mats, out + off * 25ULL);
+        }
+        cur ^= 1;
+        // the next iteration's barrier (2) also fences this item's readers of sm.occ / item[cur ^ 1] against (1)..(3)
+    }
+    cp_async_wait_all();
+    bulk_wait_all();  // every bulk store issued by this thread has landed before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1351,11 +1560,11 @@ int num_sms() {
 }
 
 cudaError_t launch_pack(cudaStream_t s, const uint16_t* d_ids, size_t n, int n_materials, uint32_t* d_bitmaps,
-                        uint32_t* d_summary, uint64_t* d_total) {
+                        uint32_t* d_summary, uint32_t* d_borders, uint32_t* d_counts, uint64_t* d_total) {
     if (n == 0) return cudaSuccess;
     size_t grid = (size_t)num_sms() * 32;
     if (grid > n) grid = n;
-    k_pack<<<(unsigned)grid, kT, 0, s>>>(d_ids, n, n_materials, d_bitmaps, d_summary, (u64*)d_total);
+    k_pack<<<(unsigned)grid, kT, 0, s>>>(d_ids, n, n_materials, d_bitmaps, d_summary, d_borders, d_counts, (u64*)d_total);
     return cudaGetLastError();
 }
 
@@ -1373,7 +1582,7 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
                             const hb_chunk_pt* d_pts, size_t n, const void* d_blocks, const int32_t* d_nbr,
                             const uint32_t* d_bitmaps, const uint32_t* d_summary, const uint32_t* d_planes,
                             uint32_t* d_counts, const uint64_t* d_offsets, hb_instance3d* d_out, uint64_t capacity,
-                            uint64_t* d_total, const int32_t* d_list) {
+                            uint64_t* d_total, const int32_t* d_list, const uint32_t* d_borders) {
     if (n == 0) return cudaSuccess;
     // Persistent CTAs.  EMIT draws work from a ticket counter (see k_mesh_ids); COUNT strides statically: batches are
     // usually ordered (ix, iz, iy) with a small number of layers, so an even stride would hand every CTA the same
@@ -1388,13 +1597,35 @@ cudaError_t launch_mesh_ids(cudaStream_t s, bool emit, const MeshTables& tb, con
     if (!emit) {
         size_t cgrid = (size_t)num_sms() * 8 - 1;  // odd, see above
         if (cgrid > n) cgrid = n;
-        if (d_planes) k_count_ids<true><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts, d_list);
-        else k_count_ids<false><<<(unsigned)cgrid, kT, 0, s>>>(n, d_nbr, d_bitmaps, d_summary, d_planes, d_counts, d_list);
+        if (d_planes) {
+            k_count_ids<<<(unsigned)cgrid, kT, 0, s>>>(n, d_summary, d_planes, d_counts, d_list);
+        } else {  // ids path: k_pack left the chunk-local faces in d_counts, the hull is added from the border records
+            if (!d_borders || d_list) return cudaErrorInvalidValue;
+            uint32_t* d_nz = const_cast<uint32_t*>(d_borders) + n * kBorderWords;  // [0] = length, [1..] = chunks with quads
+            const cudaError_t e = cudaMemsetAsync(d_nz, 0, sizeof(uint32_t), s);
+            if (e != cudaSuccess) return e;
+            k_count_border<<<(unsigned)((n + kT / 32 - 1) / (kT / 32)), kT, 0, s>>>(n, d_nbr, d_borders, d_counts, d_nz);
+        }
     } else {
         const cudaError_t e = cudaMemsetAsync(d_total + 3, 0, sizeof(uint64_t), s);  // the ticket counter
         if (e != cudaSuccess) return e;
-        if (d_planes) HB_LAUNCH(true, true);
-        else HB_LAUNCH(true, false);
+        if (d_planes) {
+            HB_LAUNCH(true, true);
+        } else {
+            if (!d_borders || d_list) return cudaErrorInvalidValue;
+            const size_t egrid = (size_t)num_sms() * kCtasPerSm;  // k_emit_ids exits at once when its first ticket is past the list
+            static bool attr_set[16] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev >= 0 && dev < 16 && !attr_set[dev]) {
+                const cudaError_t ea = cudaFuncSetAttribute(k_emit_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitIdsSmem));
+                if (ea != cudaSuccess) return ea;
+                attr_set[dev] = true;
+            }
+            k_emit_ids<<<(unsigned)egrid, kT, sizeof(EmitIdsSmem), s>>>(tb, d_mats, d_pts, static_cast<const uint16_t*>(d_blocks), d_nbr, d_bitmaps, d_borders,
+                                                      d_borders + n * kBorderWords, d_counts, (const u64*)d_offsets, (float*)d_out,
+                                                      capacity, (u64*)d_total);
+        }
     }
 #undef HB_LAUNCH
     return cudaGetLastError();
