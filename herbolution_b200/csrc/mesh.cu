@@ -190,7 +190,8 @@ struct FacesFromPlanes {
 // one TMA bulk shared->global copy (UBLKCP) of the whole window by lane 0 instead of 200 LDS.128 + STG.128 through
 // the LSU.  The window is zero-padded to a multiple of 4 quads.  The wait for the engine to release the buffer from
 // this warp's previous window sits after the register work so the two overlap.
-template <class SM>
+// MATS_SMEM: `mats` points into shared memory (k_emit_ids keeps a copy there: its L1 is thrashed by the block-array reads)
+template <bool MATS_SMEM = false, class SM>
 __device__ __forceinline__ void emit_window(SM& sm, const MaterialsDev* __restrict__ mats, float* __restrict__ ws,
                                             uint32_t ws_shared, char* __restrict__ gdst, uint32_t nw, uint32_t L, uint32_t f,
                                             uint32_t ao, uint32_t id, int bx, int by, int bz) {
@@ -206,9 +207,10 @@ __device__ __forceinline__ void emit_window(SM& sm, const MaterialsDev* __restri
         // ids above the palette are reported through total[2] & 2 by the pack stage; the device-pointer entry points
         // emit regardless, so keep the table reads in bounds (such a quad gets material 1's colours)
         const uint32_t mi = id - 1u < (uint32_t)HB_MAX_MATERIALS ? id - 1u : 0u;
-        const int nc = __ldg(&mats->n_colors[mi]);
+        const int nc = MATS_SMEM ? mats->n_colors[mi] : __ldg(&mats->n_colors[mi]);
         const int ci = __float2int_rz(__fmul_rn(__int2float_rn(nc > 0 ? nc - 1 : 0), p));
-        rgba = __ldg(reinterpret_cast<const float4*>(mats->rgba[mi][ci]));
+        const float4* const col = reinterpret_cast<const float4*>(mats->rgba[mi][ci]);
+        rgba = MATS_SMEM ? *col : __ldg(col);
     }
     if (lane == 0) bulk_wait_read();  // previous window of this warp has left the staging buffer
     __syncwarp();
@@ -245,7 +247,7 @@ __device__ __forceinline__ void emit_window(SM& sm, const MaterialsDev* __restri
 // PACKED (with EMIT): instead of the 100-byte instance, `out` receives one 32-bit word per quad (hb_packed_quad:
 // L | face << 15 | ao << 18 | (material - 1) << 26), the gap zero-filled the same way.  The colour is not part of
 // the word: it is a pure function of (chunk, L, face) and the expander recomputes it (expand.cpp).
-template <bool EMIT, bool PACKED = false, class SM, class MatFn, class FacesFn>
+template <bool EMIT, bool PACKED = false, bool MATS_SMEM = false, class SM, class MatFn, class FacesFn>
 __device__ __forceinline__ uint32_t mesh_tile(SM& sm, const MatFn& mat, const FacesFn& faces, int bx, int by, int bz,
                                               const MaterialsDev* __restrict__ mats, float* __restrict__ out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -339,7 +341,7 @@ __device__ __forceinline__ uint32_t mesh_tile(SM& sm, const MatFn& mat, const Fa
             const uint32_t L = d & 0x7FFFu, f = d >> 15;
             uint32_t ao = 0;
             if ((uint32_t)lane < nw) ao = ao_bits(sm.occ, sm.ao_tab[f], L >> 10, L & 31, (L >> 5) & 31);
-            emit_window(sm, mats, ws, ws_shared, out_bytes + (d0 + q0) * 100u, nw, L, f, ao, id, bx, by, bz);  // < 2^24 B / chunk
+            emit_window<MATS_SMEM>(sm, mats, ws, ws_shared, out_bytes + (d0 + q0) * 100u, nw, L, f, ao, id, bx, by, bz);  // < 2^24 B / chunk
         }
         }  // !PACKED
         if (d0 + SM::kDesc < total) __syncthreads();  // descriptors are rewritten in the next round
@@ -724,6 +726,7 @@ struct IdsPipe {
 struct EmitIdsSmem {
     MeshSmem sm;
     IdsPipe pp;
+    MaterialsDev mats;
 };
 static_assert((sizeof(EmitIdsSmem) + 1024) * kCtasPerSm <= 228 * 1024, "k_emit_ids: shared memory per SM");
 
@@ -755,6 +758,8 @@ k_emit_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* const raw = reinterpret_cast<uint32_t*>(sm.hts);  // dy = 0 words of the tile being fetched (region kernels keep heights here)
     load_tables(sm, tb);
+    for (int i = tid; i < (int)(sizeof(MaterialsDev) / sizeof(uint32_t)); i += kT)
+        reinterpret_cast<uint32_t*>(&es.mats)[i] = __ldg(reinterpret_cast<const uint32_t*>(mats) + i);
     const uint32_t n_nz = __ldg(nz);
     const uint32_t* const list = nz + 1;
 
@@ -855,8 +860,8 @@ k_emit_ids(const MeshTables tb, const MaterialsDev* __restrict__ mats, const hb_
             if (tid == 0) atomicOr(total + 2, 1ULL);  // error path only
         } else {
             const hb_chunk_pt pt = it.pt;
-            mesh_tile<true>(sm, MatIds{ids + (size_t)it.chunk * HB_CHUNK_VOLUME}, FacesFromOcc{sm.occ}, pt.x * 32, pt.y * 32,
-                            pt.z * 32, mats, out + off * 25ULL);
+            mesh_tile<true, false, true>(sm, MatIds{ids + (size_t)it.chunk * HB_CHUNK_VOLUME}, FacesFromOcc{sm.occ}, pt.x * 32,
+                                         pt.y * 32, pt.z * 32, &es.mats, out + off * 25ULL);
         }
         cur ^= 1;
         // the next iteration's barrier (2) also fences this item's readers of sm.occ / item[cur ^ 1] against (1)..(3)

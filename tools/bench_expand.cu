@@ -63,5 +63,13 @@ int main(int argc, char** argv) {
         double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (rep) printf("%-24s threads %2d: %6.1f GB/s  (%.2f ns/quad/thread)\n", e.name, nthreads, bytes / dt / 1e9, dt * 1e9 * nthreads / ((double)nchunks * nq));
     }
+    // cached stores into a reused window of F MiB (does a cache-resident hand-over buffer beat the DRAM write path?)
+    for (int fmib : {4, 8, 16, 32, 64, 128}) for (int rep = 0; rep < 2; ++rep) {
+        const size_t ring = ((size_t)fmib << 20) / ((size_t)nq * 100);
+        auto t0 = std::chrono::steady_clock::now();
+        pool.run(nchunks, 8, [&](size_t i) { expand_cached(T, hb_chunk_pt{(int)i, -1, 3}, packed.data() + (i & 63) * nq, nq, (hb_instance3d*)A + (i % ring) * nq); });
+        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rep) printf("cached, %3d MiB window    threads %2d: %6.1f GB/s\n", fmib, nthreads, bytes / dt / 1e9);
+    }
     return 0;
 }
