@@ -521,7 +521,7 @@ def main():
                     "c3": {"workload": f"BASELINE config 3: meshing of {c3['chunks']} pre-generated chunks incl. cross-chunk borders",
                            "chunks_per_s": c3["chunks_per_s"], "quads": c3["quads"], "ms": c3["ms_total"],
                            "ms_pack_count_scan": c3["ms_pack_count_scan"], "ms_emit": c3["ms_emit"],
-                           "roofline": {"kernel": "k_pack + k_count_ids + scan + k_mesh_ids<EMIT> (whole config)", "bound": "hbm",
+                           "roofline": {"kernel": "k_pack + k_count_border + scan + k_emit_ids (whole config)", "bound": "hbm",
                                         "achieved": c3["algorithmic_GBs"], "peak": peak, "unit": "GB/s", "frac": c3["algorithmic_GBs"] / peak,
                                         "algorithmic_bytes": c3["algorithmic_bytes"],
                                         "emit_gbs": c3["quads"] * 100 / (c3["ms_emit"] * 1e-3) / 1e9,
