@@ -188,3 +188,27 @@ def test_noise_kernel_has_no_unintended_fma_contraction():
     # (reference: no FMAs there except ridge_3d's neg_mul_add, functions/ridge_32.rs:43)
     n3 = [f for f in funcs if "k_noise3d" in f.split("\n", 1)[0]]
     assert n3 and len(re.findall(r"\bFFMA\b", n3[0])) == 1
+
+
+def test_mesher_kernels_use_the_hardware_paths_the_design_claims():
+    """k_pack tests ids with the DPX packed 16-bit min/max (VIMNMX3.U16x2), k_emit_ids fetches the next
+    chunk's occupancy words with cp.async (LDGSTS) and both emit kernels write their records with TMA bulk stores
+    (UBLKCP).  Pinned in the shipped SASS so a refactor cannot silently fall back to the slow forms."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.check_output(["cuobjdump", "-sass", _lib.LIB_PATH], text=True)
+    funcs = {f.split("\n", 1)[0]: f for f in re.split(r"\n\s*Function : ", sass)[1:]}
+
+    def one(pred):
+        hits = [body for name, body in funcs.items() if pred(name)]
+        assert hits, "kernel not found in the library"
+        return hits
+
+    pack = one(lambda n: re.search(r"\d+k_packE", n))[0]
+    assert len(re.findall(r"VIMNMX3\.U16x2", pack)) >= 6 * 16  # 6 per 8-id unit, 16 units per thread
+    emit = one(lambda n: "k_emit_ids" in n)[0]
+    assert "LDGSTS" in emit and "UBLKCP" in emit
+    for body in one(lambda n: "k_mesh_region" in n and "Lb1ELb0E" in n):  # EMIT, 100-byte records
+        assert "UBLKCP" in body
+    assert one(lambda n: "k_count_border" in n)
