@@ -325,7 +325,8 @@ HB_API int hb_dev_download(hb_ctx *ctx, void *host_dst, const void *dev_src, siz
 HB_API int hb_dev_generate(hb_ctx *ctx, void *stream, const int32_t *d_cols_xz, size_t ncol,
                     const hb_chunk_pt *d_pts, const int32_t *d_col_of_chunk, size_t n,
                     int32_t *d_heights, float *d_noise, uint16_t *d_ids, hb_palette_cube *d_cubes);
-/* hb_dev_mesh: d_workspace of hb_dev_mesh_workspace_bytes(n) bytes.  d_total[0] = span (instances),
+/* hb_dev_mesh: d_workspace of hb_dev_mesh_workspace_bytes(n) bytes (about 5.1 KiB per chunk: occupancy bitmaps, border
+ * records, scan scratch and the emit work list; contents are scratch between calls).  d_total[0] = span (instances),
  * d_total[1] = quads, d_total[2] = error flags (1 = capacity exceeded, 2 = unknown material id), d_total[3] = scratch
  * (the emit kernel's work-ticket counter); d_total is 4 x u64. */
 HB_API size_t hb_dev_mesh_workspace_bytes(size_t n);
