@@ -544,6 +544,25 @@ int hb_world_load(hb_world* w, const hb_chunk_pt* pts, size_t n) {
         w->slot_pt[slots[i]] = fresh[i];
         w->used[slots[i]] = 1;
     }
+    // Device side in two halves with the host's neighbour bookkeeping in between, so that the generator kernels
+    // (heights + fill: they need only the new chunks' positions and slots) run while the host wires the 27-shells and
+    // collects the cull pairs.  If anything fails the host mirror is taken back to where it was, so no chunk is left
+    // "loaded" with cubes that were never written (neighbours a failed cull may have touched keep valid, if stale,
+    // flags; a CUDA error at this point is sticky for the context anyway).  Un-wiring a chunk that was never wired
+    // only rewrites -1 entries, so the rollback below is the same wherever the failure happened.
+    auto generate = [&]() -> int {
+        int rc;
+        if ((rc = upload(s, w->d_a, cols.data(), cols.size() * sizeof(int32_t))) != HB_OK) return rc;
+        if ((rc = upload(s, w->d_b, colidx.data(), m * sizeof(int32_t))) != HB_OK) return rc;
+        if ((rc = upload(s, w->d_c, fresh.data(), m * sizeof(hb_chunk_pt))) != HB_OK) return rc;
+        if ((rc = upload(s, w->d_d, slots.data(), m * sizeof(int32_t))) != HB_OK) return rc;
+        HB_CUDA(w->d_heights.reserve(ncol * HB_CHUNK_AREA * sizeof(int32_t)));
+        HB_CUDA(launch_heights(s, c->world, w->d_a.as<int32_t>(), ncol, w->d_heights.as<int32_t>(), nullptr));
+        HB_CUDA(launch_fill_world(s, w->d_c.as<hb_chunk_pt>(), w->d_b.as<int32_t>(), m, w->d_heights.as<int32_t>(),
+                                  w->d_cubes.as<hb_palette_cube>(), w->d_d.as<int32_t>(), w->d_touched.as<uint32_t>()));
+        return HB_OK;
+    };
+    int rc = generate();
     for (size_t i = 0; i < m; ++i) wire_neighbours(w, fresh[i], slots[i], true);
     // load_provided (map.rs:203-228): one cull per (new chunk, loaded face neighbour); a pair of two new chunks once
     std::vector<CullPair> pairs;
@@ -556,21 +575,10 @@ int hb_world_load(hb_world* w, const hb_chunk_pt* pts, size_t n) {
             w->stale[o] = w->touched[o] = 1;
         }
     }
-    // device side; if anything here fails the host mirror is taken back to where it was, so no chunk is left
-    // "loaded" with cubes that were never written (neighbours a failed cull may have touched keep valid, if stale,
-    // flags; a CUDA error at this point is sticky for the context anyway)
-    auto device_side = [&]() -> int {
-        int rc;
-        if ((rc = upload(s, w->d_a, cols.data(), cols.size() * sizeof(int32_t))) != HB_OK) return rc;
-        if ((rc = upload(s, w->d_b, colidx.data(), m * sizeof(int32_t))) != HB_OK) return rc;
-        if ((rc = upload(s, w->d_c, fresh.data(), m * sizeof(hb_chunk_pt))) != HB_OK) return rc;
-        if ((rc = upload(s, w->d_d, slots.data(), m * sizeof(int32_t))) != HB_OK) return rc;
-        HB_CUDA(w->d_heights.reserve(ncol * HB_CHUNK_AREA * sizeof(int32_t)));
-        HB_CUDA(launch_heights(s, c->world, w->d_a.as<int32_t>(), ncol, w->d_heights.as<int32_t>(), nullptr));
-        HB_CUDA(launch_fill_world(s, w->d_c.as<hb_chunk_pt>(), w->d_b.as<int32_t>(), m, w->d_heights.as<int32_t>(),
-                                  w->d_cubes.as<hb_palette_cube>(), w->d_d.as<int32_t>(), w->d_touched.as<uint32_t>()));
+    auto cull = [&]() -> int {
         if (!pairs.empty()) {
-            if ((rc = upload(s, w->d_a, pairs.data(), pairs.size() * sizeof(CullPair))) != HB_OK) return rc;
+            const int rc2 = upload(s, w->d_a, pairs.data(), pairs.size() * sizeof(CullPair));  // stream-ordered after the heights kernel's reads of d_a
+            if (rc2 != HB_OK) return rc2;
             k_world_cull<<<(unsigned)pairs.size(), kWT, 0, s>>>(w->d_cubes.as<hb_palette_cube>(), w->d_touched.as<uint32_t>(),
                                                                 w->d_a.as<CullPair>());
             HB_CUDA(cudaGetLastError());
@@ -578,7 +586,8 @@ int hb_world_load(hb_world* w, const hb_chunk_pt* pts, size_t n) {
         HB_CUDA(cudaStreamSynchronize(s));
         return HB_OK;
     };
-    const int rc = device_side();
+    if (rc == HB_OK) rc = cull();
+    else cudaStreamSynchronize(s);
     if (rc != HB_OK) {
         for (size_t i = m; i-- > 0;) {
             w->map.erase(fresh[i].x, fresh[i].y, fresh[i].z);
