@@ -563,16 +563,50 @@ int hb_world_load(hb_world* w, const hb_chunk_pt* pts, size_t n) {
         return HB_OK;
     };
     int rc = generate();
-    for (size_t i = 0; i < m; ++i) wire_neighbours(w, fresh[i], slots[i], true);
-    // load_provided (map.rs:203-228): one cull per (new chunk, loaded face neighbour); a pair of two new chunks once
+    // Neighbour rows and cull pairs, one new chunk per work item on the context's host threads.  Every new chunk is
+    // already in the table, so the entry two new neighbours have for each other comes from each one's own lookup;
+    // back-pointers are written only into the rows of chunks that were loaded before, at the entry that faces this
+    // chunk -- no two items write the same word.  load_provided (map.rs:203-228): one cull per (new chunk, loaded
+    // face neighbour); a pair of two new chunks once.
+    std::vector<CullPair> pair_buf(m * 6);
+    std::vector<uint8_t> pair_cnt(m, 0);
+    auto wire_one = [&](size_t i) {
+        const hb_chunk_pt p = fresh[i];
+        const int32_t slot = slots[i];
+        int32_t* row = &w->h_nbr[(size_t)slot * 27];
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dz = -1; dz <= 1; ++dz) {
+                    const int o = (dx || dy || dz) ? w->find(p.x + dx, p.y + dy, p.z + dz) : slot;
+                    row[shell_index(dx, dy, dz)] = o;
+                    if (o >= 0 && o != slot && !is_new[o]) w->h_nbr[(size_t)o * 27 + shell_index(-dx, -dy, -dz)] = slot;
+                }
+        int k = 0;
+        for (int f = 0; f < 6; ++f) {
+            const int o = row[shell_index(kNormal[f][0], kNormal[f][1], kNormal[f][2])];
+            if (o < 0 || (is_new[o] && o < slot)) continue;
+            pair_buf[i * 6 + k++] = CullPair{slot, o, f, 0};
+        }
+        pair_cnt[i] = (uint8_t)k;
+    };
+    if (m >= 1024) {
+        if (c->host_threads == 0) {
+            c->host_threads = default_host_threads();
+            c->pool.resize(c->host_threads);
+        }
+        c->pool.run(m, 64, wire_one);
+    } else {
+        for (size_t i = 0; i < m; ++i) wire_one(i);
+    }
+    w->tables_dirty = true;
     std::vector<CullPair> pairs;
+    pairs.reserve(m * 3);
     for (size_t i = 0; i < m; ++i) {
         w->stale[slots[i]] = w->touched[slots[i]] = 1;
-        for (int f = 0; f < 6; ++f) {
-            const int o = w->find(fresh[i].x + kNormal[f][0], fresh[i].y + kNormal[f][1], fresh[i].z + kNormal[f][2]);
-            if (o < 0 || (is_new[o] && o < slots[i])) continue;
-            pairs.push_back(CullPair{slots[i], o, f, 0});
-            w->stale[o] = w->touched[o] = 1;
+        for (int k = 0; k < pair_cnt[i]; ++k) {
+            const CullPair& cp = pair_buf[i * 6 + k];
+            pairs.push_back(cp);
+            w->stale[cp.b] = w->touched[cp.b] = 1;
         }
     }
     auto cull = [&]() -> int {
