@@ -361,7 +361,8 @@ HB_API size_t hb_world_len(const hb_world *world);          /* chunks currently 
  * server/src/generator/mod.rs:32-95): generates every not-yet-loaded chunk of pts[0..n) straight into its slot
  * (PaletteCube image as CubeMesh::set leaves it), then runs cull_shared_faces (server/src/chunk/mesh.rs:76-123)
  * for every (new chunk, loaded face neighbour) pair.  Already-loaded and repeated positions are ignored, as
- * queue_load does.  HB_ERR_CAPACITY (nothing changed) if the free slots do not suffice. */
+ * queue_load does.  HB_ERR_CAPACITY (nothing changed) if the free slots do not suffice.  Batches of 1024 or more
+ * new chunks wire their neighbour rows on the context's host threads (hb_set_host_threads). */
 HB_API int hb_world_load(hb_world *world, const hb_chunk_pt *pts, size_t n);
 /* ChunkMap::unload_requested (map.rs:230-235): the slot is freed; neighbours keep whatever faces the earlier
  * cull removed, exactly as the reference leaves them. */
